@@ -1,0 +1,175 @@
+/* vp_engine.h -- C ABI of the B200 batch engine for VocoderProject's DSP core.
+ *
+ * Drop-in boundary for the path VocoderAudioProcessor::processBlock drives
+ * (reference: Source/PluginProcessor.cpp:203-234) -- MyBuffer ring buffering,
+ * LPC, VocoderProcess, PitchProcess, Notes -- batched over independent
+ * streams. Plain pointers and sizes only; no C++/CUDA/torch types. The C++
+ * facade with the reference's class names lives in
+ * vocoderproject_b200/csrc/vp_facade.hpp and is implemented on top of this
+ * ABI; INTEGRATION.md shows the PluginProcessor-side binding.
+ *
+ * Semantics. One "stream" is one plug-in instance (1 mono voice + stereo
+ * side-chain in, stereo out). vp_engine_process* is equivalent, per stream,
+ * to: construct the plug-in, set the parameters, prepareToPlay(sampleRate,
+ * samplesPerBlock), then nBlocks consecutive processBlock calls. Results do
+ * depend (sparsely) on samplesPerBlock exactly as in the reference (whole-ring
+ * RMS gate, MyBuffer.cpp:258-261; PSOLA look-ahead test, PitchProcess.cpp:
+ * 799-803), hence the "virtual block size" argument of vp_engine_prepare.
+ *
+ * All functions return VP_OK (0) or a negative VP_E_* code; none throws, none
+ * aborts. There is no CPU fallback: without a usable CUDA device every
+ * compute entry point returns VP_E_CUDA.
+ */
+#ifndef VP_ENGINE_H
+#define VP_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_OK 0
+#define VP_E_ARG (-1)     /* bad argument */
+#define VP_E_STATE (-2)   /* call order (e.g. process before prepare) */
+#define VP_E_CUDA (-3)    /* CUDA runtime error / no device; see vp_last_error */
+#define VP_E_NOMEM (-4)   /* device or host allocation failed */
+#define VP_E_RANGE (-5)   /* parameter outside the plug-in's range */
+
+/* The ten plug-in parameters (Source/PluginProcessor.cpp:37-73), pushed by
+ * the caller instead of pulled through audioProcPtr->treeState. Gains in dB
+ * as float, exactly what the plug-in's std::atomic<float> holds. */
+typedef struct vp_params {
+    float gainPitch; /* [-60, 6]  default 0    PitchProcess.cpp:336 */
+    float gainVoice; /* [-60, 6]  default -60  PluginProcessor.cpp:226 (dry voice, off <= -59) */
+    float gainSynth; /* [-60, 6]  default -60  PluginProcessor.cpp:229 (dry synth, off <= -59) */
+    float gainVoc;   /* [-60, 6]  default 0    VocoderProcess.cpp:291 */
+    int lpcVoice;    /* [2, 100]  default 40   VocoderProcess.cpp:139 */
+    int lpcPitch;    /* [2, 100]  default 15   PitchProcess.cpp:70 (read in prepare only) */
+    int lpcSynth;    /* [2, 30]   default 5    VocoderProcess.cpp:155 */
+    int keyPitch;    /* Notes::key 0..12 (A..G#, 12 = chromatic), default 12; Notes.h:26 */
+    int pitchBool;   /* default 1 */
+    int vocBool;     /* default 1 */
+} vp_params;
+
+/* Sizes prepareToPlay derives from the sample rate
+ * (PluginProcessor.cpp:160-176, PitchProcess.cpp:100-107, MyBuffer.cpp:46-48). */
+typedef struct vp_sizes {
+    int hopV, wlenV;           /* vocoder hop / frame length */
+    int hopP, frameLenP, chunk;/* pitch hop / frame length / chunk */
+    int tauMin, tauMax;        /* YIN lag search range [tauMin, tauMax) */
+    int latency, keep;         /* plug-in latency, samplesToKeep */
+    int inSize, outSize;       /* MyBuffer ring lengths for this block size */
+    int anCap;                 /* capacity of the pitch-mark vectors */
+    int nFreq;                 /* entries in the note table for keyPitch */
+} vp_sizes;
+
+/* Per pitch frame decisions (one record per processChunkStart call,
+ * PitchProcess.cpp:203-247). */
+#define VP_MAX_MARKS 24
+#define VP_PF_GATED 1u       /* silence gate fired (PitchProcess.cpp:208-214) */
+#define VP_PF_VOICED 2u      /* pitch > 1 */
+#define VP_PF_HAS_MARKS 4u   /* anMarks non-empty -> frame is synthesised */
+#define VP_PF_NEAR_GATE 16u      /* gate level within eps of -60 dB */
+#define VP_PF_NEAR_YIN 32u       /* a deciding YIN comparison within eps (after the FP64 re-check) */
+#define VP_PF_UB 64u             /* the reference has undefined behaviour here */
+#define VP_PF_YIN_RECHECKED 128u /* FP32 YIN was inconclusive; decided by the FP64 pass */
+typedef struct vp_pitch_frame {
+    uint32_t flags;
+    int32_t period;           /* detected period in samples (0 = unvoiced) */
+    int32_t periodPsola;      /* period else prevVoicedPeriod (PitchProcess.cpp:669-672) */
+    int32_t periodNew;        /* synthesis mark spacing */
+    int32_t note;             /* snapped note index in the key's table, -1 if none */
+    int32_t nAn, nSt;
+    int32_t anStale;          /* storage slot anMarks[nAn] (PitchProcess.cpp:818) */
+    int32_t nAnOv;
+    int32_t anMarks[VP_MAX_MARKS];
+    int32_t stMarks[VP_MAX_MARKS];
+    double beta;              /* closestFreq / pitch, carried over unvoiced frames */
+} vp_pitch_frame;
+
+typedef struct vp_engine vp_engine;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+void vp_default_params(vp_params* p);
+/* Host-only helper: the sizes prepareToPlay would derive. */
+int vp_sizes_for(double sampleRate, int samplesPerBlock, int keyPitch, vp_sizes* out);
+/* Number of visible CUDA devices (0 when there is none). */
+int vp_device_count(void);
+
+int vp_engine_create(vp_engine** e, int device);
+void vp_engine_destroy(vp_engine* e);
+const char* vp_last_error(const vp_engine* e);
+
+/* prepareToPlay(sampleRate, samplesPerBlock) for nStreams independent
+ * plug-in instances. maxBlocks bounds nBlocks of later process calls.
+ * workspaceBytes: device memory the engine may use for intermediates
+ * (0 = default); it decides how many streams are in flight per pass. */
+int vp_engine_prepare(vp_engine* e, double sampleRate, int samplesPerBlock, int nStreams, int maxBlocks,
+                      size_t workspaceBytes);
+int vp_engine_set_params(vp_engine* e, const vp_params* p);
+int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out);
+
+/* ---- processing ----------------------------------------------------------- */
+/* Device-resident batch. Layouts (row stride = strideSamples floats):
+ *   voice  [nStreams][stride]   synthL, synthR [nStreams][stride]
+ *   outL, outR [nStreams][stride]
+ * synthR may be NULL when gainSynth <= -59 dB (the vocoder analyses channel 0
+ * only, VocoderProcess.cpp:211,218). outR may be NULL (then only L is written;
+ * L == R whenever gainSynth <= -59 dB). Asynchronous on the engine's stream;
+ * vp_engine_sync waits. */
+int vp_engine_process_device(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
+                             const float* synthR, float* outL, float* outR, size_t strideSamples);
+
+/* Host buffers (pageable or pinned, see vp_host_alloc), same layouts. Streams
+ * are moved in slices with H2D / compute / D2H overlapped on three CUDA
+ * streams; returns when the outputs are in host memory. */
+int vp_engine_process_host(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
+                           const float* synthR, float* outL, float* outR, size_t strideSamples);
+
+int vp_engine_sync(vp_engine* e);
+
+/* Decisions of the most recent process call for one stream: up to cap
+ * records, *nFrames = frames available. */
+int vp_engine_get_pitch_frames(vp_engine* e, int stream, vp_pitch_frame* out, int cap, int* nFrames);
+/* Per vocoder frame of the most recent call: gate flag, excitation energies
+ * and gain (VocoderProcess.cpp:199-204, :264-272). Arrays may be NULL. */
+int vp_engine_get_voc_frames(vp_engine* e, int stream, int cap, int* nFrames, uint8_t* gated, double* EeVoice,
+                             double* EeSynth, double* g);
+
+/* Counters since prepare: kernels launched, frames re-decided in FP64. */
+int vp_engine_get_stats(const vp_engine* e, uint64_t* kernelLaunches, uint64_t* yinRechecked,
+                        uint64_t* yinFrames);
+/* Device time (ms) of the most recent process_device call, measured with
+ * CUDA events on the engine's stream; per-stage breakdown optional. */
+#define VP_NSTAGES 12
+int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageMs /* [VP_NSTAGES] or NULL */);
+const char* vp_stage_name(int stage);
+
+/* ---- memory helpers -------------------------------------------------------- */
+int vp_host_alloc(void** p, size_t bytes);   /* pinned host memory */
+void vp_host_free(void* p);
+int vp_device_alloc(vp_engine* e, void** p, size_t bytes);
+void vp_device_free(vp_engine* e, void* p);
+int vp_memcpy_h2d(vp_engine* e, void* dst, const void* src, size_t bytes);
+int vp_memcpy_d2h(vp_engine* e, void* dst, const void* src, size_t bytes);
+
+/* ---- synthetic inputs -------------------------------------- */
+/* flavour: 0 = breathy voice (-40 dBFS aspiration), 1 = clean (-80 dBFS),
+ * 2 = breathy with a silent stretch (exercises the gates). Streams are
+ * numbered firstStream.. so shards generate disjoint inputs. */
+int vp_synth_host(double sampleRate, int flavour, int firstStream, int nStreams, size_t nSamples,
+                  size_t strideSamples, float* voice, float* synthL, float* synthR);
+int vp_synth_device(vp_engine* e, double sampleRate, int flavour, int firstStream, int nStreams,
+                    size_t nSamples, size_t strideSamples, float* voice, float* synthL, float* synthR);
+
+/* ---- measurement helpers ---------------------------------------------------- */
+/* Issue-rate microbenchmarks on the engine's device: FP32 FMA and FP64 FMA
+ * lane-operations per second (the roofline denominators of DESIGN.md). */
+int vp_measure_peaks(vp_engine* e, double* fp32FmaPerSec, double* fp64FmaPerSec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP_ENGINE_H */

@@ -1,0 +1,49 @@
+"""Builds vocoderproject_b200/lib/libvp_engine.so in-tree with nvcc for sm_100a.
+No torch, no JIT cache: the .so travels with the repo snapshot."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libvp_engine.so")
+SOURCES = ["vp_engine.cu", "vp_voc.cu", "vp_pitch.cu", "vp_misc.cu"]
+HEADERS = ["vp_common.cuh", "vp_synth.h", os.path.join("..", "..", "include", "vp_engine.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc")
+    if p:
+        return p
+    p = "/usr/local/cuda/bin/nvcc"
+    if os.path.exists(p):
+        return p
+    raise RuntimeError("nvcc not found: the engine has no CPU fallback and cannot be built without CUDA")
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES + HEADERS:
+        if os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return False
+
+
+def build(force=False, verbose=False):
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

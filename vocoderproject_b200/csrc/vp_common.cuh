@@ -1,0 +1,92 @@
+// Shared definitions for the sm_100a kernels and the engine host code.
+// Timeline convention: everything is indexed on the
+// *delayed timeline* u = input time + latency. Output sample u of a stream is
+// the sum of all frame contributions at delayed position u; input before time
+// 0 is zero (MyBuffer.cpp:56-58 clears the rings).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vp_engine.h"
+
+#define VP_ORDER_MAX 100  // PluginProcessor.cpp:53-59 (parameter range ends)
+#define VP_SLOTS 32       // >= anCap (20 at 44.1/48 kHz); one warp lane per storage slot
+
+// Geometry + parameters of one prepared engine, passed by value to kernels.
+struct VPGeom {
+    double fs;
+    int B, hopV, wlenV, hopP, L, c, tauMin, tauMax, lat, keep, inSize, anCap;
+    int nBlocks;       // blocks in this call
+    long long n;       // nBlocks * B samples per stream
+    long long stride;  // row stride of the I/O arrays (floats)
+    long long wstride; // row stride of the engine's own per-sample intermediates (outV, outP)
+    int nFramesV;      // vocoder frames with start < n   (VocoderProcess.cpp:176)
+    int nFramesP;      // pitch frames with start < n     (PitchProcess.cpp:169)
+    int ordV, ordS, ordP;
+    float gainVocF, gainPitchF, gainVoiceF, gainSynthF;  // decibelsToGain<float>(dB, -59)
+    int vocOn, pitchOn, dryOn, synthOn;
+    double yinEps;  // relative margin below which the FP32 YIN decision is re-done in FP64
+};
+
+// gate flags per (stream, block)
+#define VP_GATE_VOICE 1
+#define VP_GATE_SYNTH 2
+#define VP_GATE_NEAR 4
+
+// Voice / synth sample at delayed position u of a stream row (MyBuffer.cpp:142-172).
+__device__ __forceinline__ float vp_x(const float* __restrict__ row, long long u, int lat, long long n) {
+    long long t = u - lat;
+    return (t >= 0 && t < n) ? __ldg(row + t) : 0.0f;
+}
+
+__device__ __forceinline__ double vp_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#define VP_CUDA_OK(call)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return vp_fail(e, _e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- kernel launchers (one per .cu file) -------------------------------------
+struct VPTables {
+    const double* wV;        // vocoder sine window [wlenV]            VocoderProcess.cpp:125-130
+    const double* stP;       // pitch synthesis window [L]             PitchProcess.cpp:889-905
+    const double* hann;      // PSOLA Hann tables, all T               PitchProcess.cpp:878-882
+    const int* hannOff;      // offset of table T in hann[], [tauMax+1]
+    const double* lutBeta;   // per period: closestFreq / pitch        PitchProcess.cpp:594-596
+    const int* lutPeriodNew; // per period: round(period / beta)
+    const int* lutNote;      // per period: snapped note index         Notes.cpp:79-110
+};
+
+void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate);
+
+void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                            const float* synth, const uint8_t* gate, double* rV, double* rS);
+void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                            const float* synth, const uint8_t* gate, const double* rV, const double* rS, double* aV,
+                            double* aS, double* EeV, double* EeS);
+void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
+                         const uint8_t* gate, const double* aV, const double* aS, const double* EeV,
+                         const double* EeS, double* gOut, float* outV);
+
+void vp_launch_yin(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
+                   uint32_t* yflags, int* recheckList, int* recheckCount, int maxList);
+void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
+                           uint32_t* yflags, const int* recheckList, const int* recheckCount, int maxList);
+void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                     const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames);
+void vp_launch_pitch_frame(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                           vp_pitch_frame* frames, double* aP, double* outE);
+void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const vp_pitch_frame* frames,
+                         const double* aP, const double* outE, float* outP);
+void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
+                   const float* synthR, const float* outV, const float* outP, float* outL, float* outR);
+
+void vp_launch_synth(cudaStream_t st, const void* streams, int nStreams, long long nSamples, long long stride,
+                     float* voice, float* synthL, float* synthR);
+void vp_launch_peak_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads);
+void vp_launch_peak_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads);

@@ -1,0 +1,809 @@
+// Engine host code + C ABI (include/vp_engine.h). Plain C++ over the CUDA
+// runtime; no PyTorch, no NCCL (streams are independent: SURVEY.md 8(e)).
+// The reference-side meaning of each entry point is documented in the header.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "vp_common.cuh"
+#include "vp_synth.h"
+
+enum { ST_GATE = 0, ST_VOC_AC, ST_VOC_LEV, ST_VOC_SYN, ST_YIN, ST_YIN64, ST_MARKS, ST_PFRAME, ST_PIIR, ST_MIX, ST_CLEAR, ST_OTHER };
+static const char* kStageNames[VP_NSTAGES] = {"gate", "voc_autocorr", "voc_levinson", "voc_synth", "yin_fp32", "yin_fp64_recheck",
+                                              "marks", "pitch_frame", "pitch_iir", "mix", "clear", "other"};
+
+struct vp_engine {
+    int device = 0;
+    bool prepared = false;
+    cudaStream_t st = nullptr, stIn = nullptr, stOut = nullptr;
+    std::string err;
+    vp_params prm;
+    vp_sizes sz;
+    double fs = 0;
+    int B = 0, S = 0, maxBlocks = 0;
+    int Sc = 0;  // streams per pass
+    size_t workspace = 0;
+    VPGeom geom;
+    // tables (device)
+    double *dWV = nullptr, *dStP = nullptr, *dHann = nullptr, *dLutBeta = nullptr;
+    int *dHannOff = nullptr, *dLutPeriodNew = nullptr, *dLutNote = nullptr;
+    int lutKey = -1;
+    // workspace (device), sized for Sc streams x maxBlocks
+    uint8_t* dGate = nullptr;
+    double *dRV = nullptr, *dRS = nullptr, *dAV = nullptr, *dAS = nullptr, *dEeV = nullptr, *dEeS = nullptr, *dG = nullptr;
+    int *dPeriod = nullptr, *dList = nullptr, *dListCount = nullptr;
+    uint32_t* dYFlags = nullptr;
+    vp_pitch_frame* dFrames = nullptr;
+    double *dAP = nullptr, *dOutE = nullptr;
+    float *dOutV = nullptr, *dOutP = nullptr;
+    int maxList = 0;
+    // decisions kept for the whole batch (all S streams) of the last call
+    vp_pitch_frame* dFramesAll = nullptr;
+    uint8_t* dGateAll = nullptr;
+    double *dEeVAll = nullptr, *dEeSAll = nullptr, *dGAll = nullptr;
+    bool keepDecisions = true;
+    int lastBlocks = 0;
+    // host-path staging (device), 3 slices
+    int Sh = 0;
+    float* hIn[3][3] = {{nullptr}};
+    float* hOut[3][2] = {{nullptr}};
+    cudaEvent_t evIn[3] = {nullptr}, evComp[3] = {nullptr}, evOut[3] = {nullptr};
+    // stats / timing
+    uint64_t launches = 0, yinRechecked = 0, yinFrames = 0;
+    int passCount = 0;      // passes of the current call
+    int capV = 0, capS = 0, capP = 0;  // LPC orders the workspace was sized for
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> evStage;
+    size_t evUsed = 0;
+    cudaEvent_t evT0 = nullptr, evT1 = nullptr;
+    bool stageTiming = false;
+};
+
+static int vp_fail(vp_engine* e, cudaError_t ce, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)ce, cudaGetErrorString(ce), file, line, what);
+    if (e) e->err = buf;
+    return ce == cudaErrorMemoryAllocation ? VP_E_NOMEM : VP_E_CUDA;
+}
+static int vp_err(vp_engine* e, int code, const char* msg) {
+    if (e) e->err = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------
+// Host-side restatement of the sizes and tables the reference derives in
+// prepareToPlay / prepare (PluginProcessor.cpp:160-176, PitchProcess.cpp:62-128,
+// VocoderProcess.cpp:95-135, Notes.cpp:43-110).
+// ---------------------------------------------------------------------------
+static const double kPiVoc = 3.14159265;              // VocoderProcess.cpp:13
+static const double kPi = 3.14159265358979323846;     // juce::MathConstants<double>::pi
+
+static int notes_table(int key, double fMin, double fMax, double* freq /* [128] */) {
+    static const int intervals[7] = {2, 2, 1, 2, 2, 2, 1};
+    int n = 0, i = 0;
+    double f = 27.5;
+    f = f * pow(2, (double)key / 12.0);
+    const double semi = pow(2, 1.0 / 12);
+    while (n == 0 || freq[n - 1] < fMax) {
+        if (key != 12) f = f * pow(semi, intervals[i % 7]);
+        else f = f * semi;
+        if (f > fMin && n < 127) freq[n++] = f;
+        i += 1;
+    }
+    return n - 1;  // pop_back(); freq[n-1] keeps the popped value (Notes.cpp:69)
+}
+
+extern "C" void vp_default_params(vp_params* p) {
+    if (!p) return;
+    p->gainPitch = 0.f; p->gainVoice = -60.f; p->gainSynth = -60.f; p->gainVoc = 0.f;
+    p->lpcVoice = 40; p->lpcPitch = 15; p->lpcSynth = 5; p->keyPitch = 12; p->pitchBool = 1; p->vocBool = 1;
+}
+
+extern "C" int vp_sizes_for(double fs, int B, int keyPitch, vp_sizes* s) {
+    if (!s || !(fs >= 8000.0) || fs > 400000.0 || B <= 0 || keyPitch < 0 || keyPitch > 12) return VP_E_ARG;
+    const double ratio = fs / 44100.0;
+    s->hopV = (int)floor(128.0 * ratio);
+    s->wlenV = 4 * s->hopV;
+    const int c256 = (int)floor(256.0 * ratio);
+    s->hopP = 3 * c256;
+    s->frameLenP = 4 * c256;
+    s->chunk = s->frameLenP - s->hopP;
+    s->tauMin = (int)floor(fs / 800.0);
+    s->tauMax = (int)ceil(fs / 100.0);
+    s->latency = std::max(s->frameLenP, s->wlenV);
+    s->keep = s->frameLenP;
+    s->inSize = s->keep + B + s->latency;
+    s->outSize = B + s->latency;
+    s->anCap = (int)ceil(s->frameLenP * 800.0 / fs) + 1;
+    double freq[128];
+    s->nFreq = notes_table(keyPitch, 100.0, 800.0, freq);
+    return VP_OK;
+}
+
+extern "C" int vp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static float db_to_gain(float db) { return db > -59.0f ? powf(10.0f, db * 0.05f) : 0.0f; }
+
+template <typename T>
+static int upload(vp_engine* e, T** dst, const std::vector<T>& src) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    VP_CUDA_OK(cudaMalloc((void**)dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
+    VP_CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return VP_OK;
+}
+
+static int build_note_lut(vp_engine* e) {
+    // closestFreq / beta / periodNew / note are pure functions of (period, key):
+    // pitch = fS / tau (PitchProcess.cpp:441), Notes::getClosestFreq (Notes.cpp:79-110),
+    // beta = closestFreq / pitch, periodNew = round(period / beta) (PitchProcess.cpp:594-596).
+    double freq[128];
+    const int nf = notes_table(e->prm.keyPitch, 100.0, 800.0, freq);
+    const int tauMax = e->sz.tauMax;
+    std::vector<double> beta(tauMax + 1, 1.0);
+    std::vector<int> pnew(tauMax + 1, 0), note(tauMax + 1, -1);
+    for (int tau = 1; tau <= tauMax; ++tau) {
+        const double pitch = e->fs / tau;
+        const int idx = (int)(std::lower_bound(freq, freq + nf, pitch) - freq);
+        int pick;
+        if (idx > 0) pick = (fabs(freq[idx] - pitch) <= fabs(freq[idx - 1] - pitch)) ? idx : idx - 1;  // idx == nf reads the popped slot
+        else pick = idx;
+        const double closest = freq[pick];
+        beta[tau] = closest / pitch;
+        pnew[tau] = (int)round(tau / beta[tau]);
+        note[tau] = pick;
+    }
+    int rc;
+    if ((rc = upload(e, &e->dLutBeta, beta))) return rc;
+    if ((rc = upload(e, &e->dLutPeriodNew, pnew))) return rc;
+    if ((rc = upload(e, &e->dLutNote, note))) return rc;
+    e->lutKey = e->prm.keyPitch;
+    e->sz.nFreq = nf;
+    return VP_OK;
+}
+
+static int build_tables(vp_engine* e) {
+    const vp_sizes& z = e->sz;
+    std::vector<double> wV(z.wlenV), stP(z.frameLenP, 1.0);
+    {
+        const double overlap = (double)(z.wlenV - z.hopV) / (double)z.wlenV;
+        double factor = 1.0;
+        if (fabs(overlap - 0.75) < pow(10, -10)) factor = 1.0 / sqrt(2);
+        for (int i = 0; i < z.wlenV; ++i) wV[i] = factor * sin((i + 0.5) * kPiVoc / (double)z.wlenV);
+    }
+    {
+        const double overlap = ((double)(z.frameLenP - z.hopP)) / ((double)z.frameLenP);
+        const int h = (int)round(overlap * z.frameLenP);
+        for (int i = 0; i < 2 * h; ++i) {
+            const double w = 0.5 - 0.5 * cos((double)(2 * i) * kPi / (double)(2 * h - 1));
+            if (i < h) stP[i] = w;
+            else stP[z.frameLenP - 2 * h + i] = w;
+        }
+    }
+    std::vector<int> off(z.tauMax + 2, 0);
+    size_t tot = 0;
+    for (int T = 0; T <= z.tauMax; ++T) { off[T] = (int)tot; tot += (size_t)(2 * T + 1); }
+    std::vector<double> hann(tot);
+    for (int T = 1; T <= z.tauMax; ++T) {
+        double* h = hann.data() + off[T];
+        const int len = 2 * T + 1;
+        for (int i = 0; i < len; ++i) h[i] = 0.5 - 0.5 * cos((double)(2 * i) * kPi / (double)(len - 1));
+    }
+    int rc;
+    if ((rc = upload(e, &e->dWV, wV))) return rc;
+    if ((rc = upload(e, &e->dStP, stP))) return rc;
+    if ((rc = upload(e, &e->dHann, hann))) return rc;
+    if ((rc = upload(e, &e->dHannOff, off))) return rc;
+    return build_note_lut(e);
+}
+
+static void free_workspace(vp_engine* e) {
+    void** ptrs[] = {(void**)&e->dGate, (void**)&e->dRV, (void**)&e->dRS, (void**)&e->dAV, (void**)&e->dAS, (void**)&e->dEeV,
+                     (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
+                     (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
+                     (void**)&e->dOutP, (void**)&e->dFramesAll, (void**)&e->dGateAll, (void**)&e->dEeVAll, (void**)&e->dEeSAll,
+                     (void**)&e->dGAll};
+    for (void** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) if (e->hIn[i][j]) { cudaFree(e->hIn[i][j]); e->hIn[i][j] = nullptr; }
+        for (int j = 0; j < 2; ++j) if (e->hOut[i][j]) { cudaFree(e->hOut[i][j]); e->hOut[i][j] = nullptr; }
+    }
+    e->Sh = 0;
+}
+
+extern "C" int vp_engine_create(vp_engine** out, int device) {
+    if (!out) return VP_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return VP_E_CUDA; }
+    if (device < 0 || device >= n) return VP_E_ARG;
+    vp_engine* e = new vp_engine();
+    e->device = device;
+    vp_default_params(&e->prm);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stIn, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stOut, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->evT0) != cudaSuccess || cudaEventCreate(&e->evT1) != cudaSuccess) {
+        cudaGetLastError();
+        delete e;
+        return VP_E_CUDA;
+    }
+    for (int i = 0; i < 3; ++i) {
+        cudaEventCreateWithFlags(&e->evIn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evComp[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
+    }
+    const char* pt = getenv("VP_STAGE_TIMING");
+    e->stageTiming = pt && pt[0] == '1';
+    *out = e;
+    return VP_OK;
+}
+
+extern "C" void vp_engine_destroy(vp_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    free_workspace(e);
+    void** t[] = {(void**)&e->dWV, (void**)&e->dStP, (void**)&e->dHann, (void**)&e->dHannOff, (void**)&e->dLutBeta,
+                  (void**)&e->dLutPeriodNew, (void**)&e->dLutNote};
+    for (void** p : t) if (*p) cudaFree(*p);
+    for (auto ev : e->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 3; ++i) { cudaEventDestroy(e->evIn[i]); cudaEventDestroy(e->evComp[i]); cudaEventDestroy(e->evOut[i]); }
+    cudaEventDestroy(e->evT0); cudaEventDestroy(e->evT1);
+    cudaStreamDestroy(e->st); cudaStreamDestroy(e->stIn); cudaStreamDestroy(e->stOut);
+    delete e;
+}
+
+extern "C" const char* vp_last_error(const vp_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+static int check_params(const vp_params* p) {
+    if (!p) return VP_E_ARG;
+    if (p->lpcVoice < 2 || p->lpcVoice > 100 || p->lpcPitch < 2 || p->lpcPitch > 100 || p->lpcSynth < 2 || p->lpcSynth > 30)
+        return VP_E_RANGE;
+    if (p->keyPitch < 0 || p->keyPitch > 12) return VP_E_RANGE;
+    const float gs[4] = {p->gainPitch, p->gainVoice, p->gainSynth, p->gainVoc};
+    for (float g : gs) if (!(g >= -60.0f && g <= 6.0f)) return VP_E_RANGE;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_set_params(vp_engine* e, const vp_params* p) {
+    if (!e) return VP_E_ARG;
+    int rc = check_params(p);
+    if (rc) return vp_err(e, rc, "parameter outside the plug-in's range");
+    const bool keyChanged = p->keyPitch != e->prm.keyPitch;
+    // LPC orders size the workspace; lpcPitch is read in prepare only in the reference too (PitchProcess.cpp:70)
+    if (e->prepared && (p->lpcVoice > e->capV || p->lpcSynth > e->capS || p->lpcPitch != e->capP))
+        return vp_err(e, VP_E_STATE, "LPC order beyond what vp_engine_prepare sized (lpcPitch is fixed at prepare): set params before prepare");
+    e->prm = *p;
+    if (e->prepared && (keyChanged || e->lutKey != p->keyPitch)) {
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->st);
+        return build_note_lut(e);
+    }
+    return VP_OK;
+}
+
+template <typename T>
+static int wsalloc(vp_engine* e, T** p, size_t count) {
+    VP_CUDA_OK(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return VP_OK;
+}
+
+static void frame_counts(const vp_sizes& z, long long n, int* nV, int* nP) {
+    *nV = (int)((n + z.hopV - 1) / z.hopV);
+    *nP = (int)((n + z.hopP - 1) / z.hopP);
+}
+
+extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxBlocks, size_t workspaceBytes) {
+    if (!e) return VP_E_ARG;
+    if (S <= 0 || maxBlocks <= 0 || B <= 0) return vp_err(e, VP_E_ARG, "nStreams, maxBlocks, samplesPerBlock must be > 0");
+    vp_sizes z;
+    if (vp_sizes_for(fs, B, e->prm.keyPitch, &z) != VP_OK) return vp_err(e, VP_E_ARG, "unsupported sample rate / block size");
+    if (z.anCap > VP_MAX_MARKS - 1 || z.tauMin < 2) return vp_err(e, VP_E_ARG, "sample rate outside the supported range");
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaDeviceSynchronize());
+    free_workspace(e);
+    e->prepared = false;
+    e->fs = fs; e->B = B; e->S = S; e->maxBlocks = maxBlocks; e->sz = z;
+    int rc = build_tables(e);
+    if (rc) return rc;
+    const long long n = (long long)maxBlocks * B;
+    int nV, nP;
+    frame_counts(z, n, &nV, &nP);
+    // bytes of intermediates per stream
+    const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(2 * (e->prm.lpcVoice + 1) + 2 * (e->prm.lpcSynth + 1) + 3) +
+                             (size_t)nP * (8 + sizeof(vp_pitch_frame) + 8 * (size_t)(e->prm.lpcPitch + 1) + 8 * (size_t)z.frameLenP) +
+                             (size_t)n * 8;
+    if (workspaceBytes == 0) workspaceBytes = (size_t)24 << 30;
+    long long Sc = (long long)(workspaceBytes / perStream);
+    if (Sc < 1) Sc = 1;
+    if (Sc > S) Sc = S;
+    if (Sc > 32) Sc &= ~31LL;
+    if (Sc > 65535) Sc = 65535 & ~31;
+    e->Sc = (int)Sc;
+    e->workspace = perStream * (size_t)Sc;
+    const size_t fV = (size_t)Sc * nV, fP = (size_t)Sc * nP;
+    if ((rc = wsalloc(e, &e->dGate, (size_t)Sc * maxBlocks))) return rc;
+    if ((rc = wsalloc(e, &e->dRV, fV * (e->prm.lpcVoice + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dRS, fV * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dAV, fV * (e->prm.lpcVoice + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dAS, fV * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dEeV, fV))) return rc;
+    if ((rc = wsalloc(e, &e->dEeS, fV))) return rc;
+    if ((rc = wsalloc(e, &e->dG, fV))) return rc;
+    if ((rc = wsalloc(e, &e->dPeriod, fP))) return rc;
+    if ((rc = wsalloc(e, &e->dYFlags, fP))) return rc;
+    e->maxList = (int)std::min<size_t>(fP, (size_t)1 << 22);
+    if ((rc = wsalloc(e, &e->dList, (size_t)e->maxList))) return rc;
+    if ((rc = wsalloc(e, &e->dListCount, 1024))) return rc;
+    VP_CUDA_OK(cudaMemset(e->dListCount, 0, 1024 * sizeof(int)));
+    if ((rc = wsalloc(e, &e->dFrames, fP))) return rc;
+    if ((rc = wsalloc(e, &e->dAP, fP * (e->prm.lpcPitch + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dOutE, fP * (size_t)z.frameLenP))) return rc;
+    if ((rc = wsalloc(e, &e->dOutV, (size_t)Sc * n))) return rc;
+    if ((rc = wsalloc(e, &e->dOutP, (size_t)Sc * n))) return rc;
+    // decisions for all streams (small): frames, gates, energies
+    const char* kd = getenv("VP_KEEP_DECISIONS");
+    e->keepDecisions = !(kd && kd[0] == '0');
+    if (e->keepDecisions) {
+        if ((rc = wsalloc(e, &e->dFramesAll, (size_t)S * nP))) return rc;
+        if ((rc = wsalloc(e, &e->dGateAll, (size_t)S * maxBlocks))) return rc;
+        if ((rc = wsalloc(e, &e->dEeVAll, (size_t)S * nV))) return rc;
+        if ((rc = wsalloc(e, &e->dEeSAll, (size_t)S * nV))) return rc;
+        if ((rc = wsalloc(e, &e->dGAll, (size_t)S * nV))) return rc;
+    }
+    e->launches = e->yinRechecked = e->yinFrames = 0;
+    e->capV = e->prm.lpcVoice; e->capS = e->prm.lpcSynth; e->capP = e->prm.lpcPitch;
+    e->prepared = true;
+    e->lastBlocks = 0;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out) {
+    if (!e || !out) return VP_E_ARG;
+    if (!e->prepared) return VP_E_STATE;
+    *out = e->sz;
+    return VP_OK;
+}
+
+static void stage_mark(vp_engine* e, int stage) {
+    if (!e->stageTiming) return;
+    if (e->evUsed >= e->ev.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->ev.push_back(ev);
+        e->evStage.push_back(0);
+    }
+    e->evStage[e->evUsed] = stage;
+    cudaEventRecord(e->ev[e->evUsed++], e->st);
+}
+
+static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
+    const vp_sizes& z = e->sz;
+    memset(g, 0, sizeof *g);
+    g->fs = e->fs; g->B = e->B; g->hopV = z.hopV; g->wlenV = z.wlenV; g->hopP = z.hopP; g->L = z.frameLenP; g->c = z.chunk;
+    g->tauMin = z.tauMin; g->tauMax = z.tauMax; g->lat = z.latency; g->keep = z.keep; g->inSize = z.inSize; g->anCap = z.anCap;
+    g->nBlocks = nBlocks; g->n = (long long)nBlocks * e->B; g->stride = (long long)stride;
+    g->wstride = (long long)e->maxBlocks * e->B;
+    frame_counts(z, g->n, &g->nFramesV, &g->nFramesP);
+    g->ordV = e->prm.lpcVoice; g->ordS = e->prm.lpcSynth; g->ordP = e->prm.lpcPitch;
+    g->gainVocF = db_to_gain(e->prm.gainVoc); g->gainPitchF = db_to_gain(e->prm.gainPitch);
+    g->gainVoiceF = db_to_gain(e->prm.gainVoice); g->gainSynthF = db_to_gain(e->prm.gainSynth);
+    g->vocOn = e->prm.vocBool != 0; g->pitchOn = e->prm.pitchBool != 0;
+    g->dryOn = e->prm.gainVoice > -59.0f; g->synthOn = e->prm.gainSynth > -59.0f;
+    g->yinEps = 1e-4;
+    if (const char* ye = getenv("VP_YIN_EPS")) g->yinEps = atof(ye);
+    return VP_OK;
+}
+
+// One pass over Sc' <= Sc streams whose I/O rows start at the given pointers.
+static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, const float* voice, const float* synthL,
+                    const float* synthR, float* outL, float* outR) {
+    cudaStream_t st = e->st;
+    VPTables tb = {e->dWV, e->dStP, e->dHann, e->dHannOff, e->dLutBeta, e->dLutPeriodNew, e->dLutNote};
+    const VPGeom& g = gIO;
+    int* listCount = e->dListCount + (e->passCount % 1024);
+    e->passCount++;
+    const size_t fV = (size_t)Sp * g.nFramesV, fP = (size_t)Sp * g.nFramesP;
+    stage_mark(e, ST_OTHER);
+    vp_launch_gate(st, g, Sp, voice, synthL, e->dGate);
+    e->launches++;
+    stage_mark(e, ST_GATE);
+    if (g.vocOn) {
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.n * sizeof(float), st));
+        stage_mark(e, ST_CLEAR);
+        vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
+        stage_mark(e, ST_VOC_AC);
+        vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
+        stage_mark(e, ST_VOC_LEV);
+        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dGate, e->dAV, e->dAS, e->dEeV, e->dEeS, e->dG, e->dOutV);
+        stage_mark(e, ST_VOC_SYN);
+        e->launches += 3;
+    }
+    if (g.pitchOn) {
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.n * sizeof(float), st));
+        VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
+        stage_mark(e, ST_CLEAR);
+        vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+        stage_mark(e, ST_YIN);
+        vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+        stage_mark(e, ST_YIN64);
+        vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
+        stage_mark(e, ST_MARKS);
+        vp_launch_pitch_frame(st, g, tb, Sp, voice, e->dFrames, e->dAP, e->dOutE);
+        stage_mark(e, ST_PFRAME);
+        vp_launch_pitch_iir(st, g, tb, Sp, e->dFrames, e->dAP, e->dOutE, e->dOutP);
+        stage_mark(e, ST_PIIR);
+        e->launches += 5;
+        e->yinFrames += fP;
+    }
+    vp_launch_mix(st, g, Sp, voice, synthL, synthR, e->dOutV, e->dOutP, outL, outR);
+    e->launches++;
+    stage_mark(e, ST_MIX);
+    if (e->keepDecisions && streamBase >= 0) {
+        if (g.pitchOn)
+            VP_CUDA_OK(cudaMemcpyAsync(e->dFramesAll + (size_t)streamBase * g.nFramesP, e->dFrames, fP * sizeof(vp_pitch_frame),
+                                       cudaMemcpyDeviceToDevice, st));
+        VP_CUDA_OK(cudaMemcpyAsync(e->dGateAll + (size_t)streamBase * g.nBlocks, e->dGate, (size_t)Sp * g.nBlocks,
+                                   cudaMemcpyDeviceToDevice, st));
+        if (g.vocOn) {
+            VP_CUDA_OK(cudaMemcpyAsync(e->dEeVAll + (size_t)streamBase * g.nFramesV, e->dEeV, fV * 8, cudaMemcpyDeviceToDevice, st));
+            VP_CUDA_OK(cudaMemcpyAsync(e->dEeSAll + (size_t)streamBase * g.nFramesV, e->dEeS, fV * 8, cudaMemcpyDeviceToDevice, st));
+            VP_CUDA_OK(cudaMemcpyAsync(e->dGAll + (size_t)streamBase * g.nFramesV, e->dG, fV * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        stage_mark(e, ST_OTHER);
+    }
+    VP_CUDA_OK(cudaGetLastError());
+    return VP_OK;
+}
+
+static int check_process_args(vp_engine* e, int nBlocks, const float* voice, const float* synthL, const float* synthR,
+                              float* outL, size_t stride) {
+    if (!e) return VP_E_ARG;
+    if (!e->prepared) return vp_err(e, VP_E_STATE, "vp_engine_prepare has not been called");
+    if (nBlocks <= 0 || nBlocks > e->maxBlocks) return vp_err(e, VP_E_ARG, "nBlocks outside (0, maxBlocks]");
+    if (!voice || !synthL || !outL) return vp_err(e, VP_E_ARG, "voice, synthL and outL must be non-null");
+    if (stride < (size_t)nBlocks * e->B) return vp_err(e, VP_E_ARG, "strideSamples < nBlocks * samplesPerBlock");
+    if (e->prm.gainSynth > -59.0f && !synthR) return vp_err(e, VP_E_ARG, "synthR is required when gainSynth > -59 dB");
+    return VP_OK;
+}
+
+extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
+                                        const float* synthR, float* outL, float* outR, size_t stride) {
+    int rc = check_process_args(e, nBlocks, voice, synthL, synthR, outL, stride);
+    if (rc) return rc;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VPGeom g;
+    make_geom(e, nBlocks, stride, &g);
+    e->lastBlocks = nBlocks;
+    e->evUsed = 0;
+    e->passCount = 0;
+    VP_CUDA_OK(cudaEventRecord(e->evT0, e->st));
+    for (int s0 = 0; s0 < e->S; s0 += e->Sc) {
+        const int Sp = std::min(e->Sc, e->S - s0);
+        const size_t off = (size_t)s0 * stride;
+        rc = run_pass(e, g, Sp, s0, voice + off, synthL + off, synthR ? synthR + off : nullptr, outL + off,
+                      outR ? outR + off : nullptr);
+        if (rc) return rc;
+    }
+    VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
+    return VP_OK;
+}
+
+extern "C" int vp_engine_sync(vp_engine* e) {
+    if (!e) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->stIn));
+    VP_CUDA_OK(cudaStreamSynchronize(e->stOut));
+    return VP_OK;
+}
+
+// Host path: slices of Sh streams, H2D on stIn, compute on st, D2H on stOut, three slice buffers in rotation.
+extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
+                                      const float* synthR, float* outL, float* outR, size_t stride) {
+    int rc = check_process_args(e, nBlocks, voice, synthL, synthR, outL, stride);
+    if (rc) return rc;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    const long long n = (long long)nBlocks * e->B;
+    const bool synthOn = e->prm.gainSynth > -59.0f;
+    if (e->Sh == 0) {
+        // slice = at most Sc streams and at most ~1 GiB per array
+        long long Sh = std::max<long long>(1, ((long long)1 << 28) / ((long long)e->maxBlocks * e->B));
+        Sh = std::min<long long>(Sh, e->Sc);
+        Sh = std::min<long long>(Sh, (e->S + 2) / 3 > 0 ? (e->S + 2) / 3 : 1);
+        if (Sh < 1) Sh = 1;
+        const size_t cnt = (size_t)Sh * (size_t)e->maxBlocks * e->B;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) if ((rc = wsalloc(e, &e->hIn[i][j], cnt))) return rc;
+            for (int j = 0; j < 2; ++j) if ((rc = wsalloc(e, &e->hOut[i][j], cnt))) return rc;
+        }
+        e->Sh = (int)Sh;
+    }
+    VPGeom g;
+    make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense
+    e->lastBlocks = nBlocks;
+    e->evUsed = 0;
+    e->passCount = 0;
+    const size_t rowB = (size_t)n * sizeof(float);
+    int slice = 0;
+    VP_CUDA_OK(cudaEventRecord(e->evT0, e->st));
+    for (int s0 = 0; s0 < e->S; s0 += e->Sh, ++slice) {
+        const int Sp = std::min(e->Sh, e->S - s0);
+        const int bi = slice % 3;
+        // the buffers of this rotation slot must have been drained (D2H of slice-3 done)
+        if (slice >= 3) VP_CUDA_OK(cudaStreamWaitEvent(e->stIn, e->evOut[bi], 0));
+        const size_t hoff = (size_t)s0 * stride;
+        VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][0], rowB, voice + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
+        VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][1], rowB, synthL + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
+        if (synthOn)
+            VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][2], rowB, synthR + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
+        VP_CUDA_OK(cudaEventRecord(e->evIn[bi], e->stIn));
+        VP_CUDA_OK(cudaStreamWaitEvent(e->st, e->evIn[bi], 0));
+        rc = run_pass(e, g, Sp, s0, e->hIn[bi][0], e->hIn[bi][1], synthOn ? e->hIn[bi][2] : nullptr, e->hOut[bi][0],
+                      (synthOn && outR) ? e->hOut[bi][1] : nullptr);
+        if (rc) return rc;
+        VP_CUDA_OK(cudaEventRecord(e->evComp[bi], e->st));
+        VP_CUDA_OK(cudaStreamWaitEvent(e->stOut, e->evComp[bi], 0));
+        VP_CUDA_OK(cudaMemcpy2DAsync(outL + hoff, stride * 4, e->hOut[bi][0], rowB, rowB, Sp, cudaMemcpyDeviceToHost, e->stOut));
+        if (outR)  // L == R unless the dry synth is mixed in (MyBuffer.cpp:380-448)
+            VP_CUDA_OK(cudaMemcpy2DAsync(outR + hoff, stride * 4, synthOn ? e->hOut[bi][1] : e->hOut[bi][0], rowB, rowB, Sp,
+                                         cudaMemcpyDeviceToHost, e->stOut));
+        VP_CUDA_OK(cudaEventRecord(e->evOut[bi], e->stOut));
+    }
+    VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
+    return vp_engine_sync(e);
+}
+
+extern "C" int vp_engine_get_pitch_frames(vp_engine* e, int stream, vp_pitch_frame* out, int cap, int* nFrames) {
+    if (!e || stream < 0) return VP_E_ARG;
+    if (!e->prepared || e->lastBlocks == 0 || !e->keepDecisions) return VP_E_STATE;
+    if (stream >= e->S) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VPGeom g;
+    make_geom(e, e->lastBlocks, 0, &g);
+    const int nP = g.pitchOn ? g.nFramesP : 0;
+    if (nFrames) *nFrames = nP;
+    if (out && cap > 0 && nP > 0) {
+        VP_CUDA_OK(cudaStreamSynchronize(e->st));
+        VP_CUDA_OK(cudaMemcpy(out, e->dFramesAll + (size_t)stream * g.nFramesP, (size_t)std::min(cap, nP) * sizeof(vp_pitch_frame),
+                              cudaMemcpyDeviceToHost));
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_engine_get_voc_frames(vp_engine* e, int stream, int cap, int* nFrames, uint8_t* gated, double* EeVoice,
+                                        double* EeSynth, double* gOut) {
+    if (!e || stream < 0) return VP_E_ARG;
+    if (!e->prepared || e->lastBlocks == 0 || !e->keepDecisions) return VP_E_STATE;
+    if (stream >= e->S) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VPGeom g;
+    make_geom(e, e->lastBlocks, 0, &g);
+    const int nV = g.vocOn ? g.nFramesV : 0;
+    if (nFrames) *nFrames = nV;
+    const int m = std::min(cap, nV);
+    if (m <= 0) return VP_OK;
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    const size_t off = (size_t)stream * g.nFramesV;
+    if (EeVoice) VP_CUDA_OK(cudaMemcpy(EeVoice, e->dEeVAll + off, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (EeSynth) VP_CUDA_OK(cudaMemcpy(EeSynth, e->dEeSAll + off, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (gOut) VP_CUDA_OK(cudaMemcpy(gOut, e->dGAll + off, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (gated) {
+        std::vector<uint8_t> gb(g.nBlocks);
+        VP_CUDA_OK(cudaMemcpy(gb.data(), e->dGateAll + (size_t)stream * g.nBlocks, (size_t)g.nBlocks, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < m; ++k) {
+            const int b = (int)(((long long)k * g.hopV) / g.B);
+            gated[k] = (gb[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) ? 1 : 0;
+        }
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_engine_get_stats(const vp_engine* e, uint64_t* launches, uint64_t* yinRechecked, uint64_t* yinFrames) {
+    if (!e) return VP_E_ARG;
+    if (launches) *launches = e->launches;
+    if (yinFrames) *yinFrames = e->yinFrames;
+    if (yinRechecked) {
+        // re-check list counters of the passes of the most recent call
+        uint64_t cnt = 0;
+        if (e->dListCount && e->prepared && e->passCount > 0) {
+            int h[1024];
+            cudaSetDevice(e->device);
+            cudaStreamSynchronize(e->st);
+            const int np = e->passCount < 1024 ? e->passCount : 1024;
+            cudaMemcpy(h, e->dListCount, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost);
+            for (int i = 0; i < np; ++i) cnt += (uint64_t)h[i];
+        }
+        *yinRechecked = cnt;
+    }
+    return VP_OK;
+}
+
+extern "C" const char* vp_stage_name(int stage) { return (stage >= 0 && stage < VP_NSTAGES) ? kStageNames[stage] : ""; }
+
+extern "C" int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageMs) {
+    if (!e) return VP_E_ARG;
+    if (!e->prepared || e->lastBlocks == 0) return VP_E_STATE;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaEventSynchronize(e->evT1));
+    if (totalMs) VP_CUDA_OK(cudaEventElapsedTime(totalMs, e->evT0, e->evT1));
+    if (stageMs) {
+        for (int i = 0; i < VP_NSTAGES; ++i) stageMs[i] = 0.f;
+        for (size_t i = 1; i < e->evUsed; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e->ev[i - 1], e->ev[i]) == cudaSuccess) stageMs[e->evStage[i]] += ms;
+        }
+    }
+    return VP_OK;
+}
+
+// ---- memory helpers ------------------------------------------------------------
+extern "C" int vp_host_alloc(void** p, size_t bytes) {
+    if (!p) return VP_E_ARG;
+    if (cudaHostAlloc(p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return VP_E_NOMEM; }
+    return VP_OK;
+}
+extern "C" void vp_host_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" int vp_device_alloc(vp_engine* e, void** p, size_t bytes) {
+    if (!e || !p) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaMalloc(p, bytes));
+    return VP_OK;
+}
+extern "C" void vp_device_free(vp_engine* e, void* p) { if (e && p) { cudaSetDevice(e->device); cudaFree(p); } }
+extern "C" int vp_memcpy_h2d(vp_engine* e, void* dst, const void* src, size_t bytes) {
+    if (!e) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    return VP_OK;
+}
+extern "C" int vp_memcpy_d2h(vp_engine* e, void* dst, const void* src, size_t bytes) {
+    if (!e) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    return VP_OK;
+}
+
+// ---- synthetic inputs ------------------------------------------------------------
+static void make_streams(double fs, int flavour, int first, int S, size_t nSamples, std::vector<vp_synth_stream>& out) {
+    static const double vowels[5][4] = {{700, 1220, 2600, 3300}, {400, 2000, 2550, 3400}, {300, 2300, 3000, 3500},
+                                        {450, 800, 2830, 3300}, {325, 700, 2530, 3400}};
+    static const double bws[4] = {130, 70, 160, 250};
+    out.resize(S);
+    for (int i = 0; i < S; ++i) {
+        vp_synth_stream& p = out[i];
+        memset(&p, 0, sizeof p);
+        const uint32_t seed = 0x5EED0000u + (uint32_t)(first + i);
+        auto u = [&](int k) { return (double)vps_hash(seed ^ 0xA5A5A5A5u, (uint64_t)k) / 4294967296.0; };
+        p.seed = seed;
+        const double f0 = 120.0 * pow(330.0 / 120.0, u(0));
+        p.f0inc = (float)(f0 / fs);
+        p.glideInc = (uint32_t)((0.1 + 0.2 * u(1)) / fs * 4294967296.0);
+        p.vibInc = (uint32_t)((5.0 + u(2)) / fs * 4294967296.0);
+        p.glidePh0 = (uint32_t)(u(3) * 4294967296.0);
+        p.vibPh0 = (uint32_t)(u(4) * 4294967296.0);
+        p.glideDepth = (float)(3.0 / 12.0);
+        p.vibDepth = (float)(0.3 / 12.0);
+        p.tilt = (float)(0.90 + 0.05 * u(5));
+        const int vw = (int)(u(6) * 5.0) % 5;
+        const double scale = 0.9 + 0.25 * u(7);
+        for (int k = 0; k < VPS_NFORMANTS; ++k) {
+            const double fr = vowels[vw][k] * scale, bw = bws[k];
+            const double r = exp(-kPi * bw / fs), th = 2.0 * kPi * fr / fs;
+            const double a1 = -2.0 * r * cos(th), a2 = r * r;
+            p.a1[k] = (float)a1; p.a2[k] = (float)a2;
+            p.b0[k] = (float)(1.0 + a1 + a2);
+        }
+        p.noiseAmp = (flavour == 1) ? 1e-4f : 1e-2f;
+        static const double chord[VPS_NSAW + 1] = {0, 4, 7, 12, 10};
+        const int root = (int)(u(8) * 12.0) % 12;
+        for (int k = 0; k <= VPS_NSAW; ++k) {
+            const double f = 130.8127826502993 * pow(2.0, (root + chord[k]) / 12.0);
+            p.sawInc[k] = (uint32_t)(f / fs * 4294967296.0);
+            p.sawPh0[k] = (uint32_t)(u(9 + k) * 4294967296.0);
+        }
+        p.sawAmp = 0.25f / VPS_NSAW;
+        p.muteStart = p.muteEnd = 0;
+        if (flavour == 2 && nSamples > 0) {
+            p.muteStart = (int64_t)(nSamples * (0.35 + 0.1 * u(20)));
+            p.muteEnd = p.muteStart + (int64_t)(fs * (0.25 + 0.2 * u(21)));
+        }
+        // calibrate the output gain so that the voiced peak sits near 0.5
+        p.gain = 1.0f;
+        const float keepNoise = p.noiseAmp;
+        p.noiseAmp = 0.f;
+        const int64_t ms = p.muteStart, me = p.muteEnd;
+        p.muteStart = p.muteEnd = 0;
+        vp_synth_state stt;
+        vps_init(&p, &stt);
+        float peak = 1e-9f;
+        for (int j = 0; j < 4096; ++j) {
+            float a, b, c;
+            vps_step(&p, &stt, j, &a, &b, &c);
+            if (j >= 1024) peak = fmaxf(peak, fabsf(a));
+        }
+        p.gain = 0.5f / peak;
+        p.noiseAmp = keepNoise;
+        p.muteStart = ms; p.muteEnd = me;
+    }
+}
+
+extern "C" int vp_synth_host(double fs, int flavour, int first, int S, size_t nSamples, size_t stride, float* voice,
+                             float* synthL, float* synthR) {
+    if (!voice || S <= 0 || stride < nSamples || !(fs > 0)) return VP_E_ARG;
+    std::vector<vp_synth_stream> ps;
+    make_streams(fs, flavour, first, S, nSamples, ps);
+    for (int s = 0; s < S; ++s) {
+        vp_synth_state st;
+        vps_init(&ps[s], &st);
+        for (size_t i = 0; i < nSamples; ++i) {
+            float a, b, c;
+            vps_step(&ps[s], &st, (int64_t)i, &a, &b, &c);
+            voice[(size_t)s * stride + i] = a;
+            if (synthL) synthL[(size_t)s * stride + i] = b;
+            if (synthR) synthR[(size_t)s * stride + i] = c;
+        }
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_synth_device(vp_engine* e, double fs, int flavour, int first, int S, size_t nSamples, size_t stride,
+                               float* voice, float* synthL, float* synthR) {
+    if (!e || !voice || S <= 0 || stride < nSamples || !(fs > 0)) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    std::vector<vp_synth_stream> ps;
+    make_streams(fs, flavour, first, S, nSamples, ps);
+    vp_synth_stream* d = nullptr;
+    VP_CUDA_OK(cudaMalloc((void**)&d, ps.size() * sizeof(vp_synth_stream)));
+    VP_CUDA_OK(cudaMemcpy(d, ps.data(), ps.size() * sizeof(vp_synth_stream), cudaMemcpyHostToDevice));
+    vp_launch_synth(e->st, d, S, (long long)nSamples, (long long)stride, voice, synthL, synthR);
+    cudaError_t ce = cudaStreamSynchronize(e->st);
+    cudaFree(d);
+    if (ce != cudaSuccess) return vp_fail(e, ce, "k_synth", __FILE__, __LINE__);
+    return VP_OK;
+}
+
+// ---- measurement -------------------------------------------------------------------
+extern "C" int vp_measure_peaks(vp_engine* e, double* fp32, double* fp64) {
+    if (!e) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    VP_CUDA_OK(cudaGetDeviceProperties(&prop, e->device));
+    void* sink = nullptr;
+    VP_CUDA_OK(cudaMalloc(&sink, 64));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int iters = pass == 0 ? 4096 : 1024;
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(a, e->st);
+            if (pass == 0) vp_launch_peak_fp32(e->st, (float*)sink, iters, blocks, threads);
+            else vp_launch_peak_fp64(e->st, (double*)sink, iters, blocks, threads);
+            cudaEventRecord(b, e->st);
+            cudaEventSynchronize(b);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+            if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+        }
+        if (pass == 0 && fp32) *fp32 = best;
+        if (pass == 1 && fp64) *fp64 = best;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(sink);
+    VP_CUDA_OK(cudaGetLastError());
+    return VP_OK;
+}

@@ -1,0 +1,109 @@
+// Mix/egress, synthetic-input generation and issue-rate microbenchmarks.
+#include "vp_common.cuh"
+#include "vp_synth.h"
+
+// ---------------------------------------------------------------------------
+// Mix + egress (PluginProcessor.cpp:226-232, MyBuffer.cpp:113-133, :309-448):
+// out = vocoder OLA + pitch OLA (+ gainVoice * delayed voice) (+ gainSynth *
+// delayed synth), cast to float. Output sample u carries input time u - latency.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mix(VPGeom g, const float* __restrict__ voice, const float* __restrict__ synthL,
+                                             const float* __restrict__ synthR, const float* __restrict__ outV,
+                                             const float* __restrict__ outP, float* __restrict__ outL,
+                                             float* __restrict__ outR) {
+    const int s = blockIdx.y;
+    const size_t row = (size_t)s * g.stride, wrow = (size_t)s * g.wstride;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < g.n; u += (long long)gridDim.x * blockDim.x) {
+        float l = 0.0f;
+        if (g.vocOn) l += outV[wrow + u];
+        if (g.pitchOn) l += outP[wrow + u];
+        float r = l;
+        if (g.dryOn) {
+            const float d = g.gainVoiceF * vp_x(voice + row, u, g.lat, g.n);
+            l += d; r += d;
+        }
+        if (g.synthOn) {
+            l += g.gainSynthF * vp_x(synthL + row, u, g.lat, g.n);
+            r += g.gainSynthF * vp_x((synthR ? synthR : synthL) + row, u, g.lat, g.n);
+        }
+        outL[row + u] = l;
+        if (outR) outR[row + u] = r;
+    }
+}
+
+void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
+                   const float* synthR, const float* outV, const float* outP, float* outL, float* outR) {
+    long long bx = (g.n + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, S);
+    k_mix<<<grid, 256, 0, st>>>(g, voice, synthL, synthR, outV, outP, outL, outR);
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic inputs: one thread per stream (the formant cascade is a serial
+// recursion), 32 samples buffered per thread and written through a shared
+// transpose so that global stores are 128-byte rows.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_synth(const vp_synth_stream* __restrict__ streams, int nStreams, long long nSamples,
+                                              long long stride, float* __restrict__ voice, float* __restrict__ synthL,
+                                              float* __restrict__ synthR) {
+    __shared__ float tv[32][33], tl[32][33], tr[32][33];
+    const int lane = threadIdx.x;
+    const int s0 = blockIdx.x * 32;
+    const int s = s0 + lane;
+    vp_synth_stream p;
+    vp_synth_state st;
+    const bool live = s < nStreams;
+    if (live) { p = streams[s]; vps_init(&p, &st); }
+    for (long long i0 = 0; i0 < nSamples; i0 += 32) {
+        if (live) {
+            for (int j = 0; j < 32; ++j) {
+                float a, b, c;
+                vps_step(&p, &st, i0 + j, &a, &b, &c);
+                tv[lane][j] = a; tl[lane][j] = b; tr[lane][j] = c;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int sr = s0 + r;
+            const long long i = i0 + lane;
+            if (sr < nStreams && i < nSamples) {
+                voice[(size_t)sr * stride + i] = tv[r][lane];
+                if (synthL) synthL[(size_t)sr * stride + i] = tl[r][lane];
+                if (synthR) synthR[(size_t)sr * stride + i] = tr[r][lane];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+void vp_launch_synth(cudaStream_t st, const void* streams, int nStreams, long long nSamples, long long stride,
+                     float* voice, float* synthL, float* synthR) {
+    k_synth<<<(nStreams + 31) / 32, 32, 0, st>>>((const vp_synth_stream*)streams, nStreams, nSamples, stride, voice,
+                                                 synthL, synthR);
+}
+
+// ---------------------------------------------------------------------------
+// Issue-rate microbenchmarks: 8 independent FMA chains per thread.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_peak(T* sink, int iters) {
+    T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T m = (T)0.999999, c = (T)1e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == (T)123456789) sink[0] = r;
+}
+
+void vp_launch_peak_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads) {
+    k_peak<float><<<blocks, threads, 0, st>>>(sink, iters);
+}
+void vp_launch_peak_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads) {
+    k_peak<double><<<blocks, threads, 0, st>>>(sink, iters);
+}

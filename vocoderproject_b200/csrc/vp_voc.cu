@@ -1,0 +1,470 @@
+// Vocoder path kernels (sm_100a): ring-RMS gate, windowed autocorrelation,
+// Levinson-Durbin + residual energies, all-pole resynthesis + overlap-add.
+// Reference behaviour: Source/VocoderProcess.cpp:190-297, Source/LPC.cpp:44-148,
+// Source/MyBuffer.cpp:258-261,:299-302.
+#include "vp_common.cuh"
+
+// ---------------------------------------------------------------------------
+// Gate: RMS of the whole ring at every host block (MyBuffer.cpp:258-261).
+// The ring at block b holds input times [(b+1)B - inSize, (b+1)B); zeros
+// before time 0. One CTA per (block, stream); FP64 accumulation.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gate(VPGeom g, const float* __restrict__ voice,
+                                              const float* __restrict__ synth, uint8_t* __restrict__ gate) {
+    const int b = blockIdx.x, s = blockIdx.y;
+    const float* v = voice + (size_t)s * g.stride;
+    const float* y = synth + (size_t)s * g.stride;
+    long long t1 = (long long)(b + 1) * g.B;
+    long long t0 = t1 - g.inSize;
+    if (t0 < 0) t0 = 0;
+    double sv = 0.0, ss = 0.0;
+    for (long long t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        double a = (double)__ldg(v + t), c = (double)__ldg(y + t);
+        sv = fma(a, a, sv);
+        ss = fma(c, c, ss);
+    }
+    sv = vp_warp_sum(sv);
+    ss = vp_warp_sum(ss);
+    __shared__ double red[2][4];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sv = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        ss = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        // juce::Decibels::gainToDecibels(rms) < -60 (VocoderProcess.cpp:199-204)
+        double rv = sqrt(sv / (double)g.inSize), rs = sqrt(ss / (double)g.inSize);
+        double dv = rv > 0.0 ? fmax(-100.0, log10(rv) * 20.0) : -100.0;
+        double ds = rs > 0.0 ? fmax(-100.0, log10(rs) * 20.0) : -100.0;
+        uint8_t f = 0;
+        if (dv < -60.0) f |= VP_GATE_VOICE;
+        if (ds < -60.0) f |= VP_GATE_SYNTH;
+        if (fabs(dv + 60.0) < 1e-7 || fabs(ds + 60.0) < 1e-7) f |= VP_GATE_NEAR;
+        gate[(size_t)s * g.nBlocks + b] = f;
+    }
+}
+
+void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate) {
+    dim3 grid(g.nBlocks, S);
+    k_gate<<<grid, 128, 0, st>>>(g, voice, synth, gate);
+}
+
+// ---------------------------------------------------------------------------
+// Windowed biased autocorrelation (LPC.cpp:44-97), FP64.
+// CTA = 4 consecutive frames of one stream. Warp w owns one group of R lags of
+// either signal; lane = segment (8 n-segments) + 8 * frame. Each thread keeps
+// R accumulators and an R-deep sliding window of the windowed signal in
+// registers: 2 shared loads per R DFMAs. Segment length == 2 (mod 4) and a
+// frame stride == 1 (mod 16) make the 64-bit shared loads conflict-free.
+// ---------------------------------------------------------------------------
+#define AC_R 14
+#define AC_FRAMES 4
+#define AC_SEGS 8
+
+template <int R>
+__device__ __forceinline__ void ac_task(const double* __restrict__ xw, int n0, int segLen, int m0, double* acc) {
+    double W[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { acc[j] = 0.0; W[j] = xw[n0 + m0 + j]; }
+    const int nEnd = n0 + segLen;
+    for (int nb = n0; nb < nEnd; nb += R) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const int n = nb + u;
+            if (u > 0) W[(u + R - 1) % R] = xw[n + m0 + R - 1];
+            const double a = (n < nEnd) ? xw[n] : 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = fma(a, W[(u + j) % R], acc[j]);
+        }
+        W[(R - 1) % R] = xw[nb + R + m0 + R - 1];  // element for u = 0 of the next round
+    }
+}
+
+__global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb, const float* __restrict__ voice,
+                                                          const float* __restrict__ synth, double* __restrict__ rV,
+                                                          double* __restrict__ rS, int segLen, int FS, int Gv) {
+    extern __shared__ double sm[];
+    double* xw = sm;                   // [AC_FRAMES][FS] voice * window
+    double* sw = sm + AC_FRAMES * FS;  // [AC_FRAMES][FS] synth ch0 * window
+    const int s = blockIdx.y;
+    const int k0 = blockIdx.x * AC_FRAMES;
+    const float* v = voice + (size_t)s * g.stride;
+    const float* y = synth + (size_t)s * g.stride;
+    for (int i = threadIdx.x; i < AC_FRAMES * FS; i += blockDim.x) {
+        const int f = i / FS, j = i - f * FS;
+        const int k = k0 + f;
+        double a = 0.0, c = 0.0;
+        if (j < g.wlenV && k < g.nFramesV) {
+            const long long u = (long long)k * g.hopV + j;
+            const double w = tb.wV[j];
+            a = (double)vp_x(v, u, g.lat, g.n) * w;
+            c = (double)vp_x(y, u, g.lat, g.n) * w;
+        }
+        xw[i] = a;
+        sw[i] = c;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = lane & (AC_SEGS - 1), f = lane >> 3;
+    const bool isVoice = warp < Gv;
+    const int grp = isVoice ? warp : warp - Gv;
+    const double* sig = (isVoice ? xw : sw) + f * FS;
+    const int order = isVoice ? g.ordV : g.ordS;
+    double acc[AC_R];
+    ac_task<AC_R>(sig, seg * segLen, segLen, grp * AC_R, acc);
+#pragma unroll
+    for (int j = 0; j < AC_R; ++j) {
+        double a = acc[j];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        acc[j] = a;
+    }
+    const int k = k0 + f;
+    if (seg == 0 && k < g.nFramesV) {
+        double* r = (isVoice ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)(order + 1);
+#pragma unroll
+        for (int j = 0; j < AC_R; ++j) {
+            const int m = grp * AC_R + j;
+            if (m <= order) r[m] = acc[j] / (double)g.wlenV;
+        }
+    }
+}
+
+void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                            const float* synth, const uint8_t* gate, double* rV, double* rS) {
+    (void)gate;
+    int segLen = (g.wlenV + AC_SEGS - 1) / AC_SEGS;
+    while ((segLen & 3) != 2) ++segLen;
+    const int Gv = (g.ordV + 1 + AC_R - 1) / AC_R, Gs = (g.ordS + 1 + AC_R - 1) / AC_R;
+    // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
+    int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
+    while ((FS & 15) != 1) ++FS;
+    const size_t smem = (size_t)2 * AC_FRAMES * FS * sizeof(double);
+    cudaFuncSetAttribute(k_voc_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    dim3 grid((g.nFramesV + AC_FRAMES - 1) / AC_FRAMES, S);
+    k_voc_autocorr<<<grid, 32 * (Gv + Gs), smem, st>>>(g, tb, voice, synth, rV, rS, segLen, FS, Gv);
+}
+
+// ---------------------------------------------------------------------------
+// Levinson-Durbin (LPC.cpp:107-148) + residual energies, one thread per frame.
+// The energy of the zero-state FIR residual over the frame
+// (VocoderProcess.cpp:235-251) is evaluated in closed form:
+//   E = wlen * (r0 + sum_k a_k r_k)  -  sum_{i=wlen}^{wlen+p-1} e_full[i]^2
+// (total energy of the full convolution minus its tail past the frame end),
+// 41 + p^2/2 DFMAs instead of wlen*(p+1). Verified to ~1e-14 relative against
+// the reference's direct sum.
+// ---------------------------------------------------------------------------
+__device__ void lev_solve(const double* r, double* a, int order) {
+    // |r0| < 1e-9 -> a = [1, 0, ...]   (LPC.cpp:110-114)
+    a[0] = 1.0;
+    if (fabs(r[0]) < 1e-9) {
+        for (int i = 1; i <= order; ++i) a[i] = 0.0;
+        return;
+    }
+    a[1] = r[1] / r[0];
+    for (int p = 2; p <= order; ++p) {
+        double rho = 0.0, ra = 0.0;
+        for (int i = 1; i < p; ++i) { rho = fma(r[p - i], a[i], rho); ra = fma(r[i], a[i], ra); }
+        const double k = (r[p] - rho) / (r[0] - ra);  // error energy recomputed every order (LPC.cpp:131-136)
+        for (int i = 1; 2 * i <= p; ++i) {
+            const double t1 = a[i], t2 = a[p - i];
+            a[i] = fma(-k, t2, t1);
+            if (i != p - i) a[p - i] = fma(-k, t1, t2);
+        }
+        a[p] = k;
+    }
+    for (int i = 1; i <= order; ++i) a[i] = -a[i];
+}
+
+__device__ double fir_energy(const double* r, const double* a, int order, int wlen, const float* __restrict__ row,
+                             long long u0, const double* __restrict__ w, int lat, long long n) {
+    double q = r[0];
+    for (int k = 1; k <= order; ++k) q = fma(a[k], r[k], q);
+    double E = q * (double)wlen;
+    // tail of the full convolution: i = wlen + d, d = 0..order-1, taps k = d+1..order on xw[wlen + d - k]
+    double tail = 0.0;
+    for (int d = 0; d < order; ++d) {
+        double e = 0.0;
+        for (int k = d + 1; k <= order; ++k) {
+            const int j = wlen + d - k;
+            if (j >= 0) e = fma(a[k], (double)vp_x(row, u0 + j, lat, n) * w[j], e);
+        }
+        tail = fma(e, e, tail);
+    }
+    E -= tail;
+    return E > 0.0 ? E : 0.0;
+}
+
+__global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, const float* __restrict__ voice,
+                                                      const float* __restrict__ synth,
+                                                      const double* __restrict__ rV, const double* __restrict__ rS,
+                                                      double* __restrict__ aV, double* __restrict__ aS,
+                                                      double* __restrict__ EeV, double* __restrict__ EeS, int S) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)S * g.nFramesV) return;
+    const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+    const long long u0 = (long long)k * g.hopV;
+    double r[VP_ORDER_MAX + 1], a[VP_ORDER_MAX + 1];
+    {
+        const double* rp = rV + (size_t)idx * (g.ordV + 1);
+        for (int m = 0; m <= g.ordV; ++m) r[m] = rp[m];
+        lev_solve(r, a, g.ordV);
+        double* ap = aV + (size_t)idx * (g.ordV + 1);
+        for (int m = 0; m <= g.ordV; ++m) ap[m] = a[m];
+        EeV[idx] = fir_energy(r, a, g.ordV, g.wlenV, voice + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+    }
+    {
+        const double* rp = rS + (size_t)idx * (g.ordS + 1);
+        for (int m = 0; m <= g.ordS; ++m) r[m] = rp[m];
+        lev_solve(r, a, g.ordS);
+        double* ap = aS + (size_t)idx * (g.ordS + 1);
+        for (int m = 0; m <= g.ordS; ++m) ap[m] = a[m];
+        EeS[idx] = fir_energy(r, a, g.ordS, g.wlenV, synth + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+    }
+}
+
+void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                            const float* synth, const uint8_t* gate, const double* rV, const double* rS, double* aV,
+                            double* aS, double* EeV, double* EeS) {
+    (void)gate;
+    const long long tot = (long long)S * g.nFramesV;
+    k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
+}
+
+// ---------------------------------------------------------------------------
+// Gain + all-pole resynthesis + sine-window overlap-add
+// (VocoderProcess.cpp:260-297). One thread per frame, one warp per tile of 32
+// consecutive frames of one stream: the recursion is serial in i, so frames
+// are the parallel axis. The tile's side-chain samples and its overlap-add
+// accumulator live in shared memory with a +1-per-hop skew so that lanes
+// (hop apart) hit distinct banks.
+// ---------------------------------------------------------------------------
+#define VS_WARPS 2
+
+template <int P>
+struct IirState {
+    double h[P];
+};
+
+// Skewed shared-memory index of tile position pos = lane*hop + i (i < 5*hop):
+// pos + floor(pos / hop), with the division done by compares on the uniform i.
+__device__ __forceinline__ int vs_idx(int lane, int i, int hop) {
+    return lane * hop + i + lane + (i >= hop) + (i >= 2 * hop) + (i >= 3 * hop) + (i >= 4 * hop);
+}
+__device__ __forceinline__ int vs_skew(int pos, int hop) { return pos + pos / hop; }
+
+// gain of frame k (VocoderProcess.cpp:264-276): sums over the last 10 processed
+// (non-gated) frames, newest to oldest.
+__device__ double voc_gain(const VPGeom& g, const uint8_t* __restrict__ gate, const double* __restrict__ EeV,
+                           const double* __restrict__ EeS, int k) {
+    const double es = EeS[k];
+    if (!(es > 1e-4)) return 0.0;
+    double sv = 0.0, ss = 0.0;
+    int cnt = 0;
+    for (int q = k; q >= 0 && cnt < 10; --q) {
+        const int b = (int)(((long long)q * g.hopV) / g.B);
+        if (gate[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) continue;
+        sv += EeV[q];
+        ss += EeS[q];
+        ++cnt;
+    }
+    return sqrt(sv / ss);
+}
+
+template <int P, int PS>
+__global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables tb, const float* __restrict__ synth,
+                                                             const uint8_t* __restrict__ gate,
+                                                             const double* __restrict__ aV,
+                                                             const double* __restrict__ aS,
+                                                             const double* __restrict__ EeV,
+                                                             const double* __restrict__ EeS, double* __restrict__ gOut,
+                                                             float* __restrict__ outV, int tilesPerStream, int S,
+                                                             int spanPad) {
+    extern __shared__ float smf[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tile = (long long)blockIdx.x * VS_WARPS + warp;
+    const bool live = tile < (long long)tilesPerStream * S;
+    const int s = live ? (int)(tile / tilesPerStream) : 0;
+    const int k0 = live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0;
+    float* sbuf = smf + (size_t)warp * 2 * spanPad;  // side-chain samples, skewed, origin = u(k0)
+    float* obuf = sbuf + spanPad;                    // overlap-add accumulator, skewed, origin = u(k0)
+    const int hop = g.hopV, wlen = g.wlenV;
+    const int span = 31 * hop + wlen;                // samples covered by the tile
+    const float* y = synth + (size_t)s * g.stride;
+    const long long uBase = (long long)k0 * hop;
+    if (live) {
+        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop)] = vp_x(y, uBase + i, g.lat, g.n);
+        for (int i = lane; i < span; i += 32) obuf[vs_skew(i, hop)] = 0.0f;
+    }
+    __syncwarp();
+    const int k = k0 + lane;
+    const size_t fidx = (size_t)s * g.nFramesV + k;
+    bool active = live && k < g.nFramesV;
+    if (active) {
+        const int b = (int)(((long long)k * hop) / g.B);
+        if (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) active = false;
+    }
+    double gain = 0.0;
+    double a[P + 1], as[PS + 1];
+#pragma unroll
+    for (int j = 0; j <= P; ++j) a[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= PS; ++j) as[j] = 0.0;
+    if (active) {
+        gain = voc_gain(g, gate + (size_t)s * g.nBlocks, EeV + (size_t)s * g.nFramesV, EeS + (size_t)s * g.nFramesV, k);
+        const double* ap = aV + fidx * (P + 1);
+#pragma unroll
+        for (int j = 0; j <= P; ++j) a[j] = ap[j];
+        const double* sp = aS + fidx * (PS + 1);
+#pragma unroll
+        for (int j = 0; j <= PS; ++j) as[j] = sp[j];
+    }
+    if (live && k < g.nFramesV && gOut) gOut[fidx] = gain;
+    const double gv = (double)g.gainVocF;
+    double h[P];   // h[j] = out[i0 + j] of the current / previous round (circular, statically indexed)
+    double sw[PS + 1];  // windowed side-chain samples, sw[q] = value at step with (i mod (PS+1)) == q
+#pragma unroll
+    for (int j = 0; j < P; ++j) h[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= PS; ++j) sw[j] = 0.0;
+    // step i of every lane runs in lock step; rounds of lcm-free static indexing:
+    // the outer loop advances by P steps, the side-chain window is indexed mod (PS+1) dynamically
+    // through a second small unrolled rotation.
+    for (int i0 = 0; i0 < wlen; i0 += P) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int i = i0 + j;
+            if (i < wlen) {
+                const double w = tb.wV[i];
+                // rotate the (PS+1)-deep windowed side-chain history: shift is cheap for PS <= 8
+#pragma unroll
+                for (int q = PS; q > 0; --q) sw[q] = sw[q - 1];
+                sw[0] = (double)sbuf[vs_idx(lane, i, hop)] * w;
+                double e = 0.0;
+#pragma unroll
+                for (int q = 0; q <= PS; ++q) e = fma(as[q], sw[q], e);  // zero state: sw starts at 0
+                double acc0 = gain * e, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+                for (int kk = P; kk >= 1; --kk) {
+                    const double hv = h[((j - kk) % P + P) % P];
+                    if ((kk & 3) == 0) acc0 = fma(-a[kk], hv, acc0);
+                    else if ((kk & 3) == 1) acc1 = fma(-a[kk], hv, acc1);
+                    else if ((kk & 3) == 2) acc2 = fma(-a[kk], hv, acc2);
+                    else acc3 = fma(-a[kk], hv, acc3);
+                }
+                const double o = (acc0 + acc2) + (acc3 + acc1);
+                h[j] = o;
+                if (active) obuf[vs_idx(lane, i, hop)] += (float)(gv * o * w);
+            }
+            if ((j & 31) == 31) __syncwarp();
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (live) {
+        // interior of the tile: plain stores; first/last (wlen - hop) samples are shared with the
+        // neighbouring tiles: exactly two contributors -> float atomics stay deterministic.
+        float* o = outV + (size_t)s * g.wstride;
+        const int ov = wlen - hop;
+        for (int i = lane; i < span; i += 32) {
+            const long long u = uBase + i;
+            if (u >= g.n) break;
+            const float v = obuf[vs_skew(i, hop)];
+            if (i < ov || i >= 32 * hop) atomicAdd(o + u, v);
+            else o[u] = v;
+        }
+    }
+}
+
+// Generic-order fallback (orders other than the plug-in defaults): same tiling,
+// histories in local memory.
+__global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, VPTables tb, const float* __restrict__ synth,
+                                                                     const uint8_t* __restrict__ gate,
+                                                                     const double* __restrict__ aV,
+                                                                     const double* __restrict__ aS,
+                                                                     const double* __restrict__ EeV,
+                                                                     const double* __restrict__ EeS,
+                                                                     double* __restrict__ gOut, float* __restrict__ outV,
+                                                                     int tilesPerStream, int S, int spanPad) {
+    extern __shared__ float smf[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tile = (long long)blockIdx.x * VS_WARPS + warp;
+    const bool live = tile < (long long)tilesPerStream * S;
+    const int s = live ? (int)(tile / tilesPerStream) : 0;
+    const int k0 = live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0;
+    const int P = g.ordV, PS = g.ordS;
+    float* sbuf = smf + (size_t)warp * 2 * spanPad;
+    float* obuf = sbuf + spanPad;
+    const int hop = g.hopV, wlen = g.wlenV;
+    const int span = 31 * hop + wlen;
+    const float* y = synth + (size_t)s * g.stride;
+    const long long uBase = (long long)k0 * hop;
+    if (live) {
+        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop)] = vp_x(y, uBase + i, g.lat, g.n);
+        for (int i = lane; i < span; i += 32) obuf[vs_skew(i, hop)] = 0.0f;
+    }
+    __syncwarp();
+    const int k = k0 + lane;
+    const size_t fidx = (size_t)s * g.nFramesV + k;
+    bool active = live && k < g.nFramesV;
+    if (active) {
+        const int b = (int)(((long long)k * hop) / g.B);
+        if (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) active = false;
+    }
+    double gain = 0.0;
+    if (active)
+        gain = voc_gain(g, gate + (size_t)s * g.nBlocks, EeV + (size_t)s * g.nFramesV, EeS + (size_t)s * g.nFramesV, k);
+    if (live && k < g.nFramesV && gOut) gOut[fidx] = gain;
+    const double* ap = aV + fidx * (size_t)(P + 1);
+    const double* sp = aS + fidx * (size_t)(PS + 1);
+    double h[VP_ORDER_MAX];
+    for (int j = 0; j < P; ++j) h[j] = 0.0;
+    const double gv = (double)g.gainVocF;
+    for (int i = 0; i < wlen; ++i) {
+        const double w = tb.wV[i];
+        double o = 0.0;
+        if (active) {
+            double e = 0.0;
+            for (int q = 0; q <= PS && q <= i; ++q)
+                e = fma(sp[q], (double)sbuf[vs_idx(lane, i - q, hop)] * tb.wV[i - q], e);
+            o = gain * e;
+            for (int kk = 1; kk <= P && kk <= i; ++kk) o = fma(-ap[kk], h[(i - kk) % P], o);
+            h[i % P] = o;
+            obuf[vs_idx(lane, i, hop)] += (float)(gv * o * w);
+        }
+        if ((i & 31) == 31) __syncwarp();
+    }
+    __syncwarp();
+    if (live) {
+        float* o = outV + (size_t)s * g.wstride;
+        const int ov = wlen - hop;
+        for (int i = lane; i < span; i += 32) {
+            const long long u = uBase + i;
+            if (u >= g.n) break;
+            const float v = obuf[vs_skew(i, hop)];
+            if (i < ov || i >= 32 * hop) atomicAdd(o + u, v);
+            else o[u] = v;
+        }
+    }
+}
+
+void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
+                         const uint8_t* gate, const double* aV, const double* aS, const double* EeV,
+                         const double* EeS, double* gOut, float* outV) {
+    const int tilesPerStream = (g.nFramesV + 31) / 32;
+    const int span = 31 * g.hopV + g.wlenV + VP_ORDER_MAX;
+    int spanPad = span + span / g.hopV + 8;
+    spanPad = (spanPad + 31) & ~31;
+    const size_t smem = (size_t)VS_WARPS * 2 * spanPad * sizeof(float);
+    const long long tiles = (long long)tilesPerStream * S;
+    const unsigned grid = (unsigned)((tiles + VS_WARPS - 1) / VS_WARPS);
+    if (g.ordV == 40 && g.ordS == 5) {
+        cudaFuncSetAttribute(k_voc_synth<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_voc_synth<40, 5><<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV,
+                                                               tilesPerStream, S, spanPad);
+    } else {
+        cudaFuncSetAttribute(k_voc_synth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV,
+                                                               tilesPerStream, S, spanPad);
+    }
+}
