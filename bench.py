@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the hot path (VocoderProject DSP core, batched over streams).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic streams: per stream it is
+equivalent to prepareToPlay + nBlocks processBlock calls of the reference plug-in
+(PluginProcessor.cpp:144-234). Metric: audio-seconds processed per second (x real-time,
+summed over streams and GPUs). Streams shard by contiguous ranges over ranks with NO
+data-path collective (weak scaling: the per-GPU batch is fixed).
+
+One JSON line on stdout (rank 0). `value`: inputs resident in HBM, device time (CUDA events
+on the engine's stream, max over ranks). `e2e`: the same batch through the C-ABI host call
+vp_engine_process_host with pinned HOST buffers (H2D + compute + D2H inside the timed region).
+`--impl reference`: the reference's own C++ (oracle/_ref, compiled in place; else the C oracle
+port) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+# workloads: SURVEY.md 8(d) / BASELINE.json configs. Per-GPU stream counts (weak scaling).
+WORKLOADS = {
+    # configs[3]: full chain, 16384 streams x 60 s @ 48 kHz over 8 GPUs = 2048 streams per GPU
+    "chain48": dict(desc="full vocoder + pitch-corrector chain, 2048 streams/GPU x 60 s @ 48 kHz, chromatic, block 1024 "
+                         "(BASELINE configs[3] = 16384 streams over 8 GPUs)",
+                    fs=48000.0, B=1024, seconds=60.0, streams=2048, params=dict()),
+    # configs[1]: vocoder only, 1024 pairs x 30 s @ 44.1 kHz
+    "voc44": dict(desc="vocoder only, 1024 voice/carrier pairs x 30 s @ 44.1 kHz, LPC 40/5 (BASELINE configs[1])",
+                  fs=44100.0, B=1024, seconds=30.0, streams=1024, params=dict(pitchBool=0)),
+    # configs[2]: pitch corrector only, 4096 streams x 30 s @ 44.1 kHz, chromatic
+    "pitch44": dict(desc="pitch corrector only, 4096 streams x 30 s @ 44.1 kHz, chromatic (BASELINE configs[2])",
+                    fs=44100.0, B=1024, seconds=30.0, streams=4096, params=dict(vocBool=0)),
+    # the north_star target line: chain at 44.1 kHz
+    "chain44": dict(desc="full chain, 2048 streams/GPU x 60 s @ 44.1 kHz, chromatic, block 1024",
+                    fs=44100.0, B=1024, seconds=60.0, streams=2048, params=dict()),
+    "tiny": dict(desc="smoke-size chain, 64 streams x 4 s @ 44.1 kHz", fs=44100.0, B=1024, seconds=4.0, streams=64,
+                 params=dict()),
+}
+
+# Algorithmic FP32 lane-operations ("slots": one FADD/FMUL/FFMA each) per frame, minimal direct
+# form, SURVEY.md App. C.5 -- the denominators of the roofline fractions.
+
+
+def slot_model(sz, prm):
+    wl, hopV, L, hopP, c, tauMax = sz["wlenV"], sz["hopV"], sz["frameLenP"], sz["hopP"], sz["chunk"], sz["tauMax"]
+    pv, ps, pp = prm.lpcVoice, prm.lpcSynth, prm.lpcPitch
+
+    def ac(n, p):  # windowed autocorrelation, lags 0..p
+        return sum(n - m for m in range(p + 1))
+
+    def lev(p):
+        return sum(2 * (q - 1) + 2 + q for q in range(2, p + 1)) + 1 + p
+
+    def fir(n, p):
+        return sum(min(i, p) + 1 for i in range(n))
+
+    voc = {"window": 2 * wl, "autocorr_voice": ac(wl, pv), "autocorr_synth": ac(wl, ps), "levinson": lev(pv) + lev(ps),
+           "fir_voice": fir(wl, pv) + wl, "fir_synth": fir(wl, ps) + wl, "gain": 22, "iir": fir(wl, pv) - wl + wl, "ola": wl}
+    keepNeeded = tauMax
+    pitch = {"yin": 2 * L * tauMax, "cmnd": 3 * tauMax, "autocorr": ac(L, pp), "levinson": lev(pp),
+             "residual_fir": (keepNeeded + L + 3 * c) * (pp + 1), "psola": 12 * L, "iir": fir(L, pp), "ola": L}
+    return {"voc_per_frame": sum(voc.values()), "pitch_per_frame": sum(pitch.values()), "voc": voc, "pitch": pitch,
+            "voc_per_sample": sum(voc.values()) / hopV, "pitch_per_sample": sum(pitch.values()) / hopP}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons of one GPU, sampled every 200 ms while running."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.th = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-1:]]
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_run(kind_pref, fs, B, voice, sl, params_kw, threads):
+    """One pass of the reference CPU path over [S][n] host arrays. Returns (seconds, kind)."""
+    import oraclebind
+    import refbind
+    prm = refbind.default_params(**params_kw)
+    if kind_pref == "reference" and refbind.available("fast"):
+        sec, _ = refbind.bench(fs, B, voice, sl, None, params=prm, threads=threads, kind="fast")
+        return sec, "reference"
+    sec, _ = oraclebind.bench(fs, B, voice, sl, None, params=prm, threads=threads)
+    return sec, "port"
+
+
+def gen_host_inputs(vp, fs, first, S, n, threads):
+    """vp_synth_host over `threads` Python threads (ctypes releases the GIL)."""
+    voice = np.zeros((S, n), np.float32)
+    sl = np.zeros((S, n), np.float32)
+    lib = vp.load_library()
+
+    def work(t):
+        for s in range(t, S, threads):
+            lib.vp_synth_host(float(fs), 0, first + s, 1, n, n, voice[s].ctypes.data, sl[s].ctypes.data, None)
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(min(threads, S))]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    return voice, sl
+
+
+def run_reference(args, wl, group):
+    """--impl reference: the reference's own CPU implementation on the host cores, rank 0 only."""
+    if group.rank != 0:
+        return
+    import vocoderproject_b200 as vp
+    fs, B = wl["fs"], wl["B"]
+    n = int(fs * wl["seconds"]) // B * B
+    cores = host_cores()
+    S = max(1, min(wl["streams"], args.ref_streams or 2 * cores))
+    voice, sl = gen_host_inputs(vp, fs, 0, S, n, cores)
+    kind = "reference"
+    for _ in range(args.warmup):
+        cpu_run("reference", fs, B, voice, sl, wl["params"], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        sec, kind = cpu_run("reference", fs, B, voice, sl, wl["params"], cores)
+        t += sec
+    audio = S * n / fs * args.steps
+    val = audio / t
+    line = {"impl": "reference", "metric": "audio-sec/sec (streams x RT)", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample_rate": fs, "block": B, "seconds_per_stream": n / fs,
+                       "params": wl["params"] or "defaults"},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                             "sample": "%d streams x %.1f s of the workload per step, one plug-in instance per stream, %d host threads"
+                                       % (S, n / fs, cores)},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_engine(args, wl, group):
+    os.environ["VP_STAGE_TIMING"] = "1"      # CUDA events between the engine's kernels (per-kernel durations)
+    os.environ["VP_KEEP_DECISIONS"] = "0"    # decisions of all streams are not read back in the bench
+    import vocoderproject_b200 as vp
+    fs, B = wl["fs"], wl["B"]
+    n = int(fs * wl["seconds"]) // B * B
+    nBlocks = n // B
+    S = args.streams or wl["streams"]          # per GPU (weak scaling)
+    first = group.rank * S                      # global stream index of this shard
+    dev = group.local_rank
+    prm = vp.default_params(**wl["params"])
+    eng = vp.Engine(fs, B, S, nBlocks, params=prm, device=dev)
+    sz = eng.sizes
+    nb = S * n * 4
+    dv, dl, do = eng.device_alloc(nb), eng.device_alloc(nb), eng.device_alloc(nb)
+    eng.synth_device(0, first, S, n, n, dv, dl, None)
+    peaks_fp = eng.measure_peaks()
+    sampler = ClockSampler(dev)
+
+    # ---- device-resident: W warm-up + K timed steps, barrier + sync on both sides
+    for _ in range(args.warmup):
+        eng.process_device(nBlocks, dv, dl, None, do, None, n, sync=False)
+    eng.sync()
+    l0 = eng.stats()["kernel_launches"]
+    eng.timing_reset(accumulate=True)
+    group.barrier()
+    t0 = time.time()
+    eng.timer_record(0)
+    for _ in range(args.steps):
+        eng.process_device(nBlocks, dv, dl, None, do, None, n, sync=False)
+    eng.timer_record(1)
+    eng.sync()
+    t1 = time.time()
+    group.barrier()
+    dev_s = eng.timer_elapsed_ms(0, 1) * 1e-3
+    launches = eng.stats()["kernel_launches"] - l0
+    tot_ms, stage_ms = eng.last_timing()
+    stage_cnt = eng.last_timing_counts()
+    eng.timing_reset(accumulate=False)
+    clocks = sampler.window(t0, t1)
+    audio_rank = S * n / fs * args.steps
+    value, t_max, audio_total = vp.shard.aggregate_throughput(group, audio_rank, dev_s)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
+    e2e = None
+    if not args.no_e2e:
+        hv, hl, ho = vp.PinnedArray(S, n), vp.PinnedArray(S, n), vp.PinnedArray(S, n)
+        eng.d2h(hv.array, dv)
+        eng.d2h(hl.array, dl)
+        for p in (dv, dl, do):
+            eng.device_free(p)
+        dv = dl = do = None
+        we = max(1, min(args.warmup, 2))
+        for _ in range(we):
+            eng.process_host_ptrs(nBlocks, hv.ptr, hl.ptr, None, ho.ptr, None, n)
+        group.barrier()
+        te0 = time.time()
+        for _ in range(args.steps):
+            eng.process_host_ptrs(nBlocks, hv.ptr, hl.ptr, None, ho.ptr, None, n)  # returns with outputs in host memory
+        te = time.time() - te0
+        group.barrier()
+        e_val, e_t, _ = vp.shard.aggregate_throughput(group, audio_rank, te)
+        e2e = {"value": e_val, "unit": "audio-s/s", "h2d_bytes_per_step": 2 * nb * group.world, "d2h_bytes_per_step": nb * group.world,
+               "ms_per_step": 1e3 * e_t / args.steps, "timer": "host wall clock around vp_engine_process_host, max over ranks",
+               "note": "voice + side-chain ch0 uploaded (the path reads ch0 only, VocoderProcess.cpp:211,218); one output channel "
+                       "returned (L == R while gainSynth <= -59 dB)", "checksum": float(np.abs(ho.array[:, ::4097]).sum())}
+    sampler.stop()
+
+    # ---- CPU baseline on rank 0 at N = 1: bounded sample of the same workload
+    cpu = None
+    if group.world == 1 and not args.no_cpu:
+        cores = host_cores()
+        Sc = max(1, min(S, args.cpu_streams or 8 * cores))
+        secs_cpu = min(n / fs, 20.0)
+        ncpu = int(fs * secs_cpu) // B * B
+        if e2e is not None:
+            cv, cl = np.ascontiguousarray(hv.array[:Sc, :ncpu]), np.ascontiguousarray(hl.array[:Sc, :ncpu])
+        else:
+            cv = np.zeros((Sc, n), np.float32); cl = np.zeros((Sc, n), np.float32)
+            for s in range(Sc):  # row copies of the device inputs
+                eng.lib.vp_memcpy_d2h(eng.h, cv[s].ctypes.data, C.c_void_p(dv + s * n * 4), n * 4)
+                eng.lib.vp_memcpy_d2h(eng.h, cl[s].ctypes.data, C.c_void_p(dl + s * n * 4), n * 4)
+            cv, cl = np.ascontiguousarray(cv[:, :ncpu]), np.ascontiguousarray(cl[:, :ncpu])
+        sec, kind = cpu_run("reference", fs, B, cv, cl, wl["params"], cores)
+        cpu = {"value": Sc * ncpu / fs / sec, "unit": "audio-s/s", "cores": cores, "kind": kind,
+               "sample": "%d streams x %.1f s of the workload (%.1f s wall), one plug-in instance per stream, %d host threads, "
+                         "-O3 build of the reference's own C++" % (Sc, ncpu / fs, sec, cores)}
+
+    if group.rank == 0:
+        sm = slot_model(sz, prm)
+        peaks, peaks_src = measured_peaks()
+        p32 = peaks_fp["fp32_fma_per_s"]
+        samples_rank = S * n * args.steps
+        chain_slots = (sm["voc_per_sample"] if prm.vocBool else 0.0) + (sm["pitch_per_sample"] if prm.pitchBool else 0.0)
+        # dominant kernel: the stage with the largest share of the device time
+        kname = max(stage_ms, key=lambda k: stage_ms[k])
+        kms, kcnt = stage_ms[kname], max(stage_cnt.get(kname, 1), 1)
+        frames_v = S * ((n + sz["hopV"] - 1) // sz["hopV"]) * args.steps
+        frames_p = S * ((n + sz["hopP"] - 1) // sz["hopP"]) * args.steps
+        kslots = {"yin_fp32": sm["pitch"]["yin"] * frames_p,
+                  "voc_autocorr": (sm["voc"]["window"] + sm["voc"]["autocorr_voice"] + sm["voc"]["autocorr_synth"]) * frames_v,
+                  "voc_levinson": (sm["voc"]["levinson"] + sm["voc"]["fir_voice"] + sm["voc"]["fir_synth"]) * frames_v,
+                  "voc_synth": (sm["voc"]["gain"] + sm["voc"]["iir"] + sm["voc"]["ola"] + sm["voc"]["fir_synth"]) * frames_v,
+                  "pitch_frame": (sm["pitch"]["autocorr"] + sm["pitch"]["levinson"] + sm["pitch"]["residual_fir"] + sm["pitch"]["psola"]) * frames_p,
+                  "pitch_iir": (sm["pitch"]["iir"] + sm["pitch"]["ola"]) * frames_p}.get(kname, 0.0)
+        ach = 2.0 * kslots / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+        peak = 2.0 * p32 / 1e12
+        io_bytes = 12.0 * samples_rank  # voice + synth ch0 in, one channel out (float32)
+        roofline = {"bound": "fp32", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                    "traffic": None, "kernel_ms_per_launch": kms / kcnt, "kernel_launches_timed": kcnt,
+                    "kernel_share_of_step": kms / tot_ms if tot_ms else None,
+                    "peak_source": "vp_measure_peaks FP32 FMA issue-rate microbenchmark on this GPU in this run (2 flop per lane-op); "
+                                   "MEASURED_PEAKS.json (%s) has no FP32 CUDA-core figure" % peaks_src,
+                    "note": "algorithmic FP32 lane-ops of the minimal direct form (SURVEY App. C.5), 1 lane-op counted as 2 flop on both sides",
+                    "chain": {"slots_per_sample": chain_slots, "achieved_tflops": 2.0 * chain_slots * samples_rank / dev_s / 1e12,
+                              "frac": chain_slots * samples_rank / dev_s / p32 if p32 else None},
+                    "hbm": {"achieved_gbs": io_bytes / dev_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src,
+                            "frac": io_bytes / dev_s / 1e9 / peaks.get("hbm_gbs", 1.0), "algorithmic_bytes_per_sample": 12},
+                    "fp64_fma_per_s": peaks_fp["fp64_fma_per_s"], "fp32_fma_per_s": p32,
+                    "stage_ms": {k: round(v, 3) for k, v in stage_ms.items() if v > 0}, "stage_launches": {k: v for k, v in stage_cnt.items() if v}}
+        line = {"metric": "audio-sec/sec (streams x RT)", "value": value, "unit": "audio-s/s", "n_gpus": group.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "sample_rate": fs, "block": B, "streams_per_gpu": S, "streams_total": S * group.world,
+                           "seconds_per_stream": n / fs, "params": wl["params"] or "defaults", "parallelism": "streams sharded x%d, no collective" % group.world,
+                           "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" % (2 * nb / 1e9),
+                           "timer": "CUDA events on the engine's stream around the K steps, max over ranks"},
+                "x_realtime_per_gpu": value / group.world, "clocks": clocks, "gpu_launches": int(launches) * group.world,
+                "roofline": roofline}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="chain48", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
+    ap.add_argument("--seconds", type=float, default=0.0, help="seconds per stream (default: the workload's)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-streams", type=int, default=0)
+    ap.add_argument("--ref-streams", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        print("note: --warmup < 3 breaks the timing rules; use it for smoke runs only", file=sys.stderr)
+    wl = dict(WORKLOADS[args.workload])
+    if args.seconds:
+        wl["seconds"] = args.seconds
+        wl["desc"] += " [--seconds %g]" % args.seconds
+    if args.streams:
+        wl["desc"] += " [--streams %d]" % args.streams
+    from vocoderproject_b200.shard import Group, dist_env
+    rank, _, world = dist_env()
+    if args.impl == "reference":
+        if rank != 0:
+            return 0  # rank 0 alone runs the CPU reference
+        class Solo:
+            rank, local_rank, world = 0, 0, 1
+        run_reference(args, wl, Solo())
+        return 0
+    if world != args.gpus and world > 1:
+        print("warning: WORLD_SIZE=%d but --gpus %d; using WORLD_SIZE" % (world, args.gpus), file=sys.stderr)
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    group = Group()
+    try:
+        run_engine(args, wl, group)
+    finally:
+        group.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -145,7 +145,16 @@ int vp_engine_get_stats(const vp_engine* e, uint64_t* kernelLaunches, uint64_t* 
  * CUDA events on the engine's stream; per-stage breakdown optional. */
 #define VP_NSTAGES 12
 int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageMs /* [VP_NSTAGES] or NULL */);
+/* Number of timed intervals (= kernel launches of that stage) behind each stageMs entry. */
+int vp_engine_last_timing_counts(vp_engine* e, int* stageCount /* [VP_NSTAGES] */);
 const char* vp_stage_name(int stage);
+/* accumulate != 0: vp_engine_last_timing sums over every process call since this reset
+ * (total = first call's start .. last call's end); 0 (default): most recent call only. */
+int vp_engine_timing_reset(vp_engine* e, int accumulate);
+/* Device timers on the engine's stream (CUDA events), slots 0..7: bracket any sequence of
+ * asynchronous calls; _elapsed_ms waits for slotB and returns the time since slotA. */
+int vp_engine_timer_record(vp_engine* e, int slot);
+int vp_engine_timer_elapsed_ms(vp_engine* e, int slotA, int slotB, float* ms);
 
 /* ---- memory helpers -------------------------------------------------------- */
 int vp_host_alloc(void** p, size_t bytes);   /* pinned host memory */

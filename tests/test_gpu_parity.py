@@ -1,0 +1,228 @@
+"""Parity tests proper (B200): the CUDA engine, called through the C ABI
+(include/vp_engine.h via the ctypes mirror), against
+  * the committed golden fixtures = the reference's own C++ output (tests/golden/),
+  * the CPU oracle on the same seeded inputs (oracle/vp_oracle.c),
+  * SURVEY.md App. E's known-answer table,
+and, at larger sizes, through size-independent properties (shard / pass / host-vs-device
+invariance, determinism, pure-delay of the dry path, latency).
+
+Tolerances (BASELINE.json north_star): audio SNR >= 80 dB and max |err| <= 1e-4 vs the float32
+reference; detected period, snapped note index and pitch marks bit-exact except frames the engine
+flags as within epsilon of a decision boundary."""
+import numpy as np
+import pytest
+
+import refbind
+from cases import CASES, KAT, KAT_BETA, KAT_MARKS, KAT_NOTE, KAT_PERIOD, KAT_PERIODNEW, case_inputs
+from common import MAXABS_MAX, SNR_MIN_DB, compare_decisions, golden_index, golden_load, kat_inputs, maxabs, oracle_decisions, snr_db, stats
+
+pytestmark = pytest.mark.gpu
+
+
+def run_engine(vp, fs, B, voice, sl, sr, params, **kw):
+    """voice/sl/sr: [S][n]; returns (outL, outR, engine) -- caller closes the engine."""
+    S, n = voice.shape
+    eng = vp.Engine(fs, B, S, n // B, params=vp.default_params(**params), **kw)
+    outL, outR = eng.process(voice, sl, sr)
+    return outL, outR, eng
+
+
+def assert_audio(ref, got, what):
+    s, m = snr_db(ref, got), maxabs(ref, got)
+    assert s >= SNR_MIN_DB and m <= MAXABS_MAX, "%s: SNR %.1f dB, max abs err %.3e" % (what, s, m)
+    return s, m
+
+
+def golden_rows(g):
+    rows = []
+    for i in range(len(g["period"])):
+        rows.append({"gated": int(g["gated"][i]), "period": int(g["period"][i]), "periodNew": int(g["periodNew"][i]),
+                     "note": int(g["note"][i]), "an": [int(v) for v in g["anMarks"][i] if v >= 0],
+                     "st": [int(v) for v in g["stMarks"][i] if v >= 0], "stale": int(g["stale"][i]), "beta": float(g["beta"][i])})
+    return rows
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_engine_matches_reference_golden(vp, name):
+    case = CASES[name]
+    g = golden_load(name)
+    voice, sl, sr = case_inputs(vp, case)
+    outL, outR, eng = run_engine(vp, case["fs"], case["B"], voice[None], sl[None], sr[None], case["params"])
+    try:
+        assert_audio(g["outL"], outL[0], name + " L")
+        assert_audio(g["outR"] if len(g["outR"]) else g["outL"], outR[0], name + " R")
+        if case["params"].get("pitchBool", 1):
+            n, bad, flagged, first = compare_decisions(vp, golden_rows(g), eng.pitch_frames(0))
+            assert n == golden_index()[name]["pitch_frames"]
+            assert bad == 0, first
+            assert flagged <= max(1, n // 50)
+        if case["params"].get("vocBool", 1):
+            vf = eng.voc_frames(0)
+            assert list(vf["gated"]) == list(g["vocGated"])
+            live = g["vocGated"] == 0
+            for k in ("EeVoice", "EeSynth", "g"):
+                rel = np.abs(vf[k][live] - g[k][live]) / np.maximum(np.abs(g[k][live]), 1e-300)
+                assert rel.max() < 1e-6, (k, rel.max())
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("which", ["chain", "voc", "pitch"])
+def test_engine_known_answer_table(vp, which):
+    voice, synth = kat_inputs()
+    k = KAT[which]
+    outL, outR, eng = run_engine(vp, 44100.0, 1024, voice[None], synth[None], synth[None], k["params"])
+    try:
+        out = outL[0]
+        assert np.array_equal(out, outR[0])
+        s = stats(out)
+        assert s["first_nonzero"] == k["first_nonzero"]
+        assert abs(s["rms"] - k["rms"]) < 1e-6 and abs(s["max_abs"] - k["max_abs"]) < 1e-5
+        assert abs(s["sum_abs"] - k["sum_abs"]) < 1e-5 * k["sum_abs"]
+        for i, v in k["samples"].items():
+            assert abs(float(out[i]) - v) < 1e-5
+        if which != "voc":
+            pf = eng.pitch_frames(0)
+            assert len(pf) == 230 and pf[0].period == 0 and pf[1].period == 0
+            for f in pf[2:]:
+                assert f.period == KAT_PERIOD and f.note == KAT_NOTE and f.periodNew == KAT_PERIODNEW and f.beta == KAT_BETA
+            for f, (_, an, st) in KAT_MARKS.items():
+                assert list(pf[f].anMarks[:pf[f].nAn]) == an and list(pf[f].stMarks[:pf[f].nSt]) == st
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("fs,B,S,secs,flavour,params", [
+    (44100.0, 1024, 6, 3.0, 0, dict()),                       # chain, chromatic
+    (48000.0, 1024, 4, 3.0, 0, dict(keyPitch=3)),             # chain 48 kHz, C major
+    (44100.0, 1024, 4, 3.0, 1, dict(pitchBool=0)),            # vocoder only, clean voice (FP64 stress)
+    (44100.0, 1024, 6, 3.0, 0, dict(vocBool=0)),              # pitch only
+    (44100.0, 64, 2, 2.0, 0, dict()),                         # small host block (block-size dependent semantics)
+    (44100.0, 1000, 2, 2.0, 0, dict(keyPitch=9)),             # ragged block
+    (44100.0, 4096, 2, 3.0, 0, dict()),                       # block larger than every frame
+    (88200.0, 1024, 1, 1.5, 0, dict()),                       # double sample rate: all sizes x2
+])
+def test_engine_matches_oracle(vp, oracle, fs, B, S, secs, flavour, params):
+    n = int(fs * secs) // B * B
+    voice, sl, sr = vp.synth_host(fs, S, n, flavour=flavour, first_stream=100)
+    outL, outR, eng = run_engine(vp, fs, B, voice, sl, sr, params)
+    try:
+        tot = bad = flg = 0
+        for s in range(S):
+            r = oracle.run(fs, B, voice[s], sl[s], synthR=sr[s], params=refbind.default_params(**params), log=True)
+            assert r["ub"] == 0
+            assert_audio(r["outL"], outL[s], "stream %d L" % s)
+            assert_audio(r["outR"], outR[s], "stream %d R" % s)
+            if params.get("pitchBool", 1):
+                n_, b_, f_, first = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s))
+                assert b_ == 0, "stream %d: %s" % (s, first)
+                tot += n_; bad += b_; flg += f_
+        assert flg <= max(1, tot // 100)
+    finally:
+        eng.close()
+
+
+def test_all_zero_and_single_block(vp):
+    z = np.zeros((2, 8 * 1024), np.float32)
+    outL, outR, eng = run_engine(vp, 44100.0, 1024, z, z, z, dict())
+    try:
+        assert not outL.any() and not outR.any()
+        assert all(f.flags & vp.PF_GATED for f in eng.pitch_frames(0))
+        assert eng.voc_frames(1)["gated"].all()
+    finally:
+        eng.close()
+    voice, synth = kat_inputs(44100, 1)
+    outL, outR, eng = run_engine(vp, 44100.0, 1024, voice[None, :1024], synth[None, :1024], synth[None, :1024], dict())
+    eng.close()
+    assert not outL.any()  # a single block only fills the latency
+
+
+def test_latency_and_dry_path_is_a_pure_delay(vp):
+    """vocBool = pitchBool = 0, gainVoice = 0 dB: output = input delayed by `latency` (MyBuffer.cpp:309-373)."""
+    fs, B = 44100.0, 512
+    voice, sl, sr = vp.synth_host(fs, 2, 40 * B, flavour=0, first_stream=7)
+    outL, outR, eng = run_engine(vp, fs, B, voice, sl, sr, dict(vocBool=0, pitchBool=0, gainVoice=0.0))
+    lat = eng.sizes["latency"]
+    eng.close()
+    assert not outL[:, :lat].any()
+    assert np.array_equal(outL[:, lat:], voice[:, :-lat]) and np.array_equal(outR, outL)
+
+
+def test_shard_pass_and_path_invariance_bitwise(vp):
+    """Streams are independent: a stream's output must not depend on which batch, pass or path carried it."""
+    fs, B, S = 44100.0, 1024, 40
+    n = 48 * B
+    voice, sl, sr = vp.synth_host(fs, S, n, flavour=0, first_stream=0)
+    outL, outR, eng = run_engine(vp, fs, B, voice, sl, sr, dict(keyPitch=3))
+    frames17 = [(f.period, f.note, list(f.anMarks[:f.nAn])) for f in eng.pitch_frames(17)]
+    eng.close()
+    # (1) the shard [16, 24) on its own engine
+    a, _, e2 = run_engine(vp, fs, B, voice[16:24], sl[16:24], sr[16:24], dict(keyPitch=3))
+    assert [(f.period, f.note, list(f.anMarks[:f.nAn])) for f in e2.pitch_frames(1)] == frames17
+    e2.close()
+    assert np.array_equal(a, outL[16:24])
+    # (2) tiny workspace -> several passes of few streams
+    b, _, e3 = run_engine(vp, fs, B, voice, sl, sr, dict(keyPitch=3), workspace_bytes=8 << 20)
+    e3.close()
+    assert np.array_equal(b, outL)
+    # (3) device-resident path == host path, and a second run is bit-identical (deterministic accumulation)
+    e4 = vp.Engine(fs, B, S, n // B, params=vp.default_params(keyPitch=3))
+    try:
+        nb = S * n * 4
+        dv, dl, do = e4.device_alloc(nb), e4.device_alloc(nb), e4.device_alloc(nb)
+        e4.h2d(dv, voice); e4.h2d(dl, sl)
+        c = np.zeros((S, n), np.float32)
+        for _ in range(2):
+            e4.process_device(n // B, dv, dl, None, do, None, n)
+            e4.d2h(c, do)
+            assert np.array_equal(c, outL)
+        # (4) the on-device synthetic generator reproduces the host generator bit for bit
+        e4.synth_device(0, 0, S, n, n, dv, dl, None)
+        e4.d2h(c, dv)
+        assert np.array_equal(c, voice)
+        e4.d2h(c, dl)
+        assert np.array_equal(c, sl)
+        for p in (dv, dl, do):
+            e4.device_free(p)
+    finally:
+        e4.close()
+
+
+def test_many_streams_spot_parity(vp, oracle):
+    """A batch wide enough to fill the GPU (1024 streams x 2 s, chain); the oracle checks a spread of streams."""
+    fs, B, S = 44100.0, 1024, 1024
+    n = 86 * B
+    voice, sl, sr = vp.synth_host(fs, S, n, flavour=0, first_stream=0)
+    outL, outR, eng = run_engine(vp, fs, B, voice, sl, None, dict())
+    try:
+        assert np.isfinite(outL).all()
+        tot = flg = 0
+        for s in (0, 1, 255, 256, 511, 777, 1023):
+            r = oracle.run(fs, B, voice[s], sl[s], params=refbind.default_params(), log=True)
+            assert_audio(r["outL"], outL[s], "stream %d" % s)
+            n_, b_, f_, first = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s))
+            assert b_ == 0, "stream %d: %s" % (s, first)
+            tot += n_; flg += f_
+        assert flg <= 2
+        st = eng.stats()
+        assert st["kernel_launches"] >= 10 and st["yin_frames"] == S * len(eng.pitch_frames(0))
+        assert st["yin_rechecked"] < 0.02 * st["yin_frames"]
+    finally:
+        eng.close()
+
+
+def test_errors_are_codes(vp):
+    eng = vp.Engine(44100.0, 1024, 2, 4)
+    try:
+        z = np.zeros((2, 8 * 1024), np.float32)
+        with pytest.raises(vp.EngineError) as ei:
+            eng.process(z, z, z)  # nBlocks 8 > maxBlocks 4
+        assert ei.value.code == vp.VP_E_ARG
+        with pytest.raises(vp.EngineError) as ei:
+            eng.set_params(vp.default_params(lpcVoice=101))
+        assert ei.value.code == vp.VP_E_RANGE
+        with pytest.raises(vp.EngineError) as ei:
+            eng.set_params(vp.default_params(lpcPitch=16))  # read in prepare only (PitchProcess.cpp:70)
+        assert ei.value.code == vp.VP_E_STATE
+    finally:
+        eng.close()

@@ -8,6 +8,8 @@ import os
 
 import numpy as np
 
+from . import shard  # noqa: F401  (stream sharding over GPUs; no data-path collective)
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvp_engine.so")
 
@@ -24,7 +26,8 @@ ABI_SYMBOLS = [
     "vp_engine_process_device", "vp_engine_process_host", "vp_engine_sync", "vp_engine_get_pitch_frames",
     "vp_engine_get_voc_frames", "vp_engine_get_stats", "vp_engine_last_timing", "vp_stage_name",
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
-    "vp_synth_host", "vp_synth_device", "vp_measure_peaks",
+    "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
+    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts",
 ]
 
 
@@ -96,6 +99,10 @@ def load_library(path=None):
         "vp_synth_host": (i, [dbl, i, i, i, sz, sz, fp, fp, fp]),
         "vp_synth_device": (i, [vp, dbl, i, i, i, sz, sz, fp, fp, fp]),
         "vp_measure_peaks": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
+        "vp_engine_timing_reset": (i, [vp, i]),
+        "vp_engine_last_timing_counts": (i, [vp, C.POINTER(i)]),
+        "vp_engine_timer_record": (i, [vp, i]),
+        "vp_engine_timer_elapsed_ms": (i, [vp, i, i, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -293,6 +300,22 @@ class Engine:
         st = (C.c_float * VP_NSTAGES)()
         self._check(self.lib.vp_engine_last_timing(self.h, C.byref(tot), st))
         return tot.value, {self.lib.vp_stage_name(i).decode(): st[i] for i in range(VP_NSTAGES)}
+
+    def last_timing_counts(self):
+        cnt = (C.c_int * VP_NSTAGES)()
+        self._check(self.lib.vp_engine_last_timing_counts(self.h, cnt))
+        return {self.lib.vp_stage_name(i).decode(): cnt[i] for i in range(VP_NSTAGES)}
+
+    def timing_reset(self, accumulate=False):
+        self._check(self.lib.vp_engine_timing_reset(self.h, 1 if accumulate else 0))
+
+    def timer_record(self, slot):
+        self._check(self.lib.vp_engine_timer_record(self.h, int(slot)))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = C.c_float(0)
+        self._check(self.lib.vp_engine_timer_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
+        return ms.value
 
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)

@@ -62,6 +62,9 @@ struct vp_engine {
     size_t evUsed = 0;
     cudaEvent_t evT0 = nullptr, evT1 = nullptr;
     bool stageTiming = false;
+    bool timingOpen = false;
+    bool timingAccumulate = false;  // vp_engine_timing_reset(e, 1): stage times accumulate over calls  // evT0 already recorded since the last vp_engine_timing_reset
+    cudaEvent_t evTimer[8] = {nullptr};
 };
 
 static int vp_fail(vp_engine* e, cudaError_t ce, const char* what, const char* file, int line) {
@@ -241,6 +244,7 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
         cudaEventCreateWithFlags(&e->evComp[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
     }
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&e->evTimer[i]);
     const char* pt = getenv("VP_STAGE_TIMING");
     e->stageTiming = pt && pt[0] == '1';
     *out = e;
@@ -258,6 +262,7 @@ extern "C" void vp_engine_destroy(vp_engine* e) {
     for (auto ev : e->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { cudaEventDestroy(e->evIn[i]); cudaEventDestroy(e->evComp[i]); cudaEventDestroy(e->evOut[i]); }
     cudaEventDestroy(e->evT0); cudaEventDestroy(e->evT1);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(e->evTimer[i]);
     cudaStreamDestroy(e->st); cudaStreamDestroy(e->stIn); cudaStreamDestroy(e->stOut);
     delete e;
 }
@@ -484,9 +489,8 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
     VPGeom g;
     make_geom(e, nBlocks, stride, &g);
     e->lastBlocks = nBlocks;
-    e->evUsed = 0;
     e->passCount = 0;
-    VP_CUDA_OK(cudaEventRecord(e->evT0, e->st));
+    if (!e->timingOpen) { e->evUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
     for (int s0 = 0; s0 < e->S; s0 += e->Sc) {
         const int Sp = std::min(e->Sc, e->S - s0);
         const size_t off = (size_t)s0 * stride;
@@ -531,11 +535,10 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     VPGeom g;
     make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense
     e->lastBlocks = nBlocks;
-    e->evUsed = 0;
     e->passCount = 0;
     const size_t rowB = (size_t)n * sizeof(float);
     int slice = 0;
-    VP_CUDA_OK(cudaEventRecord(e->evT0, e->st));
+    if (!e->timingOpen) { e->evUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
     for (int s0 = 0; s0 < e->S; s0 += e->Sh, ++slice) {
         const int Sp = std::min(e->Sh, e->S - s0);
         const int bi = slice % 3;
@@ -629,6 +632,36 @@ extern "C" int vp_engine_get_stats(const vp_engine* e, uint64_t* launches, uint6
 }
 
 extern "C" const char* vp_stage_name(int stage) { return (stage >= 0 && stage < VP_NSTAGES) ? kStageNames[stage] : ""; }
+
+extern "C" int vp_engine_last_timing_counts(vp_engine* e, int* stageCount) {
+    if (!e || !stageCount) return VP_E_ARG;
+    for (int i = 0; i < VP_NSTAGES; ++i) stageCount[i] = 0;
+    for (size_t i = 1; i < e->evUsed; ++i) stageCount[e->evStage[i]]++;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_timing_reset(vp_engine* e, int accumulate) {
+    if (!e) return VP_E_ARG;
+    e->timingOpen = false;
+    e->timingAccumulate = accumulate != 0;
+    e->evUsed = 0;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_timer_record(vp_engine* e, int slot) {
+    if (!e || slot < 0 || slot >= 8) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaEventRecord(e->evTimer[slot], e->st));
+    return VP_OK;
+}
+
+extern "C" int vp_engine_timer_elapsed_ms(vp_engine* e, int slotA, int slotB, float* ms) {
+    if (!e || !ms || slotA < 0 || slotA >= 8 || slotB < 0 || slotB >= 8) return VP_E_ARG;
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaEventSynchronize(e->evTimer[slotB]));
+    VP_CUDA_OK(cudaEventElapsedTime(ms, e->evTimer[slotA], e->evTimer[slotB]));
+    return VP_OK;
+}
 
 extern "C" int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageMs) {
     if (!e) return VP_E_ARG;
