@@ -143,7 +143,7 @@ int vp_engine_get_stats(const vp_engine* e, uint64_t* kernelLaunches, uint64_t* 
                         uint64_t* yinFrames);
 /* Device time (ms) of the most recent process_device call, measured with
  * CUDA events on the engine's stream; per-stage breakdown optional. */
-#define VP_NSTAGES 12
+#define VP_NSTAGES 16
 int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageMs /* [VP_NSTAGES] or NULL */);
 /* Number of timed intervals (= kernel launches of that stage) behind each stageMs entry. */
 int vp_engine_last_timing_counts(vp_engine* e, int* stageCount /* [VP_NSTAGES] */);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libvp_engine.so")
 
 VP_OK, VP_E_ARG, VP_E_STATE, VP_E_CUDA, VP_E_NOMEM, VP_E_RANGE = 0, -1, -2, -3, -4, -5
 VP_MAX_MARKS = 24
-VP_NSTAGES = 12
+VP_NSTAGES = 16
 PF_GATED, PF_VOICED, PF_HAS_MARKS = 1, 2, 4
 PF_NEAR_GATE, PF_NEAR_YIN, PF_UB, PF_YIN_RECHECKED = 16, 32, 64, 128
 

@@ -75,6 +75,12 @@ void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
 
 void vp_launch_yin(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                    uint32_t* yflags, int* recheckList, int* recheckCount, int maxList);
+// correlation-form YIN (default): chunk partials P [S][3 nFramesP + 1][lagPad] floats, then the per-frame decision
+int vp_yin_corr_lagpad(const VPGeom& g);
+int vp_yin_corr_chunks(const VPGeom& g);
+void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P);
+void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,
+                          int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList);
 void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                            uint32_t* yflags, const int* recheckList, const int* recheckCount, int maxList);
 void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,

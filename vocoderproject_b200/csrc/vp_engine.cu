@@ -13,9 +13,11 @@
 #include "vp_common.cuh"
 #include "vp_synth.h"
 
-enum { ST_GATE = 0, ST_VOC_AC, ST_VOC_LEV, ST_VOC_SYN, ST_YIN, ST_YIN64, ST_MARKS, ST_PFRAME, ST_PIIR, ST_MIX, ST_CLEAR, ST_OTHER };
+enum { ST_GATE = 0, ST_VOC_AC, ST_VOC_LEV, ST_VOC_SYN, ST_YIN, ST_YIN64, ST_MARKS, ST_PFRAME, ST_PIIR, ST_MIX, ST_CLEAR, ST_OTHER,
+       ST_YIN_DECIDE, ST_SPARE1, ST_SPARE2, ST_SPARE3 };
 static const char* kStageNames[VP_NSTAGES] = {"gate", "voc_autocorr", "voc_levinson", "voc_synth", "yin_fp32", "yin_fp64_recheck",
-                                              "marks", "pitch_frame", "pitch_iir", "mix", "clear", "other"};
+                                              "marks", "pitch_frame", "pitch_iir", "mix", "clear", "other",
+                                              "yin_decide", "", "", ""};
 
 struct vp_engine {
     int device = 0;
@@ -40,6 +42,8 @@ struct vp_engine {
     uint32_t* dYFlags = nullptr;
     vp_pitch_frame* dFrames = nullptr;
     double *dAP = nullptr, *dOutE = nullptr;
+    float* dYinP = nullptr;   // correlation-form YIN chunk partials
+    int yinDirect = 0;        // VP_YIN_MODE=direct: FP32 direct-form (a-b)^2 kernel instead
     float *dOutV = nullptr, *dOutP = nullptr;
     int maxList = 0;
     // decisions kept for the whole batch (all S streams) of the last call
@@ -213,7 +217,7 @@ static void free_workspace(vp_engine* e) {
                      (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
                      (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
                      (void**)&e->dOutP, (void**)&e->dFramesAll, (void**)&e->dGateAll, (void**)&e->dEeVAll, (void**)&e->dEeSAll,
-                     (void**)&e->dGAll};
+                     (void**)&e->dGAll, (void**)&e->dYinP};
     for (void** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) if (e->hIn[i][j]) { cudaFree(e->hIn[i][j]); e->hIn[i][j] = nullptr; }
@@ -323,10 +327,18 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     const long long n = (long long)maxBlocks * B;
     int nV, nP;
     frame_counts(z, n, &nV, &nP);
+    {
+        const char* ym = getenv("VP_YIN_MODE");
+        e->yinDirect = (ym && strcmp(ym, "direct") == 0) ? 1 : 0;
+    }
+    VPGeom gy;
+    memset(&gy, 0, sizeof gy);
+    gy.tauMax = z.tauMax; gy.nFramesP = nP;
+    const size_t yinP = e->yinDirect ? 0 : (size_t)vp_yin_corr_chunks(gy) * (size_t)vp_yin_corr_lagpad(gy);
     // bytes of intermediates per stream
     const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(2 * (e->prm.lpcVoice + 1) + 2 * (e->prm.lpcSynth + 1) + 3) +
                              (size_t)nP * (8 + sizeof(vp_pitch_frame) + 8 * (size_t)(e->prm.lpcPitch + 1) + 8 * (size_t)z.frameLenP) +
-                             (size_t)n * 8;
+                             (size_t)n * 8 + yinP * 4;
     if (workspaceBytes == 0) workspaceBytes = (size_t)24 << 30;
     long long Sc = (long long)(workspaceBytes / perStream);
     if (Sc < 1) Sc = 1;
@@ -353,6 +365,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     if ((rc = wsalloc(e, &e->dFrames, fP))) return rc;
     if ((rc = wsalloc(e, &e->dAP, fP * (e->prm.lpcPitch + 1)))) return rc;
     if ((rc = wsalloc(e, &e->dOutE, fP * (size_t)z.frameLenP))) return rc;
+    if ((rc = wsalloc(e, &e->dYinP, (size_t)Sc * yinP))) return rc;
     if ((rc = wsalloc(e, &e->dOutV, (size_t)Sc * n))) return rc;
     if ((rc = wsalloc(e, &e->dOutP, (size_t)Sc * n))) return rc;
     // decisions for all streams (small): frames, gates, energies
@@ -437,8 +450,16 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.n * sizeof(float), st));
         VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
         stage_mark(e, ST_CLEAR);
-        vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-        stage_mark(e, ST_YIN);
+        if (e->yinDirect) {
+            vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+            stage_mark(e, ST_YIN);
+        } else {
+            vp_launch_yin_corr(st, g, Sp, voice, e->dYinP);
+            stage_mark(e, ST_YIN);
+            vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+            stage_mark(e, ST_YIN_DECIDE);
+            e->launches++;
+        }
         vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
         stage_mark(e, ST_YIN64);
         vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);

@@ -213,6 +213,215 @@ void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float*
 }
 
 // ===========================================================================
+// YIN, correlation form (default path). d[k] = A + B(k) - 2 C(k) with
+//   A = sum_{i<L} x[q+i]^2,  B(k) = sum_{i<L} x[q+k+i]^2,  C(k) = sum_{i<L} x[q+i] x[q+k+i]
+// -- one FFMA per (i, k) pair instead of FADD + FFMA, and because hop = 3c and
+// L = 4c (PluginProcessor.cpp:168-170) C(k) splits into four chunk partials
+//   Pm(k) = sum_{j in chunk m} x[j] x[j+k],  chunk m = [m c - tauMax, (m+1) c - tauMax)
+// of which frame f uses m = 3f .. 3f+3 and shares the last with frame f+1:
+// 0.75 L tauMax FFMAs per frame instead of 2 L tauMax lane-ops.
+//   k_yin_corr   : FP32, warp <-> chunk, lane <-> 15 consecutive lags (odd stride: conflict-free
+//                  window loads; the a[n] load is a broadcast), 15-deep register window.
+//   k_yin_decide : one warp per frame, FP64: energies by running sums, CMND, threshold search and
+//                  descent, each deciding comparison checked against a rigorous bound on the FP32
+//                  accumulation error of C(k) (|err d[k]| <= c 2^-24 (A + B(k))); a frame with any
+//                  comparison inside its bound goes to the FP64 direct-form kernel above.
+// ===========================================================================
+#define YC_R 15
+#define YC_LAGS (32 * YC_R)  // lags per warp pass
+#define YC_CH 8              // chunks (= warps) per CTA
+
+__global__ void __launch_bounds__(32 * YC_CH) k_yin_corr(VPGeom g, const float* __restrict__ voice, float* __restrict__ P,
+                                                          int nChunks, int lagPad) {
+    extern __shared__ float xs[];  // [YC_CH * c + lagPad + 16]
+    const int c = g.c, tauMax = g.tauMax;
+    const int s = blockIdx.y;
+    const int m0 = blockIdx.x * YC_CH;
+    const float* v = voice + (size_t)s * g.stride;
+    const long long u0 = (long long)m0 * c - tauMax;  // delayed position of xs[0]
+    const int span = YC_CH * c + lagPad + 16;
+    for (int j = threadIdx.x; j < span; j += blockDim.x) xs[j] = vp_x(v, u0 + j, g.lat, g.n);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = m0 + warp;
+    if (m >= nChunks) return;
+    const float* xa = xs + warp * c;
+    float* out = P + ((size_t)s * nChunks + m) * (size_t)lagPad;
+    for (int k0 = lane * YC_R; k0 < lagPad; k0 += YC_LAGS) {
+        const float* xw = xa + k0;
+        float acc[YC_R], W[YC_R];
+#pragma unroll
+        for (int r = 0; r < YC_R; ++r) { acc[r] = 0.0f; W[r] = xw[r]; }
+        int n = 0;
+        for (; n + YC_R <= c; n += YC_R) {
+#pragma unroll
+            for (int u = 0; u < YC_R; ++u) {
+                const float a = xa[n + u];
+#pragma unroll
+                for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
+                W[u % YC_R] = xw[n + u + YC_R];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < YC_R; ++u) {  // tail: fewer than YC_R samples left
+            const float a = (n + u < c) ? xa[n + u] : 0.0f;
+#pragma unroll
+            for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
+            W[u % YC_R] = xw[n + u + YC_R];
+        }
+#pragma unroll
+        for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc[r];
+    }
+}
+
+#define YD_WARPS 4
+
+__global__ void __launch_bounds__(32 * YD_WARPS) k_yin_decide(VPGeom g, const float* __restrict__ voice,
+                                                              const uint8_t* __restrict__ gate, const float* __restrict__ P,
+                                                              int nChunks, int lagPad, int tauPad, int S,
+                                                              int* __restrict__ period, uint32_t* __restrict__ yflags,
+                                                              int* __restrict__ list, int* __restrict__ listCount, int maxList) {
+    extern __shared__ double smd[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long fidx = (long long)blockIdx.x * YD_WARPS + warp;
+    if (fidx >= (long long)S * g.nFramesP) return;
+    double* dp = smd + (size_t)warp * 2 * tauPad;  // d then d'
+    double* er = dp + tauPad;                      // absolute error bound of d'[k]
+    float* xlo = (float*)(smd + (size_t)YD_WARPS * 2 * tauPad) + (size_t)warp * 2 * tauPad;  // x[q + i], i < tauMax
+    float* xhi = xlo + tauPad;                                                               // x[q + L + i]
+    const int tauMax = g.tauMax, L = g.L, c = g.c;
+    const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
+    const long long p = (long long)f * g.hopP;
+    const int b = (int)(p / g.B);
+    if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {  // gated: yin() is not run (PitchProcess.cpp:208-214)
+        if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; }
+        return;
+    }
+    const float* v = voice + (size_t)s * g.stride;
+    const long long q = p - tauMax;
+    // ---- A = sum x[q+i]^2 (exact products in double), edge samples for the running B(k)
+    double A = 0.0;
+    for (int i = lane; i < L; i += 32) {
+        const float x = vp_x(v, q + i, g.lat, g.n);
+        A = fma((double)x, (double)x, A);
+        if (i < tauMax) xlo[i] = x;
+    }
+    for (int i = lane; i < tauMax; i += 32) xhi[i] = vp_x(v, q + L + i, g.lat, g.n);
+    A = vp_warp_sum(A);
+    // ---- C(k) = four chunk partials
+    const float* P0 = P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad;
+    for (int k = lane; k < tauMax; k += 32) {
+        const double cc = ((double)P0[k] + (double)P0[(size_t)lagPad + k]) + ((double)P0[(size_t)2 * lagPad + k] + (double)P0[(size_t)3 * lagPad + k]);
+        dp[k] = cc;
+    }
+    __syncwarp();
+    // ---- lane owns consecutive lags [kA, kB): B(k) = A + sum_{i<k} (xhi[i]^2 - xlo[i]^2)
+    const int per = (tauMax + 31) / 32;
+    const int kA = lane * per, kB = min(kA + per, tauMax);
+    double locDelta = 0.0;
+    for (int k = kA; k < kB; ++k) { const double h = xhi[k], l = xlo[k]; locDelta += h * h - l * l; }
+    double inc = locDelta;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    double run = inc - locDelta;  // sum of deltas before kA
+    const double beta = (double)c * 5.9604644775390625e-08 * 1.25;  // c * 2^-24, 25 % head room
+    double locD = 0.0, locE = 0.0;
+    for (int k = kA; k < kB; ++k) {
+        const double Bk = A + run;
+        const double h = xhi[k], l = xlo[k];
+        run += h * h - l * l;
+        const double d = (k == 0) ? 0.0 : (A + Bk) - 2.0 * dp[k];
+        const double e = beta * (A + Bk);
+        dp[k] = d;
+        er[k] = e;
+        if (k >= 1) { locD += d; locE += e; }
+    }
+    double incD = locD, incE = locE;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incD, o), t2 = __shfl_up_sync(0xffffffffu, incE, o);
+        if (lane >= o) { incD += t; incE += t2; }
+    }
+    double runD = incD - locD, runE = incE - locE;
+    const double total = __shfl_sync(0xffffffffu, incD, 31);
+    const double energy = __shfl_sync(0xffffffffu, incE, 31);
+    bool shaky = false;  // cumulative sum not resolved against its own error bound
+    for (int k = max(kA, 1); k < kB; ++k) {
+        runD += dp[k];
+        runE += er[k];
+        const double d = dp[k], e = er[k];
+        const double dn = d * ((double)k / runD);  // cumulative mean normalisation (PitchProcess.cpp:396-402)
+        double en;
+        if (runD > 2.0 * runE) en = e * ((double)k / runD) + fabs(dn) * (runE / runD) * 1.01;
+        else { en = 1e300; if (runE > 0.0 && k >= g.tauMin) shaky = true; }
+        dp[k] = dn;
+        er[k] = en;
+    }
+    if (lane == 0) { dp[0] = 1.0; er[0] = 0.0; }
+    __syncwarp();
+    // ---- first tau >= tauMin with d'[tau] < yinTol, then the descent (PitchProcess.cpp:429-440)
+    const double tol = 0.25;
+    int first = 0x7fffffff;
+    for (int k = max(kA, g.tauMin); k < kB; ++k)
+        if (dp[k] < tol) { first = k; break; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    int per_ = 0;
+    unsigned fl = 0;
+    bool unsafe = false;
+    const bool have = (first != 0x7fffffff) && total > 0.0;
+    if (energy > 0.0) {  // all-zero input is exact: d = 0, d' = NaN, unvoiced
+        const int kLast = have ? first : tauMax - 1;
+        for (int k = max(kA, g.tauMin); k < kB && k <= kLast; ++k)
+            if (!(fabs(dp[k] - tol) > er[k])) unsafe = true;
+        if (shaky) unsafe = true;
+    }
+    if (have) {
+        if (first + 1 >= tauMax) fl |= YF_UB;  // U3: reads yinTemp[tauMax]
+        int stop = 0x7fffffff;
+        for (int k = max(kA, first); k < kB; ++k)
+            if (k + 1 >= tauMax || !(dp[k + 1] < dp[k])) { stop = k; break; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) stop = min(stop, __shfl_xor_sync(0xffffffffu, stop, o));
+        per_ = stop;
+        for (int k = max(kA, first); k < kB && k <= stop; ++k)
+            if (k + 1 < tauMax && !(fabs(dp[k + 1] - dp[k]) > er[k] + er[k + 1])) unsafe = true;
+    }
+    unsafe = __any_sync(0xffffffffu, unsafe);
+    if (lane == 0) {
+        if (unsafe) fl |= YF_RECHECK;
+        period[fidx] = per_;
+        yflags[fidx] = fl;
+        if (unsafe) {
+            const int slot = atomicAdd(listCount, 1);
+            if (slot < maxList) list[slot] = (int)fidx;
+        }
+    }
+}
+
+int vp_yin_corr_lagpad(const VPGeom& g) { return (g.tauMax + YC_LAGS - 1) / YC_LAGS * YC_LAGS; }
+int vp_yin_corr_chunks(const VPGeom& g) { return 3 * g.nFramesP + 1; }
+
+void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P) {
+    const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
+    const size_t smem = (size_t)(YC_CH * g.c + lagPad + 16) * sizeof(float);
+    cudaFuncSetAttribute(k_yin_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    dim3 grid((nChunks + YC_CH - 1) / YC_CH, S);
+    k_yin_corr<<<grid, 32 * YC_CH, smem, st>>>(g, voice, P, nChunks, lagPad);
+}
+
+void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,
+                          int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList) {
+    const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
+    const int tauPad = (g.tauMax + 3) & ~3;
+    const size_t smem = (size_t)YD_WARPS * 2 * tauPad * (sizeof(double) + sizeof(float));
+    cudaFuncSetAttribute(k_yin_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const long long tot = (long long)S * g.nFramesP;
+    k_yin_decide<<<(unsigned)((tot + YD_WARPS - 1) / YD_WARPS), 32 * YD_WARPS, smem, st>>>(
+        g, voice, gate, P, nChunks, lagPad, tauPad, S, period, yflags, recheckList, recheckCount, maxList);
+}
+
+// ===========================================================================
 // Pitch-mark chain (PitchProcess.cpp:455-658): sequential over the frames of a
 // stream, so one warp per stream. The four mark vectors are modelled as
 // storage-slot arrays, one slot per lane: push_back writes slot[size],
