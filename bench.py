@@ -295,7 +295,8 @@ def run_engine(args, wl, group):
                   "voc_autocorr": (sm["voc"]["window"] + sm["voc"]["autocorr_voice"] + sm["voc"]["autocorr_synth"]) * frames_v,
                   "voc_levinson": (sm["voc"]["levinson"] + sm["voc"]["fir_voice"] + sm["voc"]["fir_synth"]) * frames_v,
                   "voc_synth": (sm["voc"]["gain"] + sm["voc"]["iir"] + sm["voc"]["ola"] + sm["voc"]["fir_synth"]) * frames_v,
-                  "pitch_frame": (sm["pitch"]["autocorr"] + sm["pitch"]["levinson"] + sm["pitch"]["residual_fir"] + sm["pitch"]["psola"]) * frames_p,
+                  "pitch_lpc": (sm["pitch"]["autocorr"] + sm["pitch"]["levinson"]) * frames_p,
+                  "pitch_psola": (sm["pitch"]["residual_fir"] + sm["pitch"]["psola"]) * frames_p,
                   "pitch_iir": (sm["pitch"]["iir"] + sm["pitch"]["ola"]) * frames_p}.get(kname, 0.0)
         ach = 2.0 * kslots / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
         peak = 2.0 * p32 / 1e12

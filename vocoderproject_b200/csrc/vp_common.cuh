@@ -69,6 +69,7 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
 void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                             const float* synth, const uint8_t* gate, const double* rV, const double* rS, double* aV,
                             double* aS, double* EeV, double* EeS);
+bool vp_voc_synth_needs_clear(const VPGeom& g);  // false: the kernel writes every output position itself
 void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
                          const uint8_t* gate, const double* aV, const double* aS, const double* EeV,
                          const double* EeS, double* gOut, float* outV);
@@ -78,17 +79,19 @@ void vp_launch_yin(cudaStream_t st, const VPGeom& g, int S, const float* voice, 
 // correlation-form YIN (default): chunk partials P [S][3 nFramesP + 1][lagPad] floats, then the per-frame decision
 int vp_yin_corr_lagpad(const VPGeom& g);
 int vp_yin_corr_chunks(const VPGeom& g);
-void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P);
-void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,
+void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech);
+void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P, const double* Ech,
                           int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList);
 void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                            uint32_t* yflags, const int* recheckList, const int* recheckCount, int maxList);
 void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                      const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames);
-void vp_launch_pitch_frame(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
-                           vp_pitch_frame* frames, double* aP, double* outE);
+void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* voice, const vp_pitch_frame* frames,
+                         double* rP, double* aP);
+void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                           vp_pitch_frame* frames, const double* aP, float* outE);
 void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const vp_pitch_frame* frames,
-                         const double* aP, const double* outE, float* outP);
+                         const double* aP, const float* outE, float* outP);
 void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
                    const float* synthR, const float* outV, const float* outP, float* outL, float* outR);
 

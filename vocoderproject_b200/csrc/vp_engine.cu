@@ -14,10 +14,10 @@
 #include "vp_synth.h"
 
 enum { ST_GATE = 0, ST_VOC_AC, ST_VOC_LEV, ST_VOC_SYN, ST_YIN, ST_YIN64, ST_MARKS, ST_PFRAME, ST_PIIR, ST_MIX, ST_CLEAR, ST_OTHER,
-       ST_YIN_DECIDE, ST_SPARE1, ST_SPARE2, ST_SPARE3 };
+       ST_YIN_DECIDE, ST_PLPC, ST_SPARE2, ST_SPARE3 };
 static const char* kStageNames[VP_NSTAGES] = {"gate", "voc_autocorr", "voc_levinson", "voc_synth", "yin_fp32", "yin_fp64_recheck",
-                                              "marks", "pitch_frame", "pitch_iir", "mix", "clear", "other",
-                                              "yin_decide", "", "", ""};
+                                              "marks", "pitch_psola", "pitch_iir", "mix", "clear", "other",
+                                              "yin_decide", "pitch_lpc", "", ""};
 
 struct vp_engine {
     int device = 0;
@@ -41,8 +41,10 @@ struct vp_engine {
     int *dPeriod = nullptr, *dList = nullptr, *dListCount = nullptr;
     uint32_t* dYFlags = nullptr;
     vp_pitch_frame* dFrames = nullptr;
-    double *dAP = nullptr, *dOutE = nullptr;
+    double *dAP = nullptr, *dRP = nullptr;
+    float* dOutE = nullptr;
     float* dYinP = nullptr;   // correlation-form YIN chunk partials
+    double* dYinE = nullptr;  // chunk energies
     int yinDirect = 0;        // VP_YIN_MODE=direct: FP32 direct-form (a-b)^2 kernel instead
     float *dOutV = nullptr, *dOutP = nullptr;
     int maxList = 0;
@@ -217,7 +219,7 @@ static void free_workspace(vp_engine* e) {
                      (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
                      (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
                      (void**)&e->dOutP, (void**)&e->dFramesAll, (void**)&e->dGateAll, (void**)&e->dEeVAll, (void**)&e->dEeSAll,
-                     (void**)&e->dGAll, (void**)&e->dYinP};
+                     (void**)&e->dGAll, (void**)&e->dYinP, (void**)&e->dYinE, (void**)&e->dRP};
     for (void** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) if (e->hIn[i][j]) { cudaFree(e->hIn[i][j]); e->hIn[i][j] = nullptr; }
@@ -337,8 +339,8 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     const size_t yinP = e->yinDirect ? 0 : (size_t)vp_yin_corr_chunks(gy) * (size_t)vp_yin_corr_lagpad(gy);
     // bytes of intermediates per stream
     const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(2 * (e->prm.lpcVoice + 1) + 2 * (e->prm.lpcSynth + 1) + 3) +
-                             (size_t)nP * (8 + sizeof(vp_pitch_frame) + 8 * (size_t)(e->prm.lpcPitch + 1) + 8 * (size_t)z.frameLenP) +
-                             (size_t)n * 8 + yinP * 4;
+                             (size_t)nP * (8 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
+                             (size_t)n * 8 + yinP * 4 + (size_t)(3 * nP + 1) * 8;
     if (workspaceBytes == 0) workspaceBytes = (size_t)24 << 30;
     long long Sc = (long long)(workspaceBytes / perStream);
     if (Sc < 1) Sc = 1;
@@ -364,8 +366,10 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     VP_CUDA_OK(cudaMemset(e->dListCount, 0, 1024 * sizeof(int)));
     if ((rc = wsalloc(e, &e->dFrames, fP))) return rc;
     if ((rc = wsalloc(e, &e->dAP, fP * (e->prm.lpcPitch + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dRP, fP * (e->prm.lpcPitch + 1)))) return rc;
     if ((rc = wsalloc(e, &e->dOutE, fP * (size_t)z.frameLenP))) return rc;
     if ((rc = wsalloc(e, &e->dYinP, (size_t)Sc * yinP))) return rc;
+    if ((rc = wsalloc(e, &e->dYinE, e->yinDirect ? 1 : (size_t)Sc * vp_yin_corr_chunks(gy)))) return rc;
     if ((rc = wsalloc(e, &e->dOutV, (size_t)Sc * n))) return rc;
     if ((rc = wsalloc(e, &e->dOutP, (size_t)Sc * n))) return rc;
     // decisions for all streams (small): frames, gates, energies
@@ -436,8 +440,10 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     e->launches++;
     stage_mark(e, ST_GATE);
     if (g.vocOn) {
-        VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.n * sizeof(float), st));
-        stage_mark(e, ST_CLEAR);
+        if (vp_voc_synth_needs_clear(g)) {
+            VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.n * sizeof(float), st));
+            stage_mark(e, ST_CLEAR);
+        }
         vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
         stage_mark(e, ST_VOC_AC);
         vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
@@ -454,9 +460,9 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
             vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
             stage_mark(e, ST_YIN);
         } else {
-            vp_launch_yin_corr(st, g, Sp, voice, e->dYinP);
+            vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE);
             stage_mark(e, ST_YIN);
-            vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+            vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
             stage_mark(e, ST_YIN_DECIDE);
             e->launches++;
         }
@@ -464,8 +470,11 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         stage_mark(e, ST_YIN64);
         vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
         stage_mark(e, ST_MARKS);
-        vp_launch_pitch_frame(st, g, tb, Sp, voice, e->dFrames, e->dAP, e->dOutE);
+        vp_launch_pitch_lpc(st, g, Sp, voice, e->dFrames, e->dRP, e->dAP);
+        stage_mark(e, ST_PLPC);
+        vp_launch_pitch_psola(st, g, tb, Sp, voice, e->dFrames, e->dAP, e->dOutE);
         stage_mark(e, ST_PFRAME);
+        e->launches += 2;
         vp_launch_pitch_iir(st, g, tb, Sp, e->dFrames, e->dAP, e->dOutE, e->dOutP);
         stage_mark(e, ST_PIIR);
         e->launches += 5;

@@ -3,6 +3,8 @@
 // Reference behaviour: Source/PitchProcess.cpp:166-342 (scheduling, filters),
 // :350-448 (YIN), :455-658 (marks), :665-870 (PSOLA); Source/Notes.cpp:79-110.
 // SURVEY.md App. A.4 / App. B describe the semantics that are restated here.
+#include <algorithm>
+
 #include "vp_common.cuh"
 
 // ===========================================================================
@@ -231,8 +233,10 @@ void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float*
 #define YC_LAGS (32 * YC_R)  // lags per warp pass
 #define YC_CH 8              // chunks (= warps) per CTA
 
+#define YC_SUB (4 * YC_R)    // first-level accumulation length (two-level FP32 summation: tighter error bound)
+
 __global__ void __launch_bounds__(32 * YC_CH) k_yin_corr(VPGeom g, const float* __restrict__ voice, float* __restrict__ P,
-                                                          int nChunks, int lagPad) {
+                                                          double* __restrict__ Ech, int nChunks, int lagPad) {
     extern __shared__ float xs[];  // [YC_CH * c + lagPad + 16]
     const int c = g.c, tauMax = g.tauMax;
     const int s = blockIdx.y;
@@ -247,20 +251,31 @@ __global__ void __launch_bounds__(32 * YC_CH) k_yin_corr(VPGeom g, const float* 
     if (m >= nChunks) return;
     const float* xa = xs + warp * c;
     float* out = P + ((size_t)s * nChunks + m) * (size_t)lagPad;
+    {   // chunk energy sum_j x[j]^2 in FP64 (exact products): A and B(k) of the decision kernel build on it
+        double e2 = 0.0;
+        for (int n = lane; n < c; n += 32) { const double x = (double)xa[n]; e2 = fma(x, x, e2); }
+        e2 = vp_warp_sum(e2);
+        if (lane == 0) Ech[(size_t)s * nChunks + m] = e2;
+    }
     for (int k0 = lane * YC_R; k0 < lagPad; k0 += YC_LAGS) {
         const float* xw = xa + k0;
-        float acc[YC_R], W[YC_R];
+        float acc[YC_R], acc2[YC_R], W[YC_R];
 #pragma unroll
-        for (int r = 0; r < YC_R; ++r) { acc[r] = 0.0f; W[r] = xw[r]; }
+        for (int r = 0; r < YC_R; ++r) { acc[r] = 0.0f; acc2[r] = 0.0f; W[r] = xw[r]; }
         int n = 0;
-        for (; n + YC_R <= c; n += YC_R) {
+        while (n + YC_R <= c) {
+            const int nSub = min(n + YC_SUB, c);
+            for (; n + YC_R <= nSub; n += YC_R) {
 #pragma unroll
-            for (int u = 0; u < YC_R; ++u) {
-                const float a = xa[n + u];
+                for (int u = 0; u < YC_R; ++u) {
+                    const float a = xa[n + u];
 #pragma unroll
-                for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
-                W[u % YC_R] = xw[n + u + YC_R];
+                    for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
+                    W[u % YC_R] = xw[n + u + YC_R];
+                }
             }
+#pragma unroll
+            for (int r = 0; r < YC_R; ++r) { acc2[r] += acc[r]; acc[r] = 0.0f; }
         }
 #pragma unroll
         for (int u = 0; u < YC_R; ++u) {  // tail: fewer than YC_R samples left
@@ -270,15 +285,20 @@ __global__ void __launch_bounds__(32 * YC_CH) k_yin_corr(VPGeom g, const float* 
             W[u % YC_R] = xw[n + u + YC_R];
         }
 #pragma unroll
-        for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc[r];
+        for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc2[r] + acc[r];
     }
+}
+
+// relative bound on |err d[k]| / (A + B(k)): first level <= YC_SUB terms, second level c / YC_SUB + 2 adds, 25 % head room
+__host__ __device__ inline double yin_corr_beta(int c) {
+    return (double)(YC_SUB + c / YC_SUB + 4) * 5.9604644775390625e-08 * 1.25;
 }
 
 #define YD_WARPS 4
 
 __global__ void __launch_bounds__(32 * YD_WARPS) k_yin_decide(VPGeom g, const float* __restrict__ voice,
                                                               const uint8_t* __restrict__ gate, const float* __restrict__ P,
-                                                              int nChunks, int lagPad, int tauPad, int S,
+                                                              const double* __restrict__ Ech, int nChunks, int lagPad, int tauPad, int S,
                                                               int* __restrict__ period, uint32_t* __restrict__ yflags,
                                                               int* __restrict__ list, int* __restrict__ listCount, int maxList) {
     extern __shared__ double smd[];
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(32 * YD_WARPS) k_yin_decide(VPGeom g, const fl
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     double run = inc - locDelta;  // sum of deltas before kA
-    const double beta = (double)c * 5.9604644775390625e-08 * 1.25;  // c * 2^-24, 25 % head room
+    const double beta = yin_corr_beta(c);
     double locD = 0.0, locE = 0.0;
     for (int k = kA; k < kB; ++k) {
         const double Bk = A + run;
@@ -399,26 +419,165 @@ __global__ void __launch_bounds__(32 * YD_WARPS) k_yin_decide(VPGeom g, const fl
     }
 }
 
+// Register-resident decision kernel for tauMax <= 32 * PER: lane owns lags [lane PER, (lane + 1) PER), no shared memory.
+template <int PER>
+__global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* __restrict__ voice, const uint8_t* __restrict__ gate,
+                                                        const float* __restrict__ P, const double* __restrict__ Ech, int nChunks,
+                                                        int lagPad, int S, int* __restrict__ period, uint32_t* __restrict__ yflags,
+                                                        int* __restrict__ list, int* __restrict__ listCount, int maxList) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long fidx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (fidx >= (long long)S * g.nFramesP) return;
+    const int tauMax = g.tauMax, L = g.L;
+    const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
+    const long long p = (long long)f * g.hopP;
+    const int b = (int)(p / g.B);
+    if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {
+        if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; }
+        return;
+    }
+    const float* v = voice + (size_t)s * g.stride;
+    const long long q = p - tauMax;
+    const double* Ec = Ech + (size_t)s * nChunks + (size_t)3 * f;
+    const double A = (Ec[0] + Ec[1]) + (Ec[2] + Ec[3]);
+    const int kA = lane * PER;
+    const float* P0 = P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad + kA;
+    double dn[PER], en[PER];
+    double locDelta = 0.0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int k = kA + j;
+        double dl = 0.0;
+        if (k < tauMax) {
+            const double h = (double)vp_x(v, q + L + k, g.lat, g.n), l = (double)vp_x(v, q + k, g.lat, g.n);
+            dl = h * h - l * l;
+        }
+        en[j] = dl;  // delta for now
+        locDelta += dl;
+        dn[j] = ((double)P0[j] + (double)P0[(size_t)lagPad + j]) + ((double)P0[(size_t)2 * lagPad + j] + (double)P0[(size_t)3 * lagPad + j]);
+    }
+    double inc = locDelta;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    double run = inc - locDelta;
+    const double beta = yin_corr_beta(g.c);
+    double locD = 0.0, locE = 0.0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int k = kA + j;
+        const double Bk = A + run;
+        run += en[j];
+        double d = (A + Bk) - 2.0 * dn[j], e = beta * (A + Bk);
+        if (k == 0 || k >= tauMax) { d = 0.0; e = 0.0; }
+        dn[j] = d;
+        en[j] = e;
+        locD += d;
+        locE += e;
+    }
+    double incD = locD, incE = locE;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incD, o), t2 = __shfl_up_sync(0xffffffffu, incE, o);
+        if (lane >= o) { incD += t; incE += t2; }
+    }
+    double runD = incD - locD, runE = incE - locE;
+    const double total = __shfl_sync(0xffffffffu, incD, 31);
+    const double energy = __shfl_sync(0xffffffffu, incE, 31);
+    bool shaky = false;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int k = kA + j;
+        runD += dn[j];
+        runE += en[j];
+        const double d = dn[j], e = en[j];
+        double x = d * ((double)k / runD), ex;
+        if (runD > 2.0 * runE) ex = e * ((double)k / runD) + fabs(x) * (runE / runD) * 1.01;
+        else { ex = 1e300; if (runE > 0.0 && k >= g.tauMin && k < tauMax) shaky = true; }
+        if (k == 0) { x = 1.0; ex = 0.0; }
+        dn[j] = x;
+        en[j] = ex;
+    }
+    // value at k + 1 of this lane's last lag lives in the next lane
+    const double dnNext = __shfl_down_sync(0xffffffffu, dn[0], 1), enNext = __shfl_down_sync(0xffffffffu, en[0], 1);
+    const double tol = 0.25;
+    int first = 0x7fffffff;
+#pragma unroll
+    for (int j = PER - 1; j >= 0; --j) {
+        const int k = kA + j;
+        if (k >= g.tauMin && k < tauMax && dn[j] < tol) first = k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    int per_ = 0;
+    unsigned fl = 0;
+    bool unsafe = false;
+    const bool have = (first != 0x7fffffff) && total > 0.0;
+    if (energy > 0.0) {
+        const int kLast = have ? first : tauMax - 1;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int k = kA + j;
+            if (k >= g.tauMin && k <= kLast && k < tauMax && !(fabs(dn[j] - tol) > en[j])) unsafe = true;
+        }
+        if (shaky) unsafe = true;
+    }
+    if (have) {
+        if (first + 1 >= tauMax) fl |= YF_UB;
+        int stop = 0x7fffffff;
+#pragma unroll
+        for (int j = PER - 1; j >= 0; --j) {
+            const int k = kA + j;
+            const double nx = (j == PER - 1) ? dnNext : dn[(j + 1) % PER];
+            if (k >= first && k < tauMax && (k + 1 >= tauMax || !(nx < dn[j]))) stop = k;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) stop = min(stop, __shfl_xor_sync(0xffffffffu, stop, o));
+        per_ = stop;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int k = kA + j;
+            const double nx = (j == PER - 1) ? dnNext : dn[(j + 1) % PER];
+            const double ne = (j == PER - 1) ? enNext : en[(j + 1) % PER];
+            if (k >= first && k <= stop && k + 1 < tauMax && !(fabs(nx - dn[j]) > en[j] + ne)) unsafe = true;
+        }
+    }
+    unsafe = __any_sync(0xffffffffu, unsafe);
+    if (lane == 0) {
+        if (unsafe) fl |= YF_RECHECK;
+        period[fidx] = per_;
+        yflags[fidx] = fl;
+        if (unsafe) {
+            const int slot = atomicAdd(listCount, 1);
+            if (slot < maxList) list[slot] = (int)fidx;
+        }
+    }
+}
+
 int vp_yin_corr_lagpad(const VPGeom& g) { return (g.tauMax + YC_LAGS - 1) / YC_LAGS * YC_LAGS; }
 int vp_yin_corr_chunks(const VPGeom& g) { return 3 * g.nFramesP + 1; }
 
-void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P) {
+void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech) {
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
     const size_t smem = (size_t)(YC_CH * g.c + lagPad + 16) * sizeof(float);
     cudaFuncSetAttribute(k_yin_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid((nChunks + YC_CH - 1) / YC_CH, S);
-    k_yin_corr<<<grid, 32 * YC_CH, smem, st>>>(g, voice, P, nChunks, lagPad);
+    k_yin_corr<<<grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad);
 }
 
 void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,
-                          int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList) {
+                          const double* Ech, int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList) {
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
+    const long long tot = (long long)S * g.nFramesP;
+    if (g.tauMax <= 32 * 15) {
+        k_yin_decide_reg<15><<<(unsigned)((tot + 7) / 8), 256, 0, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
+                                                                        recheckList, recheckCount, maxList);
+        return;
+    }
     const int tauPad = (g.tauMax + 3) & ~3;
     const size_t smem = (size_t)YD_WARPS * 2 * tauPad * (sizeof(double) + sizeof(float));
     cudaFuncSetAttribute(k_yin_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const long long tot = (long long)S * g.nFramesP;
     k_yin_decide<<<(unsigned)((tot + YD_WARPS - 1) / YD_WARPS), 32 * YD_WARPS, smem, st>>>(
-        g, voice, gate, P, nChunks, lagPad, tauPad, S, period, yflags, recheckList, recheckCount, maxList);
+        g, voice, gate, P, Ech, nChunks, lagPad, tauPad, S, period, yflags, recheckList, recheckCount, maxList);
 }
 
 // ===========================================================================
@@ -661,74 +820,106 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
 // can only see residual samples up to L + n*c.
 // One CTA per (frame, stream), FP64.
 // ===========================================================================
-#define PF_THREADS 256
-#define PF_R 4
+// Three kernels (no serial section inside a CTA):
+//   k_pitch_autocorr : one warp per frame, FP64, lane = (segment of 16, half of the 16-lag group)
+//   k_pitch_levinson : one thread per frame, order-15 recursion fully in registers
+//   k_pitch_psola    : one 128-thread CTA per frame: residual (register window) then PSOLA, float outE
+#define PA_WARPS 4
+#define PA_SEGS 16
+#define PA_R 8
 
-template <int R>
-__device__ __forceinline__ void pf_ac_task(const double* __restrict__ xd, int n0, int segLen, int m0, int L, double* acc) {
-    // rectangular-window autocorrelation partials: sum_{n in seg} x[n] x[n+m], x = 0 beyond L (padded)
-    double W[R];
+__global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, const float* __restrict__ voice,
+                                                                  const vp_pitch_frame* __restrict__ frames,
+                                                                  double* __restrict__ rP, int segLen, int xdLen, long long nFramesTot) {
+    extern __shared__ double smd[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long fidx = (long long)blockIdx.x * PA_WARPS + warp;
+    if (fidx >= nFramesTot) return;
+    const unsigned flags = frames[fidx].flags;
+    if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return;
+    const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
+    const int L = g.L, ord = g.ordP;
+    double* xd = smd + (size_t)warp * xdLen;  // frame samples as double, zero beyond L (rectangular window, LPC.cpp:44-97)
+    const float* v = voice + (size_t)s * g.stride;
+    const long long p = (long long)f * g.hopP;
+    for (int j = lane; j < xdLen; j += 32) xd[j] = (j < L) ? (double)vp_x(v, p + j, g.lat, g.n) : 0.0;
+    __syncwarp();
+    const int seg = lane & (PA_SEGS - 1), half = lane >> 4;
+    const int n0 = seg * segLen, nEnd = n0 + segLen;
+    double* r = rP + (size_t)fidx * (size_t)(ord + 1);
+    for (int m0 = half * PA_R; m0 <= ord; m0 += 2 * PA_R) {
+        double acc[PA_R], W[PA_R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) { acc[j] = 0.0; W[j] = xd[n0 + m0 + j]; }
-    const int nEnd = n0 + segLen;
-    for (int nb = n0; nb < nEnd; nb += R) {
+        for (int j = 0; j < PA_R; ++j) { acc[j] = 0.0; W[j] = xd[n0 + m0 + j]; }
+        for (int nb = n0; nb < nEnd; nb += PA_R) {
 #pragma unroll
-        for (int u = 0; u < R; ++u) {
-            const int n = nb + u;
-            if (u > 0) W[(u + R - 1) % R] = xd[n + m0 + R - 1];
-            const double a = (n < nEnd) ? xd[n] : 0.0;
+            for (int u = 0; u < PA_R; ++u) {
+                const int n = nb + u;
+                const double a = (n < nEnd) ? xd[n] : 0.0;
 #pragma unroll
-            for (int j = 0; j < R; ++j) acc[j] = fma(a, W[(u + j) % R], acc[j]);
+                for (int j = 0; j < PA_R; ++j) acc[j] = fma(a, W[(u + j) % PA_R], acc[j]);
+                W[u % PA_R] = xd[n + m0 + PA_R];
+            }
         }
-        W[(R - 1) % R] = xd[nb + R + m0 + R - 1];
+#pragma unroll
+        for (int j = 0; j < PA_R; ++j) {
+            double t = acc[j];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            if (seg == 0 && m0 + j <= ord) r[m0 + j] = t / (double)L;
+        }
     }
 }
 
-__global__ void __launch_bounds__(PF_THREADS) k_pitch_frame(VPGeom g, VPTables tb, const float* __restrict__ voice,
-                                                            vp_pitch_frame* __restrict__ frames,
-                                                            double* __restrict__ aP, double* __restrict__ outE,
-                                                            int segLen, int xdLen, int eLen) {
-    extern __shared__ double smd[];
-    const int f = blockIdx.x, s = blockIdx.y;
-    const size_t fidx = (size_t)s * g.nFramesP + f;
-    vp_pitch_frame* rec = frames + fidx;
-    const unsigned flags = rec->flags;
+template <int P>
+__global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch_frame* __restrict__ frames,
+                                                        const double* __restrict__ rP, double* __restrict__ aP, long long nFramesTot) {
+    const long long fidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (fidx >= nFramesTot) return;
+    const unsigned flags = frames[fidx].flags;
     if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return;
-    const int L = g.L, c = g.c, P = g.ordP, tauMax = g.tauMax;
-    double* xd = smd;                 // [xdLen]  frame samples (double), zero padded   -- reused as outE later
-    double* e = xd + xdLen;           // [eLen]   residual, index idx + tauMax, idx in [-tauMax, L + 3c)
-    double* r = e + eLen;             // [P + 1]
-    double* a = r + (VP_ORDER_MAX + 1);  // [P + 1]
-    __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
-    const float* v = voice + (size_t)s * g.stride;
-    const long long p = (long long)f * g.hopP;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = PF_THREADS / 32;
-
-    for (int j = tid; j < xdLen; j += PF_THREADS) xd[j] = (j < L) ? (double)vp_x(v, p + j, g.lat, g.n) : 0.0;
-    if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
-    if (tid == 0) sAn[VP_MAX_MARKS] = 0;
-    __syncthreads();
-    // ---- autocorrelation: warp = lag group (R lags), lane = segment
-    const int G = (P + 1 + PF_R - 1) / PF_R;
-    for (int grp = warp; grp < G; grp += nWarps) {
-        double acc[PF_R];
-        pf_ac_task<PF_R>(xd, lane * segLen, segLen, grp * PF_R, L, acc);
+    constexpr int PM = (P > 0) ? P : VP_ORDER_MAX;
+    const int ord = (P > 0) ? P : g.ordP;
+    double r[PM + 1], a[PM + 1];
+    const double* rp = rP + (size_t)fidx * (size_t)(ord + 1);
+    if (P > 0) {
 #pragma unroll
-        for (int j = 0; j < PF_R; ++j) {
-            const double t = vp_warp_sum(acc[j]);
-            const int m = grp * PF_R + j;
-            if (lane == 0 && m <= P) r[m] = t / (double)L;
-        }
+        for (int m = 0; m <= PM; ++m) r[m] = rp[m];
+    } else {
+        for (int m = 0; m <= ord; ++m) r[m] = rp[m];
     }
-    __syncthreads();
-    // ---- Levinson-Durbin (LPC.cpp:107-148), serial: thread 0
-    if (tid == 0) {
-        a[0] = 1.0;
-        if (fabs(r[0]) < 1e-9) {
-            for (int i = 1; i <= P; ++i) a[i] = 0.0;
+    // Levinson-Durbin (LPC.cpp:107-148)
+    a[0] = 1.0;
+    if (fabs(r[0]) < 1e-9) {
+        if (P > 0) {
+#pragma unroll
+            for (int i = 1; i <= PM; ++i) a[i] = 0.0;
         } else {
-            a[1] = r[1] / r[0];
-            for (int q = 2; q <= P; ++q) {
+            for (int i = 1; i <= ord; ++i) a[i] = 0.0;
+        }
+    } else {
+        a[1] = r[1] / r[0];
+        if (P > 0) {
+#pragma unroll
+            for (int q = 2; q <= PM; ++q) {
+                double rho = 0.0, ra = 0.0;
+#pragma unroll
+                for (int i = 1; i < q; ++i) { rho = fma(r[q - i], a[i], rho); ra = fma(r[i], a[i], ra); }
+                const double k = (r[q] - rho) / (r[0] - ra);
+#pragma unroll
+                for (int i = 1; 2 * i <= q; ++i) {
+                    const double t1 = a[i], t2 = a[q - i];
+                    a[i] = fma(-k, t2, t1);
+                    if (i != q - i) a[q - i] = fma(-k, t1, t2);
+                }
+                a[q] = k;
+            }
+#pragma unroll
+            for (int i = 1; i <= PM; ++i) a[i] = -a[i];
+        } else {
+            for (int q = 2; q <= ord; ++q) {
                 double rho = 0.0, ra = 0.0;
                 for (int i = 1; i < q; ++i) { rho = fma(r[q - i], a[i], rho); ra = fma(r[i], a[i], ra); }
                 const double k = (r[q] - rho) / (r[0] - ra);
@@ -739,30 +930,83 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_frame(VPGeom g, VPTables t
                 }
                 a[q] = k;
             }
-            for (int i = 1; i <= P; ++i) a[i] = -a[i];
+            for (int i = 1; i <= ord; ++i) a[i] = -a[i];
         }
-        double* ap = aP + fidx * (size_t)(P + 1);
-        for (int i = 0; i <= P; ++i) ap[i] = a[i];
+    }
+    double* ap = aP + (size_t)fidx * (size_t)(ord + 1);
+    if (P > 0) {
+#pragma unroll
+        for (int i = 0; i <= PM; ++i) ap[i] = a[i];
+    } else {
+        for (int i = 0; i <= ord; ++i) ap[i] = a[i];
+    }
+}
+
+#define PF_THREADS 128
+#define PF_RJ 11  // residual outputs per thread and pass (odd stride: conflict-free window loads)
+
+// P > 0: LPC order known at compile time (coefficients and the residual window live in registers); P == 0: any order.
+template <int P>
+__global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables tb, const float* __restrict__ voice,
+                                                            vp_pitch_frame* __restrict__ frames,
+                                                            const double* __restrict__ aP, float* __restrict__ outE,
+                                                            int xLen, int eLen) {
+    extern __shared__ double smd[];
+    const int f = blockIdx.x, s = blockIdx.y;
+    const size_t fidx = (size_t)s * g.nFramesP + f;
+    vp_pitch_frame* rec = frames + fidx;
+    const unsigned flags = rec->flags;
+    if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return;
+    const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
+    const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
+    double* e = smd;                    // [eLen] residual, e[j] <-> frame-relative idx j - tauMax
+    float* xf = (float*)(e + eLen);     // [xLen] floats; dead after the residual -> the region is reused as oE [L] doubles
+    double* oE = (double*)xf;
+    __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
+    const float* v = voice + (size_t)s * g.stride;
+    const long long p = (long long)f * g.hopP;
+    const int tid = threadIdx.x;
+
+    for (int j = tid; j < xLen; j += PF_THREADS) xf[j] = vp_x(v, p + (j - X0), g.lat, g.n);
+    if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
+    if (tid == 0) sAn[VP_MAX_MARKS] = 0;
+    const double* ap = aP + fidx * (size_t)(ord + 1);
+    __syncthreads();
+    // ---- residual e[j] = sum_k a[k] x[j - tauMax - k] over frame-relative [-tauMax, L + 3c) (PitchProcess.cpp:280-302)
+    if (P > 0) {
+        constexpr int PP = (P > 0) ? P : 1;
+        double ar[PP + 1];
+#pragma unroll
+        for (int k = 0; k <= PP; ++k) ar[k] = ap[k];
+        for (int j0 = tid * PF_RJ; j0 < eLen; j0 += PF_THREADS * PF_RJ) {
+            double w[PF_RJ + PP];
+#pragma unroll
+            for (int q = 0; q < PF_RJ + PP; ++q) w[q] = (j0 + q < xLen) ? (double)xf[j0 + q] : 0.0;  // x at e-index j0 + q - PP
+#pragma unroll
+            for (int jj = 0; jj < PF_RJ; ++jj) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k <= PP; ++k) acc = fma(ar[k], w[jj + PP - k], acc);
+                if (j0 + jj < eLen) e[j0 + jj] = acc;
+            }
+        }
+    } else {
+        for (int j = tid; j < eLen; j += PF_THREADS) {
+            double acc = 0.0;
+            for (int k = 0; k <= ord; ++k) acc = fma(ap[k], (double)xf[j + ord - k], acc);
+            e[j] = acc;
+        }
     }
     __syncthreads();
-    // ---- residual over frame-relative idx in [-tauMax, L + 3c) (full taps; App. A.4 #4)
-    for (int j = tid; j < eLen; j += PF_THREADS) {
-        const long long u = p + (j - tauMax);
-        double acc = 0.0;
-        for (int k = 0; k <= P; ++k) acc = fma(a[k], (double)vp_x(v, u - k, g.lat, g.n), acc);
-        e[j] = acc;
-    }
-    double* oE = xd;  // reuse
-    __syncthreads();
-    for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;
-    __syncthreads();
-    // ---- PSOLA, chunk by chunk
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
+    for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;  // own indices only (i mod PF_THREADS == tid): no barrier needed
+    bool ub = false;
+    // ---- PSOLA, chunk by chunk (PitchProcess.cpp:665-741, :788-870)
     const double beta = rec->beta;
     const int stale = rec->anStale;
-    bool ub = false;
     if (T > 0 && T < tauMax) {
-        const double* hann = tb.hann + tb.hannOff[T];
+        const double* __restrict__ hs = tb.hann + tb.hannOff[T];  // Hann table of this period (L1/L2 resident)
+        const double invB = 1.0 / beta;
         int stIdx = 0;
         for (int n = 0; n < 4; ++n) {
             const long long Pn = p + (long long)n * c;
@@ -793,9 +1037,10 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_frame(VPGeom g, VPTables t
                 if (cl >= 0) clAn = sAn[cl];
                 else { clAn = 0; ub = true; }  // U2: out-of-bounds prevAnMarks read in the reference
                 const bool first = (stIdx == 0), last = (stIdx == nSt - 1);
-                const double x0 = (double)stMark + (double)(-T) / beta;
-                const double xEnd = (double)stMark + (double)(T) / beta;
-                const int startIdx = max((int)floor(x0), 0);
+                const double dSt = (double)stMark;
+                const double x0 = dSt + (double)(-T) / beta;
+                const double xEnd = dSt + (double)(T) / beta;
+                const int startIdx = max(max((int)floor(x0), 0), nc);  // i < nc: chunk already filtered (App. A.4 #6)
                 const int stopIdx = min((int)ceil(xEnd), L);
                 if (x0 >= 0.0 && x0 == floor(x0)) ub = true;  // U5
                 const int eBase = clAn - T + tauMax;           // e index of grain sample j = 0
@@ -804,51 +1049,72 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_frame(VPGeom g, VPTables t
                 for (int i = (startIdx / PF_THREADS) * PF_THREADS + tid; i < stopIdx; i += PF_THREADS) {
                     const double di = (double)i;
                     if (i < startIdx || !(di >= x0 && di <= xEnd)) continue;
-                    int j = (int)ceil((double)T + (di - (double)stMark) * beta);
+                    // lower_bound over x[j] = stMark + (j - T) / beta (PitchProcess.cpp:850-853): x[j-1] < i <= x[j].
+                    // Positions are evaluated with one multiply by 1/beta; a comparison closer than 1e-9 is
+                    // re-done with the reference's exact division.
+                    int j = (int)ceil((double)T + (di - dSt) * beta);
                     j = max(0, min(j, 2 * T));
-                    // lower_bound on x[j] = stMark + (j - T) / beta (PitchProcess.cpp:850-853)
-                    while (j > 0 && (double)stMark + (double)(j - 1 - T) / beta >= di) --j;
-                    while (j < 2 * T && (double)stMark + (double)(j - T) / beta < di) ++j;
-                    double val;
-                    {
-                        const int ej = eBase + j;
-                        const int rel = clAn - T + j;  // frame-relative index of grain sample j
-                        double y1 = (ej >= 0 && ej < eLen && rel < eValid) ? e[ej] : 0.0;
-                        const bool w1 = (!first && !last) || (first ? (j >= T) : (j < T));
-                        if (w1) y1 *= hann[j];
-                        if (j > 0) {
-                            double y0 = (ej - 1 >= 0 && ej - 1 < eLen && rel - 1 < eValid) ? e[ej - 1] : 0.0;
-                            const bool w0 = (!first && !last) || (first ? (j - 1 >= T) : (j - 1 < T));
-                            if (w0) y0 *= hann[j - 1];
-                            const double xa = (double)stMark + (double)(j - 1 - T) / beta;
-                            const double xb = (double)stMark + (double)(j - T) / beta;
-                            val = y0 + (y1 - y0) / (xb - xa) * (di - xa);
-                        } else val = y1;
+                    double xb = fma((double)(j - T), invB, dSt), xa = fma((double)(j - 1 - T), invB, dSt);
+                    for (;;) {
+                        bool geA = xa >= di, geB = xb >= di;
+                        if (fabs(xa - di) < 1e-9) geA = dSt + (double)(j - 1 - T) / beta >= di;
+                        if (fabs(xb - di) < 1e-9) geB = dSt + (double)(j - T) / beta >= di;
+                        if (j > 0 && geA) { --j; xb = xa; xa = fma((double)(j - 1 - T), invB, dSt); continue; }
+                        if (j < 2 * T && !geB) { ++j; xa = xb; xb = fma((double)(j - T), invB, dSt); continue; }
+                        break;
                     }
-                    if (i >= nc) oE[i] += val;  // earlier chunks were already filtered (App. A.4 #6)
+                    const int ej = eBase + j;
+                    const int rel = clAn - T + j;  // frame-relative index of grain sample j
+                    double y1 = (ej >= 0 && ej < eLen && rel < eValid) ? e[ej] : 0.0;
+                    const bool w1 = (!first && !last) || (first ? (j >= T) : (j < T));
+                    if (w1) y1 *= __ldg(hs + j);
+                    double val = y1;
+                    if (j > 0) {
+                        double y0 = (ej - 1 >= 0 && ej - 1 < eLen && rel - 1 < eValid) ? e[ej - 1] : 0.0;
+                        const bool w0 = (!first && !last) || (first ? (j - 1 >= T) : (j - 1 < T));
+                        if (w0) y0 *= __ldg(hs + j - 1);
+                        val = y0 + (y1 - y0) / (xb - xa) * (di - xa);
+                    }
+                    oE[i] += val;
                 }
                 ++stIdx;
             }
         }
     } else ub = true;
-    __syncthreads();
-    double* dst = outE + fidx * (size_t)L;
-    for (int i = tid; i < L; i += PF_THREADS) dst[i] = oE[i];
+    float* dst = outE + fidx * (size_t)L;
+    for (int i = tid; i < L; i += PF_THREADS) dst[i] = (float)oE[i];  // own indices again
     if (ub && tid == 0) rec->flags = flags | VP_PF_UB;
 }
 
-void vp_launch_pitch_frame(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
-                           vp_pitch_frame* frames, double* aP, double* outE) {
-    int segLen = (g.L + 31) / 32;
-    if ((segLen & 1) == 0) ++segLen;  // odd -> conflict-free 64-bit loads across the 32 segments
-    const int G = (g.ordP + 1 + PF_R - 1) / PF_R;
-    int xdLen = 32 * segLen + G * PF_R + 2 * PF_R + 2;
-    if (xdLen < g.L) xdLen = g.L;
+void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* voice, const vp_pitch_frame* frames,
+                         double* rP, double* aP) {
+    const long long tot = (long long)S * g.nFramesP;
+    int segLen = (g.L + PA_SEGS - 1) / PA_SEGS;
+    if ((segLen & 1) == 0) ++segLen;  // odd -> the 16 segments of a half-warp hit 16 distinct 64-bit banks
+    const int groups = (g.ordP + 1 + 2 * PA_R - 1) / (2 * PA_R);
+    const int xdLen = (PA_SEGS * segLen + 2 * PA_R * groups + 2 * PA_R + 3) & ~1;
+    const size_t smem = (size_t)PA_WARPS * xdLen * sizeof(double);
+    cudaFuncSetAttribute(k_pitch_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_pitch_autocorr<<<(unsigned)((tot + PA_WARPS - 1) / PA_WARPS), 32 * PA_WARPS, smem, st>>>(g, voice, frames, rP, segLen, xdLen, tot);
+    if (g.ordP == 15) k_pitch_levinson<15><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot);
+    else k_pitch_levinson<0><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot);
+}
+
+void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
+                           vp_pitch_frame* frames, const double* aP, float* outE) {
     const int eLen = g.tauMax + g.L + 3 * g.c;
-    const size_t smem = ((size_t)xdLen + eLen + 2 * (VP_ORDER_MAX + 1)) * sizeof(double);
-    cudaFuncSetAttribute(k_pitch_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int xLen = g.tauMax + g.ordP + g.L + 3 * g.c;  // frame-relative [-tauMax - ord, L + 3c)
+    xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
+    xLen = (xLen + 3) & ~3;
+    const size_t smem = (size_t)eLen * sizeof(double) + (size_t)xLen * sizeof(float);
     dim3 grid(g.nFramesP, S);
-    k_pitch_frame<<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, segLen, xdLen, eLen);
+    if (g.ordP == 15) {
+        cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_pitch_psola<15><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen);
+    } else {
+        cudaFuncSetAttribute(k_pitch_psola<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_pitch_psola<0><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen);
+    }
 }
 
 // ===========================================================================
@@ -865,9 +1131,9 @@ void vp_launch_pitch_frame(cudaStream_t st, const VPGeom& g, const VPTables& tb,
 
 template <int P>
 __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables tb, const vp_pitch_frame* __restrict__ frames,
-                                                             const double* __restrict__ aP, const double* __restrict__ outE,
+                                                             const double* __restrict__ aP, const float* __restrict__ outE,
                                                              float* __restrict__ outP, long long nFramesTot) {
-    __shared__ double tin[PI_WARPS][32][33];
+    __shared__ float tin[PI_WARPS][32][33];
     __shared__ float tout[PI_WARPS][32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long f0 = ((long long)blockIdx.x * PI_WARPS + warp) * 32;
@@ -887,9 +1153,8 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
     }
     if (!active) nSteps = 0;
     constexpr int PA = (P > 0) ? P : VP_ORDER_MAX;
-    double a[PA + 1], h[PA];
-    for (int k = 0; k <= PA; ++k) a[k] = 0.0;
-    for (int k = 0; k < PA; ++k) h[k] = 0.0;
+    double a[PA + 1], h[PA + 1];  // P > 0: h[k] = transposed-form state s_{k+1} (h[PA] stays 0); P == 0: circular output history
+    for (int k = 0; k <= PA; ++k) { a[k] = 0.0; h[k] = 0.0; }
     if (active) {
         const double* ap = aP + (size_t)fidx * (order + 1);
         for (int k = 0; k <= order; ++k) a[k] = ap[k];
@@ -907,23 +1172,19 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
         // load: row fr of the tile <- outE[frame f0+fr][i0 .. i0+32)
         for (int fr = 0; fr < 32; ++fr) {
             const int steps = __shfl_sync(0xffffffffu, nSteps, fr);
-            double val = 0.0;
+            float val = 0.0f;
             if (i0 + lane < steps) val = outE[(size_t)(f0 + fr) * L + i0 + lane];
             tin[warp][fr][lane] = val;
         }
         __syncwarp();
-        if (P > 0) {
-            // statically indexed circular history: slab length 32 and order P are unrolled jointly below
-        }
         for (int j = 0; j < 32; ++j) {
             const int i = i0 + j;
-            double acc = tin[warp][lane][j];
+            double acc = (double)tin[warp][lane][j];
             if (P > 0) {
+                // transposed direct form II: y = x + s_1; s_k <- s_{k+1} - a[k] y  (independent DFMAs, no history shift)
+                acc += h[0];
 #pragma unroll
-                for (int k = 1; k <= PA; ++k) acc = fma(-a[k], h[k - 1], acc);
-#pragma unroll
-                for (int k = PA - 1; k > 0; --k) h[k] = h[k - 1];
-                h[0] = acc;
+                for (int k = 0; k < PA; ++k) h[k] = fma(-a[k + 1], acc, h[k + 1]);
             } else {
                 for (int k = 1; k <= order && k <= i; ++k) acc = fma(-a[k], h[(i - k) % order], acc);
                 h[i % order] = acc;
@@ -952,7 +1213,7 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
 }
 
 void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const vp_pitch_frame* frames,
-                         const double* aP, const double* outE, float* outP) {
+                         const double* aP, const float* outE, float* outP) {
     const long long tot = (long long)S * g.nFramesP;
     const unsigned grid = (unsigned)((tot + 32 * PI_WARPS - 1) / (32 * PI_WARPS));
     if (g.ordP == 15) k_pitch_iir<15><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot);

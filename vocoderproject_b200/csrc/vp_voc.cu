@@ -223,12 +223,87 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
     }
 }
 
+// Register-resident specialisation for a compile-time order: r[], a[] and the frame's last P windowed samples are
+// statically indexed (fully unrolled recursion, no local memory). Same operation order as lev_solve / fir_energy.
+template <int P>
+__device__ __forceinline__ double lev_energy_static(const double* __restrict__ rp, double* __restrict__ ap, int wlen,
+                                                    const float* __restrict__ row, long long u0,
+                                                    const double* __restrict__ w, int lat, long long n) {
+    double r[P + 1], a[P + 1];
+#pragma unroll
+    for (int m = 0; m <= P; ++m) r[m] = rp[m];
+    a[0] = 1.0;
+    if (fabs(r[0]) < 1e-9) {
+#pragma unroll
+        for (int i = 1; i <= P; ++i) a[i] = 0.0;
+    } else {
+        a[1] = r[1] / r[0];
+#pragma unroll
+        for (int p = 2; p <= P; ++p) {
+            double rho = 0.0, ra = 0.0;
+#pragma unroll
+            for (int i = 1; i < p; ++i) { rho = fma(r[p - i], a[i], rho); ra = fma(r[i], a[i], ra); }
+            const double k = (r[p] - rho) / (r[0] - ra);
+#pragma unroll
+            for (int i = 1; 2 * i <= p; ++i) {
+                const double t1 = a[i], t2 = a[p - i];
+                a[i] = fma(-k, t2, t1);
+                if (i != p - i) a[p - i] = fma(-k, t1, t2);
+            }
+            a[p] = k;
+        }
+#pragma unroll
+        for (int i = 1; i <= P; ++i) a[i] = -a[i];
+    }
+#pragma unroll
+    for (int m = 0; m <= P; ++m) ap[m] = a[m];
+    double q = r[0];
+#pragma unroll
+    for (int k = 1; k <= P; ++k) q = fma(a[k], r[k], q);
+    double E = q * (double)wlen;
+    double xt[P];  // xt[t] = windowed sample wlen - P + t
+#pragma unroll
+    for (int t = 0; t < P; ++t) {
+        const int j = wlen - P + t;
+        xt[t] = (j >= 0) ? (double)vp_x(row, u0 + j, lat, n) * w[j] : 0.0;
+    }
+    double tail = 0.0;
+#pragma unroll
+    for (int d = 0; d < P; ++d) {
+        double e = 0.0;
+#pragma unroll
+        for (int k = d + 1; k <= P; ++k) e = fma(a[k], xt[P + d - k], e);
+        tail = fma(e, e, tail);
+    }
+    E -= tail;
+    return E > 0.0 ? E : 0.0;
+}
+
+template <int PV, int PS>
+__global__ void __launch_bounds__(64) k_voc_levinson_static(VPGeom g, VPTables tb, const float* __restrict__ voice,
+                                                            const float* __restrict__ synth,
+                                                            const double* __restrict__ rV, const double* __restrict__ rS,
+                                                            double* __restrict__ aV, double* __restrict__ aS,
+                                                            double* __restrict__ EeV, double* __restrict__ EeS, int S) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)S * g.nFramesV) return;
+    const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+    const long long u0 = (long long)k * g.hopV;
+    EeS[idx] = lev_energy_static<PS>(rS + (size_t)idx * (PS + 1), aS + (size_t)idx * (PS + 1), g.wlenV,
+                                     synth + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+    EeV[idx] = lev_energy_static<PV>(rV + (size_t)idx * (PV + 1), aV + (size_t)idx * (PV + 1), g.wlenV,
+                                     voice + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+}
+
 void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                             const float* synth, const uint8_t* gate, const double* rV, const double* rS, double* aV,
                             double* aS, double* EeV, double* EeS) {
     (void)gate;
     const long long tot = (long long)S * g.nFramesV;
-    k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
+    if (g.ordV == 40 && g.ordS == 5 && g.wlenV >= 40)
+        k_voc_levinson_static<40, 5><<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
+    else
+        k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
 }
 
 // ---------------------------------------------------------------------------
@@ -241,17 +316,12 @@ void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb
 // ---------------------------------------------------------------------------
 #define VS_WARPS 2
 
-template <int P>
-struct IirState {
-    double h[P];
-};
-
-// Skewed shared-memory index of tile position pos = lane*hop + i (i < 5*hop):
-// pos + floor(pos / hop), with the division done by compares on the uniform i.
-__device__ __forceinline__ int vs_idx(int lane, int i, int hop) {
-    return lane * hop + i + lane + (i >= hop) + (i >= 2 * hop) + (i >= 3 * hop) + (i >= 4 * hop);
+// Skewed shared-memory index of tile position pos = lane*hop + i: pos + sk * floor(pos / hop), sk = 1 for an even hop
+// (lane stride hop + 1 odd) and 0 for an odd hop (lane stride already odd) -> lanes always hit 32 distinct banks.
+__device__ __forceinline__ int vs_idx(int lane, int i, int hop, int sk) {
+    return lane * hop + i + sk * (lane + (i >= hop) + (i >= 2 * hop) + (i >= 3 * hop) + (i >= 4 * hop));
 }
-__device__ __forceinline__ int vs_skew(int pos, int hop) { return pos + pos / hop; }
+__device__ __forceinline__ int vs_skew(int pos, int hop, int sk) { return pos + sk * (pos / hop); }
 
 // gain of frame k (VocoderProcess.cpp:264-276): sums over the last 10 processed
 // (non-gated) frames, newest to oldest.
@@ -271,6 +341,12 @@ __device__ double voc_gain(const VPGeom& g, const uint8_t* __restrict__ gate, co
     return sqrt(sv / ss);
 }
 
+// All-pole recursion in TRANSPOSED direct form II: with states s_k,
+//   o[i] = g e[i] + s_1,   s_k <- s_{k+1} - a[k] o[i]  (k = 1..P, s_{P+1} = 0)
+// which is algebraically the reference's o[i] = g e[i] - sum_k a[k] o[i-k] (zero initial state) but turns the P-term
+// dot product per sample into P INDEPENDENT DFMAs (one per state register, updated in place): the only chain from one
+// sample to the next is DADD -> DFMA(s_1), so a single warp keeps the FP64 pipe busy. The order-PS whitening FIR of
+// the side-chain runs in the same form (t_q <- t_{q+1} + as[q] x). No history rotation, no unroll-by-order.
 template <int P, int PS>
 __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables tb, const float* __restrict__ synth,
                                                              const uint8_t* __restrict__ gate,
@@ -279,24 +355,30 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables 
                                                              const double* __restrict__ EeV,
                                                              const double* __restrict__ EeS, double* __restrict__ gOut,
                                                              float* __restrict__ outV, int tilesPerStream, int S,
-                                                             int spanPad) {
-    extern __shared__ float smf[];
+                                                             int spanPad, int sk) {
+    extern __shared__ double smd[];
+    const int hop = g.hopV, wlen = g.wlenV;
+    double* wv = smd;                                    // [wlen] synthesis window (uniform reads: broadcast)
+    float* smf = (float*)(smd + ((wlen + 1) & ~1));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < wlen; i += blockDim.x) wv[i] = tb.wV[i];
     const long long tile = (long long)blockIdx.x * VS_WARPS + warp;
     const bool live = tile < (long long)tilesPerStream * S;
     const int s = live ? (int)(tile / tilesPerStream) : 0;
     const int k0 = live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0;
     float* sbuf = smf + (size_t)warp * 2 * spanPad;  // side-chain samples, skewed, origin = u(k0)
     float* obuf = sbuf + spanPad;                    // overlap-add accumulator, skewed, origin = u(k0)
-    const int hop = g.hopV, wlen = g.wlenV;
     const int span = 31 * hop + wlen;                // samples covered by the tile
     const float* y = synth + (size_t)s * g.stride;
     const long long uBase = (long long)k0 * hop;
     if (live) {
-        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop)] = vp_x(y, uBase + i, g.lat, g.n);
-        for (int i = lane; i < span; i += 32) obuf[vs_skew(i, hop)] = 0.0f;
+        for (int i = lane; i < span; i += 32) {
+            const int q = vs_skew(i, hop, sk);
+            sbuf[q] = vp_x(y, uBase + i, g.lat, g.n);
+            obuf[q] = 0.0f;
+        }
     }
-    __syncwarp();
+    __syncthreads();
     const int k = k0 + lane;
     const size_t fidx = (size_t)s * g.nFramesV + k;
     bool active = live && k < g.nFramesV;
@@ -317,48 +399,31 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables 
         for (int j = 0; j <= P; ++j) a[j] = ap[j];
         const double* sp = aS + fidx * (PS + 1);
 #pragma unroll
-        for (int j = 0; j <= PS; ++j) as[j] = sp[j];
+        for (int j = 0; j <= PS; ++j) as[j] = gain * sp[j];  // gain folded into the FIR taps: g sum(as x) = sum((g as) x)
     }
     if (live && k < g.nFramesV && gOut) gOut[fidx] = gain;
-    const double gv = (double)g.gainVocF;
-    double h[P];   // h[j] = out[i0 + j] of the current / previous round (circular, statically indexed)
-    double sw[PS + 1];  // windowed side-chain samples, sw[q] = value at step with (i mod (PS+1)) == q
+    if (__ballot_sync(0xffffffffu, active) != 0u) {
+        const double gv = (double)g.gainVocF;
+        double st[P + 1], t[PS + 1];  // st[k] = s_{k+1}: st[P] stays 0; t likewise
 #pragma unroll
-    for (int j = 0; j < P; ++j) h[j] = 0.0;
+        for (int j = 0; j <= P; ++j) st[j] = 0.0;
 #pragma unroll
-    for (int j = 0; j <= PS; ++j) sw[j] = 0.0;
-    // step i of every lane runs in lock step; rounds of lcm-free static indexing:
-    // the outer loop advances by P steps, the side-chain window is indexed mod (PS+1) dynamically
-    // through a second small unrolled rotation.
-    for (int i0 = 0; i0 < wlen; i0 += P) {
+        for (int j = 0; j <= PS; ++j) t[j] = 0.0;
+        const int base = lane * hop + sk * lane;
+        int q = base, nextHop = hop;
+#pragma unroll 2
+        for (int i = 0; i < wlen; ++i) {
+            if (i == nextHop) { q += sk; nextHop += hop; }
+            const double w = wv[i];
+            const double x = (double)sbuf[q] * w;
+            const double o = fma(as[0], x, t[0]) + st[0];
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            const int i = i0 + j;
-            if (i < wlen) {
-                const double w = tb.wV[i];
-                // rotate the (PS+1)-deep windowed side-chain history: shift is cheap for PS <= 8
+            for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
 #pragma unroll
-                for (int q = PS; q > 0; --q) sw[q] = sw[q - 1];
-                sw[0] = (double)sbuf[vs_idx(lane, i, hop)] * w;
-                double e = 0.0;
-#pragma unroll
-                for (int q = 0; q <= PS; ++q) e = fma(as[q], sw[q], e);  // zero state: sw starts at 0
-                double acc0 = gain * e, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-                for (int kk = P; kk >= 1; --kk) {
-                    const double hv = h[((j - kk) % P + P) % P];
-                    if ((kk & 3) == 0) acc0 = fma(-a[kk], hv, acc0);
-                    else if ((kk & 3) == 1) acc1 = fma(-a[kk], hv, acc1);
-                    else if ((kk & 3) == 2) acc2 = fma(-a[kk], hv, acc2);
-                    else acc3 = fma(-a[kk], hv, acc3);
-                }
-                const double o = (acc0 + acc2) + (acc3 + acc1);
-                h[j] = o;
-                if (active) obuf[vs_idx(lane, i, hop)] += (float)(gv * o * w);
-            }
-            if ((j & 31) == 31) __syncwarp();
+            for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], o, st[kk + 1]);
+            if (active) obuf[q] += (float)(gv * o * w);
+            ++q;
         }
-        __syncwarp();
     }
     __syncwarp();
     if (live) {
@@ -369,10 +434,123 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables 
         for (int i = lane; i < span; i += 32) {
             const long long u = uBase + i;
             if (u >= g.n) break;
-            const float v = obuf[vs_skew(i, hop)];
+            const float v = obuf[vs_skew(i, hop, sk)];
             if (i < ov || i >= 32 * hop) atomicAdd(o + u, v);
             else o[u] = v;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Streaming form of the same stage (default for the plug-in's orders). wlen = 4 hop, so exactly four frames overlap
+// any output position. A group of 4 lanes owns one stream, lane phase phi runs the frames k = phi (mod 4) back to
+// back, and all four lanes step through the SAME output position t in lock step:
+//   * the side-chain sample x[t] is one (broadcast) load for the group -- no staging buffer,
+//   * the overlap-add out[t] = sum of the four lanes' windowed outputs is two xor-shuffles -- no accumulator buffer,
+//     no atomics, no pre-zeroed output, every position written exactly once,
+//   * coefficients are (re)loaded once per frame, states restart at zero (VocoderProcess.cpp:243-247, :280-285).
+// A warp = 8 streams x one segment of frames; a segment starts 3 rows early (the 3 frames that still overlap its first
+// position) and only emits its own positions. No shared memory except the window table; registers hold a[], the
+// transposed-form states and the FIR taps, so several warps per scheduler stay resident.
+// ---------------------------------------------------------------------------
+#define VT_WARPS 2
+
+template <int P, int PS>
+__global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VPTables tb, const float* __restrict__ synth,
+                                                                    const uint8_t* __restrict__ gate,
+                                                                    const double* __restrict__ aV, const double* __restrict__ aS,
+                                                                    const double* __restrict__ EeV, const double* __restrict__ EeS,
+                                                                    double* __restrict__ gOut, float* __restrict__ outV, int S,
+                                                                    int nSeg, int segFrames, int rowPad) {
+    extern __shared__ double wv[];  // window rows: wv[r * rowPad + i] = w[r * hop + i] (row stride odd: 4 phases, 4 banks)
+    const int hop = g.hopV;
+    for (int i = threadIdx.x; i < 4 * hop; i += blockDim.x) wv[(i / hop) * rowPad + (i % hop)] = tb.wV[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * VT_WARPS + warp;
+    const int groups = (S + 7) / 8;
+    if (wid >= (long long)groups * nSeg) return;
+    const int grp = (int)(wid / nSeg), seg = (int)(wid - (long long)grp * nSeg);
+    const int phi = lane & 3;
+    int s = grp * 8 + (lane >> 2);
+    const bool sOk = s < S;
+    if (!sOk) s = S - 1;  // idle group: runs along on a valid stream, stores are masked
+    const int kS = seg * segFrames;
+    if (kS >= g.nFramesV) return;
+    const bool lastSeg = (seg == nSeg - 1) || (kS + segFrames >= g.nFramesV);
+    const int kE = lastSeg ? g.nFramesV : kS + segFrames;
+    const long long emit0 = (long long)kS * hop;
+    const long long emit1 = lastSeg ? g.n : (long long)kE * hop;
+    const int rowEnd = lastSeg ? (int)((g.n + hop - 1) / hop) : kE;  // rows [kS - 3, rowEnd)
+    const float* y = synth + (size_t)s * g.stride;
+    float* o = outV + (size_t)s * g.wstride;
+    const uint8_t* gt = gate + (size_t)s * g.nBlocks;
+    const double* ev = EeV + (size_t)s * g.nFramesV;
+    const double* es = EeS + (size_t)s * g.nFramesV;
+    const double gv = (double)g.gainVocF;
+    double a[P + 1], as[PS + 1], st[P + 1], t[PS + 1];
+#pragma unroll
+    for (int j = 0; j <= P; ++j) { a[j] = 0.0; st[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j <= PS; ++j) { as[j] = 0.0; t[j] = 0.0; }
+    int wrow = 0;  // window row of this lane's current frame in the current hop-row
+    float keep = 0.0f;
+    for (int rho = kS - 3; rho < rowEnd; ++rho) {
+        if (rho < 0) continue;
+        // ---- frame start for the phase that begins at this row
+        if ((rho & 3) == phi) {
+            bool active = rho < g.nFramesV;
+            if (active) {
+                const int b = (int)(((long long)rho * hop) / g.B);
+                if (gt[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) active = false;  // VocoderProcess.cpp:199-204
+            }
+#pragma unroll
+            for (int j = 0; j <= P; ++j) st[j] = 0.0;
+#pragma unroll
+            for (int j = 0; j <= PS; ++j) t[j] = 0.0;
+            double gain = 0.0;
+            if (active) {
+                gain = voc_gain(g, gt, ev, es, rho);
+                const double* ap = aV + ((size_t)s * g.nFramesV + rho) * (P + 1);
+#pragma unroll
+                for (int j = 1; j <= P; ++j) a[j] = ap[j];
+                const double* sp = aS + ((size_t)s * g.nFramesV + rho) * (PS + 1);
+#pragma unroll
+                for (int j = 0; j <= PS; ++j) as[j] = gain * sp[j];
+            } else {
+#pragma unroll
+                for (int j = 1; j <= P; ++j) a[j] = 0.0;
+#pragma unroll
+                for (int j = 0; j <= PS; ++j) as[j] = 0.0;
+            }
+            if (sOk && rho < g.nFramesV && rho >= kS && gOut) gOut[(size_t)s * g.nFramesV + rho] = gain;
+            wrow = 0;
+        }
+        const double* wr = wv + wrow * rowPad;
+        const long long tBase = (long long)rho * hop;
+        const bool emitRow = sOk && rho >= kS;
+#pragma unroll 2
+        for (int i = 0; i < hop; ++i) {
+            const long long tt = tBase + i;
+            const double w = wr[i];
+            const double x = (double)vp_x(y, tt, g.lat, g.n) * w;
+            const double ov = fma(as[0], x, t[0]) + st[0];
+#pragma unroll
+            for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
+#pragma unroll
+            for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
+            float c = (float)(gv * ov * w);
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            const int ph = (int)(tt & 3);
+            if (ph == phi) keep = c;
+            if (ph == 3 || i == hop - 1) {
+                // each lane stores the position of its own phase inside the aligned group of four
+                const long long tp = (tt & ~3LL) + phi;
+                if (emitRow && tp <= tt && tp >= tBase && tp >= emit0 && tp < emit1) o[tp] = keep;
+            }
+        }
+        ++wrow;
     }
 }
 
@@ -385,7 +563,7 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
                                                                      const double* __restrict__ EeV,
                                                                      const double* __restrict__ EeS,
                                                                      double* __restrict__ gOut, float* __restrict__ outV,
-                                                                     int tilesPerStream, int S, int spanPad) {
+                                                                     int tilesPerStream, int S, int spanPad, int sk) {
     extern __shared__ float smf[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tile = (long long)blockIdx.x * VS_WARPS + warp;
@@ -400,8 +578,8 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
     const float* y = synth + (size_t)s * g.stride;
     const long long uBase = (long long)k0 * hop;
     if (live) {
-        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop)] = vp_x(y, uBase + i, g.lat, g.n);
-        for (int i = lane; i < span; i += 32) obuf[vs_skew(i, hop)] = 0.0f;
+        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop, sk)] = vp_x(y, uBase + i, g.lat, g.n);
+        for (int i = lane; i < span; i += 32) obuf[vs_skew(i, hop, sk)] = 0.0f;
     }
     __syncwarp();
     const int k = k0 + lane;
@@ -426,11 +604,11 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
         if (active) {
             double e = 0.0;
             for (int q = 0; q <= PS && q <= i; ++q)
-                e = fma(sp[q], (double)sbuf[vs_idx(lane, i - q, hop)] * tb.wV[i - q], e);
+                e = fma(sp[q], (double)sbuf[vs_idx(lane, i - q, hop, sk)] * tb.wV[i - q], e);
             o = gain * e;
             for (int kk = 1; kk <= P && kk <= i; ++kk) o = fma(-ap[kk], h[(i - kk) % P], o);
             h[i % P] = o;
-            obuf[vs_idx(lane, i, hop)] += (float)(gv * o * w);
+            obuf[vs_idx(lane, i, hop, sk)] += (float)(gv * o * w);
         }
         if ((i & 31) == 31) __syncwarp();
     }
@@ -441,30 +619,41 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
         for (int i = lane; i < span; i += 32) {
             const long long u = uBase + i;
             if (u >= g.n) break;
-            const float v = obuf[vs_skew(i, hop)];
+            const float v = obuf[vs_skew(i, hop, sk)];
             if (i < ov || i >= 32 * hop) atomicAdd(o + u, v);
             else o[u] = v;
         }
     }
 }
 
+bool vp_voc_synth_needs_clear(const VPGeom& g) { return !(g.ordV == 40 && g.ordS == 5); }
+
 void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
                          const uint8_t* gate, const double* aV, const double* aS, const double* EeV,
                          const double* EeS, double* gOut, float* outV) {
+    if (g.ordV == 40 && g.ordS == 5) {
+        const int groups = (S + 7) / 8;
+        int nSeg = (148 * 16 + groups - 1) / groups;                    // ~16 warps per SM in flight over the grid
+        int segFrames = (g.nFramesV + nSeg - 1) / nSeg;
+        if (segFrames < 16) segFrames = 16;                              // keep the 3-row halo a small fraction
+        nSeg = (g.nFramesV + segFrames - 1) / segFrames;
+        const int rowPad = g.hopV | 1;
+        const size_t smem = (size_t)4 * rowPad * sizeof(double);
+        const long long warps = (long long)groups * nSeg;
+        cudaFuncSetAttribute(k_voc_synth_stream<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
+            g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV, S, nSeg, segFrames, rowPad);
+        return;
+    }
     const int tilesPerStream = (g.nFramesV + 31) / 32;
     const int span = 31 * g.hopV + g.wlenV + VP_ORDER_MAX;
+    const int sk = (g.hopV & 1) ? 0 : 1;
     int spanPad = span + span / g.hopV + 8;
     spanPad = (spanPad + 31) & ~31;
-    const size_t smem = (size_t)VS_WARPS * 2 * spanPad * sizeof(float);
     const long long tiles = (long long)tilesPerStream * S;
     const unsigned grid = (unsigned)((tiles + VS_WARPS - 1) / VS_WARPS);
-    if (g.ordV == 40 && g.ordS == 5) {
-        cudaFuncSetAttribute(k_voc_synth<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_voc_synth<40, 5><<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV,
-                                                               tilesPerStream, S, spanPad);
-    } else {
-        cudaFuncSetAttribute(k_voc_synth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV,
-                                                               tilesPerStream, S, spanPad);
-    }
+    const size_t smem = (size_t)VS_WARPS * 2 * spanPad * sizeof(float);
+    cudaFuncSetAttribute(k_voc_synth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV,
+                                                           tilesPerStream, S, spanPad, sk);
 }
