@@ -39,6 +39,30 @@ __device__ __forceinline__ float vp_x(const float* __restrict__ row, long long u
     return (t >= 0 && t < n) ? __ldg(row + t) : 0.0f;
 }
 
+// Cooperative staging of `count` consecutive samples (delayed positions u0 .. u0+count-1) of a stream row into shared
+// memory by `nthr` threads. Loads are issued in batches of UN per thread BEFORE the first store, so a thread has UN
+// global loads in flight instead of one (a plain `for (...) dst[j] = vp_x(...)` loop serialises on the load latency).
+template <int UN, typename T>
+__device__ __forceinline__ void vp_stage(T* __restrict__ dst, const float* __restrict__ row, long long u0, int count,
+                                         int lat, long long n, int tid, int nthr) {
+    const long long t0 = u0 - lat;
+    const bool inside = t0 >= 0 && t0 + count <= n;
+    for (int base = tid; base < count; base += nthr * UN) {
+        float tmp[UN];
+#pragma unroll
+        for (int k = 0; k < UN; ++k) {
+            const int j = base + k * nthr;
+            if (inside) tmp[k] = (j < count) ? __ldg(row + t0 + j) : 0.0f;
+            else { const long long t = t0 + j; tmp[k] = (j < count && t >= 0 && t < n) ? __ldg(row + t) : 0.0f; }
+        }
+#pragma unroll
+        for (int k = 0; k < UN; ++k) {
+            const int j = base + k * nthr;
+            if (j < count) dst[j] = (T)tmp[k];
+        }
+    }
+}
+
 __device__ __forceinline__ double vp_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -341,7 +341,13 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(2 * (e->prm.lpcVoice + 1) + 2 * (e->prm.lpcSynth + 1) + 3) +
                              (size_t)nP * (8 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
                              (size_t)n * 8 + yinP * 4 + (size_t)(3 * nP + 1) * 8;
-    if (workspaceBytes == 0) workspaceBytes = (size_t)24 << 30;
+    if (workspaceBytes == 0) {
+        // default: up to 64 GiB, never more than 40 % of what is free now (the caller's I/O arrays come on top)
+        size_t freeB = 0, totalB = 0;
+        VP_CUDA_OK(cudaMemGetInfo(&freeB, &totalB));
+        workspaceBytes = std::min<size_t>((size_t)64 << 30, (size_t)(0.40 * (double)freeB));
+        if (const char* ws = getenv("VP_WORKSPACE_GB")) workspaceBytes = (size_t)(atof(ws) * 1073741824.0);
+    }
     long long Sc = (long long)(workspaceBytes / perStream);
     if (Sc < 1) Sc = 1;
     if (Sc > S) Sc = S;

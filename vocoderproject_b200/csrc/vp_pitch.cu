@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(32 * YC_CH) k_yin_corr(VPGeom g, const float* 
     const float* v = voice + (size_t)s * g.stride;
     const long long u0 = (long long)m0 * c - tauMax;  // delayed position of xs[0]
     const int span = YC_CH * c + lagPad + 16;
-    for (int j = threadIdx.x; j < span; j += blockDim.x) xs[j] = vp_x(v, u0 + j, g.lat, g.n);
+    vp_stage<6>(xs, v, u0, span, g.lat, g.n, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = m0 + warp;
@@ -589,13 +589,13 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
 // ===========================================================================
 struct ArgMin { float v; int i; };
 
-__device__ __forceinline__ int marks_argmin(const float* __restrict__ v, long long p, int i0, int i1, int lat, long long n,
-                                            int lane) {
-    // first index of the minimum over [i0, i1) (strict '<', PitchProcess.cpp:752-764); empty range -> i0
+__device__ __forceinline__ int marks_argmin(const float* __restrict__ fr, int i0, int i1, int lane) {
+    // first index of the minimum over [i0, i1) (strict '<', PitchProcess.cpp:752-764); empty range -> i0.
+    // fr = the frame's samples staged in shared memory.
     float bv = __int_as_float(0x7f800000);
     int bi = 0x7fffffff;
     for (int i = i0 + lane; i < i1; i += 32) {
-        const float x = vp_x(v, p + i, lat, n);
+        const float x = fr[i];
         if (x < bv) { bv = x; bi = i; }
     }
 #pragma unroll
@@ -611,6 +611,8 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
                                                const uint8_t* __restrict__ gate, const int* __restrict__ periodArr,
                                                const uint32_t* __restrict__ yflags, vp_pitch_frame* __restrict__ frames,
                                                int S) {
+    extern __shared__ float smarks[];  // [warps][L] the current frame's samples (argExt searches hit shared memory)
+    float* fsm = smarks + (size_t)(threadIdx.x >> 5) * g.L;
     const int lane = threadIdx.x & 31;
     const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     if (s >= S) return;
@@ -655,6 +657,11 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
             if (voiced) prevVoicedPeriod = period;
             period = periodArr[fidx];
             voiced = period > 0;
+            if (voiced) {  // only voiced frames search the waveform
+                __syncwarp();
+                vp_stage<12>(fsm, v, p, L, g.lat, g.n, lane, 32);
+                __syncwarp();
+            }
             const uint32_t yf = yflags[fidx];
             if (yf & YF_NEAR) flags |= VP_PF_NEAR_YIN;
             if (yf & YF_UB) ub = true;
@@ -677,24 +684,24 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
                         const int mn = min(prevPeriod, period), mx = max(prevPeriod, period);
                         const int l_lim = max(lastMark + min(sw_c, (int)floor(0.94 * mn)), 0);
                         const int r_lim = min(lastMark + max(sw_f, (int)ceil((2 - 0.94) * mx)), L);
-                        t = marks_argmin(v, p, l_lim, r_lim, g.lat, g.n, lane);
+                        t = marks_argmin(fsm, l_lim, r_lim, lane);
                     } else {
                         t = SLOT(pan, nPan - nAnOv);
                     }
                 } else {
                     searchLeft = true;
-                    t = marks_argmin(v, p, 0, L, g.lat, g.n, lane);
+                    t = marks_argmin(fsm, 0, L, lane);
                 }
                 AN_PUSH(t);
                 for (;;) {
                     const int bk = SLOT(an, nAn - 1);
                     if (!(bk + sw_c < L)) break;
                     if (bk + sw_f < L) {
-                        const int m = marks_argmin(v, p, bk + sw_c, bk + sw_f, g.lat, g.n, lane);
+                        const int m = marks_argmin(fsm, bk + sw_c, bk + sw_f, lane);
                         AN_PUSH(m);
                     } else {
                         if (bk + period < L) {
-                            const int m = marks_argmin(v, p, bk + sw_c, L, g.lat, g.n, lane);
+                            const int m = marks_argmin(fsm, bk + sw_c, L, lane);
                             AN_PUSH(m);
                         }
                         break;
@@ -707,8 +714,8 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
                         if (!(fr - sw_c > 0)) break;
                         int m;
                         bool last = false;
-                        if (fr - sw_f >= 0) m = marks_argmin(v, p, fr - sw_f, fr - sw_c, g.lat, g.n, lane);
-                        else if (fr - period >= 0) { m = marks_argmin(v, p, 0, fr - sw_c, g.lat, g.n, lane); last = true; }
+                        if (fr - sw_f >= 0) m = marks_argmin(fsm, fr - sw_f, fr - sw_c, lane);
+                        else if (fr - period >= 0) { m = marks_argmin(fsm, 0, fr - sw_c, lane); last = true; }
                         else break;
                         // insert(begin): slots [0, nAn) move one to the right
                         if (nAn >= cap) ub = true;
@@ -808,7 +815,8 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
                      const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames) {
     const int threads = 128;
     const long long tot = (long long)S * 32;
-    k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, 0, st>>>(g, tb, voice, gate, period, yflags, frames, S);
+    k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * g.L * sizeof(float), st>>>(
+        g, tb, voice, gate, period, yflags, frames, S);
 }
 
 // ===========================================================================
@@ -842,7 +850,8 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
     double* xd = smd + (size_t)warp * xdLen;  // frame samples as double, zero beyond L (rectangular window, LPC.cpp:44-97)
     const float* v = voice + (size_t)s * g.stride;
     const long long p = (long long)f * g.hopP;
-    for (int j = lane; j < xdLen; j += 32) xd[j] = (j < L) ? (double)vp_x(v, p + j, g.lat, g.n) : 0.0;
+    vp_stage<8>(xd, v, p, L, g.lat, g.n, lane, 32);
+    for (int j = L + lane; j < xdLen; j += 32) xd[j] = 0.0;
     __syncwarp();
     const int seg = lane & (PA_SEGS - 1), half = lane >> 4;
     const int n0 = seg * segLen, nEnd = n0 + segLen;
@@ -868,7 +877,7 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
             t += __shfl_xor_sync(0xffffffffu, t, 2);
             t += __shfl_xor_sync(0xffffffffu, t, 4);
             t += __shfl_xor_sync(0xffffffffu, t, 8);
-            if (seg == 0 && m0 + j <= ord) r[m0 + j] = t / (double)L;
+            if (seg == 0 && m0 + j <= ord) r[m0 + j] = t;  // raw sum; k_pitch_levinson applies the 1/L of LPC.cpp:93-96
         }
     }
 }
@@ -886,9 +895,9 @@ __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch
     const double* rp = rP + (size_t)fidx * (size_t)(ord + 1);
     if (P > 0) {
 #pragma unroll
-        for (int m = 0; m <= PM; ++m) r[m] = rp[m];
+        for (int m = 0; m <= PM; ++m) r[m] = rp[m] / (double)g.L;
     } else {
-        for (int m = 0; m <= ord; ++m) r[m] = rp[m];
+        for (int m = 0; m <= ord; ++m) r[m] = rp[m] / (double)g.L;
     }
     // Levinson-Durbin (LPC.cpp:107-148)
     a[0] = 1.0;
@@ -960,14 +969,15 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
     double* e = smd;                    // [eLen] residual, e[j] <-> frame-relative idx j - tauMax
-    float* xf = (float*)(e + eLen);     // [xLen] floats; dead after the residual -> the region is reused as oE [L] doubles
+    double* hs = e + eLen;              // [2 tauMax + 2] Hann table of this frame's period (PitchProcess.cpp:878-882)
+    float* xf = (float*)(hs + 2 * tauMax + 2);  // [xLen] floats; dead after the residual -> reused as oE [L] doubles
     double* oE = (double*)xf;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
     const float* v = voice + (size_t)s * g.stride;
     const long long p = (long long)f * g.hopP;
     const int tid = threadIdx.x;
 
-    for (int j = tid; j < xLen; j += PF_THREADS) xf[j] = vp_x(v, p + (j - X0), g.lat, g.n);
+    vp_stage<8>(xf, v, p - X0, xLen, g.lat, g.n, tid, PF_THREADS);
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
     if (tid == 0) sAn[VP_MAX_MARKS] = 0;
     const double* ap = aP + fidx * (size_t)(ord + 1);
@@ -1000,12 +1010,16 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
     __syncthreads();
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
     for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;  // own indices only (i mod PF_THREADS == tid): no barrier needed
+    if (T > 0 && T < tauMax) {
+        const double* __restrict__ hg = tb.hann + tb.hannOff[T];
+        for (int i = tid; i < 2 * T + 1; i += PF_THREADS) hs[i] = __ldg(hg + i);
+    }
+    __syncthreads();
     bool ub = false;
     // ---- PSOLA, chunk by chunk (PitchProcess.cpp:665-741, :788-870)
     const double beta = rec->beta;
     const int stale = rec->anStale;
     if (T > 0 && T < tauMax) {
-        const double* __restrict__ hs = tb.hann + tb.hannOff[T];  // Hann table of this period (L1/L2 resident)
         const double invB = 1.0 / beta;
         int stIdx = 0;
         for (int n = 0; n < 4; ++n) {
@@ -1067,13 +1081,13 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
                     const int rel = clAn - T + j;  // frame-relative index of grain sample j
                     double y1 = (ej >= 0 && ej < eLen && rel < eValid) ? e[ej] : 0.0;
                     const bool w1 = (!first && !last) || (first ? (j >= T) : (j < T));
-                    if (w1) y1 *= __ldg(hs + j);
+                    if (w1) y1 *= hs[j];
                     double val = y1;
                     if (j > 0) {
                         double y0 = (ej - 1 >= 0 && ej - 1 < eLen && rel - 1 < eValid) ? e[ej - 1] : 0.0;
                         const bool w0 = (!first && !last) || (first ? (j - 1 >= T) : (j - 1 < T));
-                        if (w0) y0 *= __ldg(hs + j - 1);
-                        val = y0 + (y1 - y0) / (xb - xa) * (di - xa);
+                        if (w0) y0 *= hs[j - 1];
+                        val = y0 + (y1 - y0) * beta * (di - xa);  // 1 / (x[j] - x[j-1]) = beta up to rounding
                     }
                     oE[i] += val;
                 }
@@ -1106,7 +1120,7 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     int xLen = g.tauMax + g.ordP + g.L + 3 * g.c;  // frame-relative [-tauMax - ord, L + 3c)
     xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
     xLen = (xLen + 3) & ~3;
-    const size_t smem = (size_t)eLen * sizeof(double) + (size_t)xLen * sizeof(float);
+    const size_t smem = (size_t)(eLen + 2 * g.tauMax + 2) * sizeof(double) + (size_t)xLen * sizeof(float);
     dim3 grid(g.nFramesP, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -125,7 +125,76 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 #pragma unroll
         for (int j = 0; j < AC_R; ++j) {
             const int m = grp * AC_R + j;
-            if (m <= order) r[m] = acc[j] / (double)g.wlenV;
+            if (m <= order) r[m] = acc[j];  // raw sum; the Levinson kernel applies the 1/wlen of LPC.cpp:93-96
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// v2 (default): one WARP per frame, warps stream over batches of AB consecutive frames of one stream. The raw samples
+// of a batch (span (AB-1) hop + wlen, shared by its frames) are loaded once, coalesced, as floats; each frame then
+// builds its windowed FP64 copies from shared memory (no global latency, no integer division in the staging loop) and
+// runs lane = (segment of 8) x (lag group of 4: voice lags 0-13, 14-27, 28-41, side-chain lags 0-13) with the same
+// register-window task as above. Only warp-level synchronisation.
+// ---------------------------------------------------------------------------
+#define AV_WARPS 4
+#define AV_BATCH 4
+
+__global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTables tb, const float* __restrict__ voice,
+                                                                 const float* __restrict__ synth, double* __restrict__ rV,
+                                                                 double* __restrict__ rS, int segLen, int FS, int rawLen,
+                                                                 int batchesPerStream, int S) {
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * AV_WARPS + warp;
+    if (wid >= (long long)batchesPerStream * S) return;
+    const int s = (int)(wid / batchesPerStream);
+    const int k0 = (int)(wid - (long long)s * batchesPerStream) * AV_BATCH;
+    double* xw = sm + (size_t)warp * (2 * FS + rawLen);  // [FS] voice * window (zero padded)
+    double* sw = xw + FS;                                // [FS] synth ch0 * window
+    float* rawV = (float*)(sw + FS);                     // [rawLen] raw voice of the batch
+    float* rawS = rawV + rawLen;                         // [rawLen] raw synth ch0
+    const float* v = voice + (size_t)s * g.stride;
+    const float* y = synth + (size_t)s * g.stride;
+    const int hop = g.hopV, wlen = g.wlenV;
+    const long long uB = (long long)k0 * hop;
+    const int span = (AV_BATCH - 1) * hop + wlen;
+    vp_stage<8>(rawV, v, uB, span, g.lat, g.n, lane, 32);
+    vp_stage<8>(rawS, y, uB, span, g.lat, g.n, lane, 32);
+    for (int j = wlen + lane; j < FS; j += 32) { xw[j] = 0.0; sw[j] = 0.0; }
+    const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;  // grp 0..2: voice lags 14 grp .., grp 3: side-chain
+    const double* sig = (grp < 3 ? xw : sw);
+    // lag offsets 0 / 13 / 27 (lag 13 computed twice): odd - even offsets inside each half-warp keep the 64-bit window
+    // loads of two groups on disjoint banks (segLen = 2 mod 4 puts the 8 segments on the 8 even / 8 odd banks)
+    const int m0 = (grp == 1) ? AC_R - 1 : (grp == 2) ? 2 * AC_R - 1 : 0;
+    const int order = (grp < 3) ? g.ordV : g.ordS;
+    for (int fb = 0; fb < AV_BATCH; ++fb) {
+        const int k = k0 + fb;
+        if (k >= g.nFramesV) break;
+        __syncwarp();
+        for (int j = lane; j < wlen; j += 32) {
+            const double w = tb.wV[j];
+            xw[j] = (double)rawV[fb * hop + j] * w;
+            sw[j] = (double)rawS[fb * hop + j] * w;
+        }
+        __syncwarp();
+        double acc[AC_R];
+        ac_task<AC_R>(sig, seg * segLen, segLen, m0, acc);
+#pragma unroll
+        for (int j = 0; j < AC_R; ++j) {
+            double a = acc[j];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            acc[j] = a;
+        }
+        if (seg == 0) {
+            double* r = (grp < 3 ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)(order + 1);
+#pragma unroll
+            for (int j = 0; j < AC_R; ++j) {
+                const int m = m0 + j;
+                if (m <= order) r[m] = acc[j];  // raw sum; the Levinson kernel applies the 1/wlen of LPC.cpp:93-96
+            }
         }
     }
 }
@@ -139,6 +208,17 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
+    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1) {
+        FS = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
+        const int rawLen = ((AV_BATCH - 1) * g.hopV + g.wlenV + 3) & ~3;
+        const size_t perWarp = (size_t)(2 * FS + rawLen) * sizeof(double);  // rawLen floats x 2 signals = rawLen doubles
+        const int batchesPerStream = (g.nFramesV + AV_BATCH - 1) / AV_BATCH;
+        const long long warps = (long long)batchesPerStream * S;
+        cudaFuncSetAttribute(k_voc_autocorr2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_voc_autocorr2<<<(unsigned)((warps + AV_WARPS - 1) / AV_WARPS), 32 * AV_WARPS, perWarp * AV_WARPS, st>>>(
+            g, tb, voice, synth, rV, rS, segLen, FS, rawLen, batchesPerStream, S);
+        return;
+    }
     const size_t smem = (size_t)2 * AC_FRAMES * FS * sizeof(double);
     cudaFuncSetAttribute(k_voc_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid((g.nFramesV + AC_FRAMES - 1) / AC_FRAMES, S);
@@ -207,7 +287,7 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
     double r[VP_ORDER_MAX + 1], a[VP_ORDER_MAX + 1];
     {
         const double* rp = rV + (size_t)idx * (g.ordV + 1);
-        for (int m = 0; m <= g.ordV; ++m) r[m] = rp[m];
+        for (int m = 0; m <= g.ordV; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordV);
         double* ap = aV + (size_t)idx * (g.ordV + 1);
         for (int m = 0; m <= g.ordV; ++m) ap[m] = a[m];
@@ -215,7 +295,7 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
     }
     {
         const double* rp = rS + (size_t)idx * (g.ordS + 1);
-        for (int m = 0; m <= g.ordS; ++m) r[m] = rp[m];
+        for (int m = 0; m <= g.ordS; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordS);
         double* ap = aS + (size_t)idx * (g.ordS + 1);
         for (int m = 0; m <= g.ordS; ++m) ap[m] = a[m];
@@ -231,7 +311,7 @@ __device__ __forceinline__ double lev_energy_static(const double* __restrict__ r
                                                     const double* __restrict__ w, int lat, long long n) {
     double r[P + 1], a[P + 1];
 #pragma unroll
-    for (int m = 0; m <= P; ++m) r[m] = rp[m];
+    for (int m = 0; m <= P; ++m) r[m] = rp[m] / (double)wlen;  // biased autocorrelation (LPC.cpp:93-96)
     a[0] = 1.0;
     if (fabs(r[0]) < 1e-9) {
 #pragma unroll
@@ -332,7 +412,7 @@ __device__ double voc_gain(const VPGeom& g, const uint8_t* __restrict__ gate, co
     double sv = 0.0, ss = 0.0;
     int cnt = 0;
     for (int q = k; q >= 0 && cnt < 10; --q) {
-        const int b = (int)(((long long)q * g.hopV) / g.B);
+        const int b = (int)(((unsigned)q * (unsigned)g.hopV) / (unsigned)g.B);  // frame start < 2^31 samples
         if (gate[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) continue;
         sv += EeV[q];
         ss += EeS[q];
@@ -455,6 +535,18 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables 
 // ---------------------------------------------------------------------------
 #define VT_WARPS 2
 
+// four consecutive side-chain samples at delayed positions t .. t+3 (zero outside the call's input)
+__device__ __forceinline__ void vt_load4(const float* __restrict__ row, long long t, int lat, long long n, float* x) {
+    const long long i0 = t - lat;
+    if (i0 >= 0 && i0 + 4 <= n) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = __ldg(row + i0 + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = (i0 + j >= 0 && i0 + j < n) ? __ldg(row + i0 + j) : 0.0f;
+    }
+}
+
 template <int P, int PS>
 __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VPTables tb, const float* __restrict__ synth,
                                                                     const uint8_t* __restrict__ gate,
@@ -494,7 +586,8 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
 #pragma unroll
     for (int j = 0; j <= PS; ++j) { as[j] = 0.0; t[j] = 0.0; }
     int wrow = 0;  // window row of this lane's current frame in the current hop-row
-    float keep = 0.0f;
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};  // prefetched side-chain samples of the next block of four positions
+    bool primed = false;
     for (int rho = kS - 3; rho < rowEnd; ++rho) {
         if (rho < 0) continue;
         // ---- frame start for the phase that begins at this row
@@ -529,25 +622,49 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
         const double* wr = wv + wrow * rowPad;
         const long long tBase = (long long)rho * hop;
         const bool emitRow = sOk && rho >= kS;
-#pragma unroll 2
-        for (int i = 0; i < hop; ++i) {
-            const long long tt = tBase + i;
-            const double w = wr[i];
-            const double x = (double)vp_x(y, tt, g.lat, g.n) * w;
-            const double ov = fma(as[0], x, t[0]) + st[0];
+        if (!primed) { vt_load4(y, tBase, g.lat, g.n, xn); primed = true; }
+        for (int i0 = 0; i0 < hop; i0 += 4) {
+            float xc[4];
+            double wc[4];
 #pragma unroll
-            for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
+            for (int j = 0; j < 4; ++j) { xc[j] = xn[j]; wc[j] = wr[min(i0 + j, hop - 1)]; }
+            // software prefetch: the samples of the next block (positions are contiguous across rows)
+            vt_load4(y, (i0 + 4 < hop) ? tBase + i0 + 4 : tBase + hop, g.lat, g.n, xn);
+            const int nb = min(4, hop - i0);
+            // ---- all FP64 work of the block first (straight-line, so the scheduler can overlap the steps) ...
+            double e[4];
 #pragma unroll
-            for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
-            float c = (float)(gv * ov * w);
-            c += __shfl_xor_sync(0xffffffffu, c, 1);
-            c += __shfl_xor_sync(0xffffffffu, c, 2);
-            const int ph = (int)(tt & 3);
-            if (ph == phi) keep = c;
-            if (ph == 3 || i == hop - 1) {
-                // each lane stores the position of its own phase inside the aligned group of four
-                const long long tp = (tt & ~3LL) + phi;
-                if (emitRow && tp <= tt && tp >= tBase && tp >= emit0 && tp < emit1) o[tp] = keep;
+            for (int j = 0; j < 4; ++j) {  // whitening FIR of the side-chain, transposed form (independent of the IIR state)
+                e[j] = 0.0;
+                if (j < nb) {
+                    const double x = (double)xc[j] * wc[j];
+                    e[j] = fma(as[0], x, t[0]);
+#pragma unroll
+                    for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
+                }
+            }
+            float c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nb) {
+                    const double ov = e[j] + st[0];
+#pragma unroll
+                    for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
+                    c[j] = (float)(gv * ov * wc[j]);
+                } else c[j] = 0.0f;
+            }
+            // ---- ... then the overlap-add of the 4 phase lanes for the 4 positions: transpose-reduce, 3 shuffles.
+            // lane phi ends with sum over the group of c[phi].
+            {
+                const bool hi = (phi & 2) != 0, od = (phi & 1) != 0;
+                const float s0 = hi ? c[0] : c[2], s1 = hi ? c[1] : c[3];   // send the pair the partner (xor 2) is responsible for
+                const float k0 = hi ? c[2] : c[0], k1 = hi ? c[3] : c[1];   // keep the own pair
+                const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+                const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+                const float snd = od ? r0 : r1, kp = od ? r1 : r0;
+                const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+                const long long tp = tBase + i0 + phi;
+                if (emitRow && phi < nb && tp >= emit0 && tp < emit1) o[tp] = tot;
             }
         }
         ++wrow;
