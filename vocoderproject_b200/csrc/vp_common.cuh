@@ -63,6 +63,13 @@ __device__ __forceinline__ void vp_stage(T* __restrict__ dst, const float* __res
     }
 }
 
+// x / d for a divisor d that is reused many times: with inv = RN(1 / d), q = RN(x inv) is within 1 ulp of x / d and
+// q' = fma(fma(-q, d, x), inv, q) is the correctly rounded quotient (Markstein) -- bit-identical to x / d, 3 FP64 ops.
+__device__ __forceinline__ double vp_div_const(double x, double d, double inv) {
+    const double q = x * inv;
+    return fma(fma(-q, d, x), inv, q);
+}
+
 __device__ __forceinline__ double vp_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

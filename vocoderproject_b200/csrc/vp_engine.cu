@@ -23,6 +23,11 @@ struct vp_engine {
     int device = 0;
     bool prepared = false;
     cudaStream_t st = nullptr, stIn = nullptr, stOut = nullptr;
+    cudaStream_t st2 = nullptr;   // the sequential pitch-mark chain runs here, under the vocoder kernels of the same pass
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    std::vector<cudaEvent_t> evSide;  // (start, end) pairs of the side-stream kernel when stage timing is on
+    size_t evSideUsed = 0;
+    bool overlapMarks = true;
     std::string err;
     vp_params prm;
     vp_sizes sz;
@@ -240,6 +245,9 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stIn, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stOut, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&e->evT0) != cudaSuccess || cudaEventCreate(&e->evT1) != cudaSuccess) {
         cudaGetLastError();
         delete e;
@@ -251,6 +259,7 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
         cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
     }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&e->evTimer[i]);
+    { const char* ov = getenv("VP_OVERLAP"); e->overlapMarks = !(ov && ov[0] == '0'); }
     const char* pt = getenv("VP_STAGE_TIMING");
     e->stageTiming = pt && pt[0] == '1';
     *out = e;
@@ -269,7 +278,9 @@ extern "C" void vp_engine_destroy(vp_engine* e) {
     for (int i = 0; i < 3; ++i) { cudaEventDestroy(e->evIn[i]); cudaEventDestroy(e->evComp[i]); cudaEventDestroy(e->evOut[i]); }
     cudaEventDestroy(e->evT0); cudaEventDestroy(e->evT1);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(e->evTimer[i]);
-    cudaStreamDestroy(e->st); cudaStreamDestroy(e->stIn); cudaStreamDestroy(e->stOut);
+    for (auto ev : e->evSide) cudaEventDestroy(ev);
+    cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin);
+    cudaStreamDestroy(e->st); cudaStreamDestroy(e->stIn); cudaStreamDestroy(e->stOut); cudaStreamDestroy(e->st2);
     delete e;
 }
 
@@ -414,6 +425,16 @@ static void stage_mark(vp_engine* e, int stage) {
     cudaEventRecord(e->ev[e->evUsed++], e->st);
 }
 
+static void side_mark(vp_engine* e) {
+    if (!e->stageTiming) return;
+    if (e->evSideUsed >= e->evSide.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->evSide.push_back(ev);
+    }
+    cudaEventRecord(e->evSide[e->evSideUsed++], e->st2);
+}
+
 static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     const vp_sizes& z = e->sz;
     memset(g, 0, sizeof *g);
@@ -445,19 +466,9 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     vp_launch_gate(st, g, Sp, voice, synthL, e->dGate);
     e->launches++;
     stage_mark(e, ST_GATE);
-    if (g.vocOn) {
-        if (vp_voc_synth_needs_clear(g)) {
-            VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.n * sizeof(float), st));
-            stage_mark(e, ST_CLEAR);
-        }
-        vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
-        stage_mark(e, ST_VOC_AC);
-        vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
-        stage_mark(e, ST_VOC_LEV);
-        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dGate, e->dAV, e->dAS, e->dEeV, e->dEeS, e->dG, e->dOutV);
-        stage_mark(e, ST_VOC_SYN);
-        e->launches += 3;
-    }
+    // Order: YIN -> [side stream: pitch-mark chain, sequential per stream, latency-bound, few warps] running UNDER
+    // [main stream: the three vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.
+    bool forked = false;
     if (g.pitchOn) {
         VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.n * sizeof(float), st));
         VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
@@ -474,16 +485,46 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         }
         vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
         stage_mark(e, ST_YIN64);
-        vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
-        stage_mark(e, ST_MARKS);
+        e->launches += 2;
+        if (e->overlapMarks && g.vocOn) {
+            VP_CUDA_OK(cudaEventRecord(e->evFork, st));
+            VP_CUDA_OK(cudaStreamWaitEvent(e->st2, e->evFork, 0));
+            side_mark(e);
+            vp_launch_marks(e->st2, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
+            side_mark(e);
+            VP_CUDA_OK(cudaEventRecord(e->evJoin, e->st2));
+            forked = true;
+        } else {
+            vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
+            stage_mark(e, ST_MARKS);
+        }
+        e->launches++;
+    }
+    if (g.vocOn) {
+        if (vp_voc_synth_needs_clear(g)) {
+            VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.n * sizeof(float), st));
+            stage_mark(e, ST_CLEAR);
+        }
+        vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
+        stage_mark(e, ST_VOC_AC);
+        vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
+        stage_mark(e, ST_VOC_LEV);
+        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dGate, e->dAV, e->dAS, e->dEeV, e->dEeS, e->dG, e->dOutV);
+        stage_mark(e, ST_VOC_SYN);
+        e->launches += 3;
+    }
+    if (g.pitchOn) {
+        if (forked) {
+            VP_CUDA_OK(cudaStreamWaitEvent(st, e->evJoin, 0));
+            stage_mark(e, ST_OTHER);  // whatever of the mark chain was not hidden under the vocoder kernels
+        }
         vp_launch_pitch_lpc(st, g, Sp, voice, e->dFrames, e->dRP, e->dAP);
         stage_mark(e, ST_PLPC);
         vp_launch_pitch_psola(st, g, tb, Sp, voice, e->dFrames, e->dAP, e->dOutE);
         stage_mark(e, ST_PFRAME);
-        e->launches += 2;
         vp_launch_pitch_iir(st, g, tb, Sp, e->dFrames, e->dAP, e->dOutE, e->dOutP);
         stage_mark(e, ST_PIIR);
-        e->launches += 5;
+        e->launches += 4;
         e->yinFrames += fP;
     }
     vp_launch_mix(st, g, Sp, voice, synthL, synthR, e->dOutV, e->dOutP, outL, outR);
@@ -526,7 +567,7 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
     make_geom(e, nBlocks, stride, &g);
     e->lastBlocks = nBlocks;
     e->passCount = 0;
-    if (!e->timingOpen) { e->evUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
+    if (!e->timingOpen) { e->evUsed = 0; e->evSideUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
     for (int s0 = 0; s0 < e->S; s0 += e->Sc) {
         const int Sp = std::min(e->Sc, e->S - s0);
         const size_t off = (size_t)s0 * stride;
@@ -542,6 +583,7 @@ extern "C" int vp_engine_sync(vp_engine* e) {
     if (!e) return VP_E_ARG;
     VP_CUDA_OK(cudaSetDevice(e->device));
     VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st2));
     VP_CUDA_OK(cudaStreamSynchronize(e->stIn));
     VP_CUDA_OK(cudaStreamSynchronize(e->stOut));
     return VP_OK;
@@ -574,7 +616,7 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     e->passCount = 0;
     const size_t rowB = (size_t)n * sizeof(float);
     int slice = 0;
-    if (!e->timingOpen) { e->evUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
+    if (!e->timingOpen) { e->evUsed = 0; e->evSideUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
     for (int s0 = 0; s0 < e->S; s0 += e->Sh, ++slice) {
         const int Sp = std::min(e->Sh, e->S - s0);
         const int bi = slice % 3;
@@ -673,6 +715,7 @@ extern "C" int vp_engine_last_timing_counts(vp_engine* e, int* stageCount) {
     if (!e || !stageCount) return VP_E_ARG;
     for (int i = 0; i < VP_NSTAGES; ++i) stageCount[i] = 0;
     for (size_t i = 1; i < e->evUsed; ++i) stageCount[e->evStage[i]]++;
+    stageCount[ST_MARKS] += (int)(e->evSideUsed / 2);
     return VP_OK;
 }
 
@@ -681,6 +724,7 @@ extern "C" int vp_engine_timing_reset(vp_engine* e, int accumulate) {
     e->timingOpen = false;
     e->timingAccumulate = accumulate != 0;
     e->evUsed = 0;
+    e->evSideUsed = 0;
     return VP_OK;
 }
 
@@ -710,6 +754,12 @@ extern "C" int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageM
         for (size_t i = 1; i < e->evUsed; ++i) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, e->ev[i - 1], e->ev[i]) == cudaSuccess) stageMs[e->evStage[i]] += ms;
+        }
+        // the pitch-mark chain on the side stream: its own (start, end) pairs; it overlaps the vocoder stages
+        for (size_t i = 1; i < e->evSideUsed; i += 2) {
+            float ms = 0.f;
+            cudaEventSynchronize(e->evSide[i]);
+            if (cudaEventElapsedTime(&ms, e->evSide[i - 1], e->evSide[i]) == cudaSuccess) stageMs[ST_MARKS] += ms;
         }
     }
     return VP_OK;

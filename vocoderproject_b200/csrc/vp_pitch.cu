@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch
     const double* rp = rP + (size_t)fidx * (size_t)(ord + 1);
     if (P > 0) {
 #pragma unroll
-        for (int m = 0; m <= PM; ++m) r[m] = rp[m] / (double)g.L;
+        for (int m = 0; m <= PM; ++m) r[m] = vp_div_const(rp[m], (double)g.L, 1.0 / (double)g.L);
     } else {
         for (int m = 0; m <= ord; ++m) r[m] = rp[m] / (double)g.L;
     }
@@ -1020,7 +1020,6 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
     const double beta = rec->beta;
     const int stale = rec->anStale;
     if (T > 0 && T < tauMax) {
-        const double invB = 1.0 / beta;
         int stIdx = 0;
         for (int n = 0; n < 4; ++n) {
             const long long Pn = p + (long long)n * c;
@@ -1063,20 +1062,14 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
                 for (int i = (startIdx / PF_THREADS) * PF_THREADS + tid; i < stopIdx; i += PF_THREADS) {
                     const double di = (double)i;
                     if (i < startIdx || !(di >= x0 && di <= xEnd)) continue;
-                    // lower_bound over x[j] = stMark + (j - T) / beta (PitchProcess.cpp:850-853): x[j-1] < i <= x[j].
-                    // Positions are evaluated with one multiply by 1/beta; a comparison closer than 1e-9 is
-                    // re-done with the reference's exact division.
-                    int j = (int)ceil((double)T + (di - dSt) * beta);
+                    // interp() (PitchProcess.cpp:842-870): lower_bound j over x[j] = stMark + (j - T) / beta, then linear
+                    // interpolation between grain samples j-1 and j. In grain coordinates tg = T + (i - stMark) beta the
+                    // bound is j = ceil(tg) and the weight (i - x[j-1]) / (x[j] - x[j-1]) = tg - (j - 1). The interpolant
+                    // is continuous in tg, so a lower_bound that differs from the reference's when tg is within rounding of
+                    // an integer changes the value by O(1e-13) only.
+                    const double tg = fma(di - dSt, beta, (double)T);
+                    int j = (int)ceil(tg);
                     j = max(0, min(j, 2 * T));
-                    double xb = fma((double)(j - T), invB, dSt), xa = fma((double)(j - 1 - T), invB, dSt);
-                    for (;;) {
-                        bool geA = xa >= di, geB = xb >= di;
-                        if (fabs(xa - di) < 1e-9) geA = dSt + (double)(j - 1 - T) / beta >= di;
-                        if (fabs(xb - di) < 1e-9) geB = dSt + (double)(j - T) / beta >= di;
-                        if (j > 0 && geA) { --j; xb = xa; xa = fma((double)(j - 1 - T), invB, dSt); continue; }
-                        if (j < 2 * T && !geB) { ++j; xa = xb; xb = fma((double)(j - T), invB, dSt); continue; }
-                        break;
-                    }
                     const int ej = eBase + j;
                     const int rel = clAn - T + j;  // frame-relative index of grain sample j
                     double y1 = (ej >= 0 && ej < eLen && rel < eValid) ? e[ej] : 0.0;
@@ -1087,7 +1080,8 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
                         double y0 = (ej - 1 >= 0 && ej - 1 < eLen && rel - 1 < eValid) ? e[ej - 1] : 0.0;
                         const bool w0 = (!first && !last) || (first ? (j - 1 >= T) : (j - 1 < T));
                         if (w0) y0 *= hs[j - 1];
-                        val = y0 + (y1 - y0) * beta * (di - xa);  // 1 / (x[j] - x[j-1]) = beta up to rounding
+                        const double frac = fmin(fmax(tg - (double)(j - 1), 0.0), 1.0);
+                        val = fma(y1 - y0, frac, y0);
                     }
                     oE[i] += val;
                 }

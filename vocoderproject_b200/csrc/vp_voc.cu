@@ -310,8 +310,9 @@ __device__ __forceinline__ double lev_energy_static(const double* __restrict__ r
                                                     const float* __restrict__ row, long long u0,
                                                     const double* __restrict__ w, int lat, long long n) {
     double r[P + 1], a[P + 1];
+    const double dw = (double)wlen, iw = 1.0 / dw;
 #pragma unroll
-    for (int m = 0; m <= P; ++m) r[m] = rp[m] / (double)wlen;  // biased autocorrelation (LPC.cpp:93-96)
+    for (int m = 0; m <= P; ++m) r[m] = vp_div_const(rp[m], dw, iw);  // biased autocorrelation: r / wlen (LPC.cpp:93-96)
     a[0] = 1.0;
     if (fabs(r[0]) < 1e-9) {
 #pragma unroll
