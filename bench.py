@@ -312,6 +312,7 @@ def run_engine(args, wl, group):
                     "hbm": {"achieved_gbs": io_bytes / dev_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src,
                             "frac": io_bytes / dev_s / 1e9 / peaks.get("hbm_gbs", 1.0), "algorithmic_bytes_per_sample": 12},
                     "fp64_fma_per_s": peaks_fp["fp64_fma_per_s"], "fp32_fma_per_s": p32,
+                    "fp32_fma_2op_per_s": peaks_fp.get("fp32_fma_2op_per_s"), "fp64_fma_2op_per_s": peaks_fp.get("fp64_fma_2op_per_s"),
                     "stage_ms": {k: round(v, 3) for k, v in stage_ms.items() if v > 0}, "stage_launches": {k: v for k, v in stage_cnt.items() if v}}
         line = {"metric": "audio-sec/sec (streams x RT)", "value": value, "unit": "audio-s/s", "n_gpus": group.world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -177,6 +177,9 @@ int vp_synth_device(vp_engine* e, double sampleRate, int flavour, int firstStrea
 /* Issue-rate microbenchmarks on the engine's device: FP32 FMA and FP64 FMA
  * lane-operations per second (the roofline denominators of DESIGN.md). */
 int vp_measure_peaks(vp_engine* e, double* fp32FmaPerSec, double* fp64FmaPerSec);
+/* Same, with the operand pattern of the engine's inner loops (acc_i = fma(x, b_i, acc_i): two distinct register
+ * operands per FMA instead of one) -- the rate a real multiply-accumulate loop can reach. */
+int vp_measure_peaks2(vp_engine* e, double* fp32FmaPerSec, double* fp64FmaPerSec);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "vp_engine_get_voc_frames", "vp_engine_get_stats", "vp_engine_last_timing", "vp_stage_name",
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
-    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts",
+    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2",
 ]
 
 
@@ -100,6 +100,7 @@ def load_library(path=None):
         "vp_synth_device": (i, [vp, dbl, i, i, i, sz, sz, fp, fp, fp]),
         "vp_measure_peaks": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "vp_engine_timing_reset": (i, [vp, i]),
+        "vp_measure_peaks2": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "vp_engine_last_timing_counts": (i, [vp, C.POINTER(i)]),
         "vp_engine_timer_record": (i, [vp, i]),
         "vp_engine_timer_elapsed_ms": (i, [vp, i, i, C.POINTER(C.c_float)]),
@@ -320,4 +321,6 @@ class Engine:
     def measure_peaks(self):
         a, b = C.c_double(0), C.c_double(0)
         self._check(self.lib.vp_measure_peaks(self.h, C.byref(a), C.byref(b)))
-        return {"fp32_fma_per_s": a.value, "fp64_fma_per_s": b.value}
+        c2, d2 = C.c_double(0), C.c_double(0)
+        self._check(self.lib.vp_measure_peaks2(self.h, C.byref(c2), C.byref(d2)))
+        return {"fp32_fma_per_s": a.value, "fp64_fma_per_s": b.value, "fp32_fma_2op_per_s": c2.value, "fp64_fma_2op_per_s": d2.value}

@@ -28,6 +28,10 @@ struct VPGeom {
     double yinEps;  // relative margin below which the FP32 YIN decision is re-done in FP64
 };
 
+// Per-frame row of the vocoder's autocorrelation workspace: lags 0..order (raw sums) followed by the frame's last
+// `order` windowed samples (the Levinson kernel's residual-energy correction reads them instead of re-gathering).
+__host__ __device__ inline int vp_row(int order) { return 2 * order + 1; }
+
 // gate flags per (stream, block)
 #define VP_GATE_VOICE 1
 #define VP_GATE_SYNTH 2
@@ -130,3 +134,5 @@ void vp_launch_synth(cudaStream_t st, const void* streams, int nStreams, long lo
                      float* voice, float* synthL, float* synthR);
 void vp_launch_peak_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads);
 void vp_launch_peak_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads);
+void vp_launch_peak2_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads);
+void vp_launch_peak2_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads);

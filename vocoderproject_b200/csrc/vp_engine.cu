@@ -349,7 +349,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     gy.tauMax = z.tauMax; gy.nFramesP = nP;
     const size_t yinP = e->yinDirect ? 0 : (size_t)vp_yin_corr_chunks(gy) * (size_t)vp_yin_corr_lagpad(gy);
     // bytes of intermediates per stream
-    const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(2 * (e->prm.lpcVoice + 1) + 2 * (e->prm.lpcSynth + 1) + 3) +
+    const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(3 * (e->prm.lpcVoice + 1) + 3 * (e->prm.lpcSynth + 1) + 3) +
                              (size_t)nP * (8 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
                              (size_t)n * 8 + yinP * 4 + (size_t)(3 * nP + 1) * 8;
     if (workspaceBytes == 0) {
@@ -368,8 +368,8 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     e->workspace = perStream * (size_t)Sc;
     const size_t fV = (size_t)Sc * nV, fP = (size_t)Sc * nP;
     if ((rc = wsalloc(e, &e->dGate, (size_t)Sc * maxBlocks))) return rc;
-    if ((rc = wsalloc(e, &e->dRV, fV * (e->prm.lpcVoice + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dRS, fV * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dRV, fV * vp_row(e->prm.lpcVoice)))) return rc;
+    if ((rc = wsalloc(e, &e->dRS, fV * vp_row(e->prm.lpcSynth)))) return rc;
     if ((rc = wsalloc(e, &e->dAV, fV * (e->prm.lpcVoice + 1)))) return rc;
     if ((rc = wsalloc(e, &e->dAS, fV * (e->prm.lpcSynth + 1)))) return rc;
     if ((rc = wsalloc(e, &e->dEeV, fV))) return rc;
@@ -894,8 +894,7 @@ extern "C" int vp_synth_device(vp_engine* e, double fs, int flavour, int first, 
 }
 
 // ---- measurement -------------------------------------------------------------------
-extern "C" int vp_measure_peaks(vp_engine* e, double* fp32, double* fp64) {
-    if (!e) return VP_E_ARG;
+static int measure_peaks_impl(vp_engine* e, double* out4) {
     VP_CUDA_OK(cudaSetDevice(e->device));
     cudaDeviceProp prop;
     VP_CUDA_OK(cudaGetDeviceProperties(&prop, e->device));
@@ -904,13 +903,15 @@ extern "C" int vp_measure_peaks(vp_engine* e, double* fp32, double* fp64) {
     const int blocks = prop.multiProcessorCount * 8, threads = 256;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int pass = 0; pass < 2; ++pass) {
-        const int iters = pass == 0 ? 4096 : 1024;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int iters = (pass & 1) == 0 ? 4096 : 1024;
         double best = 0;
         for (int rep = 0; rep < 4; ++rep) {
             cudaEventRecord(a, e->st);
             if (pass == 0) vp_launch_peak_fp32(e->st, (float*)sink, iters, blocks, threads);
-            else vp_launch_peak_fp64(e->st, (double*)sink, iters, blocks, threads);
+            else if (pass == 1) vp_launch_peak_fp64(e->st, (double*)sink, iters, blocks, threads);
+            else if (pass == 2) vp_launch_peak2_fp32(e->st, (float*)sink, iters, blocks, threads);
+            else vp_launch_peak2_fp64(e->st, (double*)sink, iters, blocks, threads);
             cudaEventRecord(b, e->st);
             cudaEventSynchronize(b);
             float ms = 0;
@@ -918,11 +919,30 @@ extern "C" int vp_measure_peaks(vp_engine* e, double* fp32, double* fp64) {
             const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
             if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
         }
-        if (pass == 0 && fp32) *fp32 = best;
-        if (pass == 1 && fp64) *fp64 = best;
+        out4[pass] = best;
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaFree(sink);
     VP_CUDA_OK(cudaGetLastError());
+    return VP_OK;
+}
+
+extern "C" int vp_measure_peaks(vp_engine* e, double* fp32, double* fp64) {
+    if (!e) return VP_E_ARG;
+    double v[4];
+    int rc = measure_peaks_impl(e, v);
+    if (rc) return rc;
+    if (fp32) *fp32 = v[0];
+    if (fp64) *fp64 = v[1];
+    return VP_OK;
+}
+
+extern "C" int vp_measure_peaks2(vp_engine* e, double* fp32TwoOperand, double* fp64TwoOperand) {
+    if (!e) return VP_E_ARG;
+    double v[4];
+    int rc = measure_peaks_impl(e, v);
+    if (rc) return rc;
+    if (fp32TwoOperand) *fp32TwoOperand = v[2];
+    if (fp64TwoOperand) *fp64TwoOperand = v[3];
     return VP_OK;
 }

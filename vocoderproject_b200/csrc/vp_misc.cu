@@ -101,6 +101,35 @@ __global__ void __launch_bounds__(256) k_peak(T* sink, int iters) {
     if (r == (T)123456789) sink[0] = r;
 }
 
+// Same issue-rate measurement with the operand pattern of the engine's inner loops: acc_i = fma(x, b_i, acc_i) -- one
+// operand shared by all chains (operand-reuse cache), TWO distinct register operands per FMA (b_i and acc_i).
+template <typename T>
+__global__ void __launch_bounds__(256) k_peak2(T* sink, int iters) {
+    T a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = (T)(threadIdx.x + i); b[i] = (T)1e-3 * (T)(i + 1 + (threadIdx.x & 3)); }
+    T x = (T)0.999 + (T)1e-6 * (T)threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(x, b[i], a[i]);
+        }
+        x = -x;
+    }
+    T r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += a[i];
+    if (r == (T)123456789) sink[0] = r;
+}
+
+void vp_launch_peak2_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads) {
+    k_peak2<float><<<blocks, threads, 0, st>>>(sink, iters);
+}
+void vp_launch_peak2_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads) {
+    k_peak2<double><<<blocks, threads, 0, st>>>(sink, iters);
+}
+
 void vp_launch_peak_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads) {
     k_peak<float><<<blocks, threads, 0, st>>>(sink, iters);
 }

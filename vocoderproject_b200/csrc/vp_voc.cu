@@ -2,6 +2,8 @@
 // Levinson-Durbin + residual energies, all-pole resynthesis + overlap-add.
 // Reference behaviour: Source/VocoderProcess.cpp:190-297, Source/LPC.cpp:44-148,
 // Source/MyBuffer.cpp:258-261,:299-302.
+#include <cuda_pipeline.h>
+
 #include "vp_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -121,12 +123,23 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
     }
     const int k = k0 + f;
     if (seg == 0 && k < g.nFramesV) {
-        double* r = (isVoice ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)(order + 1);
+        double* r = (isVoice ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)vp_row(order);
 #pragma unroll
         for (int j = 0; j < AC_R; ++j) {
             const int m = grp * AC_R + j;
             if (m <= order) r[m] = acc[j];  // raw sum; the Levinson kernel applies the 1/wlen of LPC.cpp:93-96
         }
+    }
+    // the frame's last `order` windowed samples, appended to its row
+    for (int i = threadIdx.x; i < AC_FRAMES * (g.ordV + g.ordS); i += blockDim.x) {
+        const int ff = i / (g.ordV + g.ordS), t = i - ff * (g.ordV + g.ordS);
+        const int kk = k0 + ff;
+        if (kk >= g.nFramesV) continue;
+        const bool tv = t < g.ordV;
+        const int ord = tv ? g.ordV : g.ordS, tt = tv ? t : t - g.ordV;
+        const int j = g.wlenV - ord + tt;
+        double* r = (tv ? rV : rS) + ((size_t)s * g.nFramesV + kk) * (size_t)vp_row(ord);
+        r[ord + 1 + tt] = (j >= 0) ? (tv ? xw : sw)[ff * FS + j] : 0.0;
     }
 }
 
@@ -138,44 +151,82 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 // register-window task as above. Only warp-level synchronisation.
 // ---------------------------------------------------------------------------
 #define AV_WARPS 4
-#define AV_BATCH 4
+#define AV_BATCH 32  // consecutive frames per warp: the initial ring fill is paid once per batch
+#define AV_NPRE 8    // prefetch registers per lane and signal: hop <= 32 * AV_NPRE
 
+// A warp keeps the raw samples of its current frame in a ring of wlen = 4 hop floats per signal (position u lives at
+// u mod wlen). While frame k is being correlated, the hop NEW samples of frame k+1 are already in flight into
+// registers; after the correlation they overwrite the oldest hop ring entries. Global latency is hidden behind the
+// FP64 work and every input sample is loaded exactly once per batch.
 __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                                  const float* __restrict__ synth, double* __restrict__ rV,
-                                                                 double* __restrict__ rS, int segLen, int FS, int rawLen,
+                                                                 double* __restrict__ rS, int segLen, int FS, int ringLen,
                                                                  int batchesPerStream, int S) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hop = g.hopV, wlen = g.wlenV;
+    double* wv = sm;  // [wlen] analysis window, shared by the CTA
+    for (int i = threadIdx.x; i < wlen; i += blockDim.x) wv[i] = tb.wV[i];
+    __syncthreads();
     const long long wid = (long long)blockIdx.x * AV_WARPS + warp;
     if (wid >= (long long)batchesPerStream * S) return;
     const int s = (int)(wid / batchesPerStream);
     const int k0 = (int)(wid - (long long)s * batchesPerStream) * AV_BATCH;
-    double* xw = sm + (size_t)warp * (2 * FS + rawLen);  // [FS] voice * window (zero padded)
-    double* sw = xw + FS;                                // [FS] synth ch0 * window
-    float* rawV = (float*)(sw + FS);                     // [rawLen] raw voice of the batch
-    float* rawS = rawV + rawLen;                         // [rawLen] raw synth ch0
+    double* xw = sm + ((wlen + 1) & ~1) + (size_t)warp * (2 * FS + ringLen);  // [FS] voice * window (zero padded)
+    double* sw = xw + FS;                                                     // [FS] synth ch0 * window
+    float* ringV = (float*)(sw + FS);                                         // [wlen]
+    float* ringS = ringV + ringLen;                                           // [wlen]   (2 * ringLen floats = ringLen doubles)
     const float* v = voice + (size_t)s * g.stride;
     const float* y = synth + (size_t)s * g.stride;
-    const int hop = g.hopV, wlen = g.wlenV;
-    const long long uB = (long long)k0 * hop;
-    const int span = (AV_BATCH - 1) * hop + wlen;
-    vp_stage<8>(rawV, v, uB, span, g.lat, g.n, lane, 32);
-    vp_stage<8>(rawS, y, uB, span, g.lat, g.n, lane, 32);
     for (int j = wlen + lane; j < FS; j += 32) { xw[j] = 0.0; sw[j] = 0.0; }
-    const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;  // grp 0..2: voice lags 14 grp .., grp 3: side-chain
+    const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;  // grp 0..2: voice lag groups, grp 3: side-chain
     const double* sig = (grp < 3 ? xw : sw);
     // lag offsets 0 / 13 / 27 (lag 13 computed twice): odd - even offsets inside each half-warp keep the 64-bit window
     // loads of two groups on disjoint banks (segLen = 2 mod 4 puts the 8 segments on the 8 even / 8 odd banks)
     const int m0 = (grp == 1) ? AC_R - 1 : (grp == 2) ? 2 * AC_R - 1 : 0;
     const int order = (grp < 3) ? g.ordV : g.ordS;
+    // ---- initial fill: frame k0 occupies ring positions (k0 hop + j) mod wlen
+    {
+        const long long u0 = (long long)k0 * hop;
+        const int r0 = (int)(u0 % wlen);
+        // positions are contiguous modulo the ring: stage linearly, then the index wraps
+        for (int base = lane; base < wlen; base += 32 * 6) {
+            float tv[6], ts[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int j = base + q * 32;
+                tv[q] = (j < wlen) ? vp_x(v, u0 + j, g.lat, g.n) : 0.0f;
+                ts[q] = (j < wlen) ? vp_x(y, u0 + j, g.lat, g.n) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int j = base + q * 32;
+                if (j < wlen) { int idx = r0 + j; if (idx >= wlen) idx -= wlen; ringV[idx] = tv[q]; ringS[idx] = ts[q]; }
+            }
+        }
+    }
     for (int fb = 0; fb < AV_BATCH; ++fb) {
         const int k = k0 + fb;
         if (k >= g.nFramesV) break;
+        const long long u0 = (long long)k * hop;
+        const int r0 = (int)(u0 % wlen);
+        // ---- prefetch the hop new samples of frame k+1 (positions u0 + wlen .. u0 + wlen + hop)
+        float nv[AV_NPRE], ns[AV_NPRE];
+        const bool more = (fb + 1 < AV_BATCH) && (k + 1 < g.nFramesV);
+#pragma unroll
+        for (int q = 0; q < AV_NPRE; ++q) {
+            const int j = lane + q * 32;
+            nv[q] = (more && j < hop) ? vp_x(v, u0 + wlen + j, g.lat, g.n) : 0.0f;
+            ns[q] = (more && j < hop) ? vp_x(y, u0 + wlen + j, g.lat, g.n) : 0.0f;
+        }
         __syncwarp();
+        // ---- windowed FP64 copies from the ring
         for (int j = lane; j < wlen; j += 32) {
-            const double w = tb.wV[j];
-            xw[j] = (double)rawV[fb * hop + j] * w;
-            sw[j] = (double)rawS[fb * hop + j] * w;
+            int idx = r0 + j;
+            if (idx >= wlen) idx -= wlen;
+            const double w = wv[j];
+            xw[j] = (double)ringV[idx] * w;
+            sw[j] = (double)ringS[idx] * w;
         }
         __syncwarp();
         double acc[AC_R];
@@ -188,12 +239,25 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
             a += __shfl_xor_sync(0xffffffffu, a, 4);
             acc[j] = a;
         }
+        double* rowV = rV + ((size_t)s * g.nFramesV + k) * (size_t)vp_row(g.ordV);
+        double* rowS = rS + ((size_t)s * g.nFramesV + k) * (size_t)vp_row(g.ordS);
         if (seg == 0) {
-            double* r = (grp < 3 ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)(order + 1);
+            double* r = (grp < 3) ? rowV : rowS;
 #pragma unroll
             for (int j = 0; j < AC_R; ++j) {
                 const int m = m0 + j;
                 if (m <= order) r[m] = acc[j];  // raw sum; the Levinson kernel applies the 1/wlen of LPC.cpp:93-96
+            }
+        }
+        // the frame's last `order` windowed samples, appended to its row (coalesced)
+        for (int t = lane; t < g.ordV; t += 32) rowV[g.ordV + 1 + t] = (wlen - g.ordV + t >= 0) ? xw[wlen - g.ordV + t] : 0.0;
+        for (int t = lane; t < g.ordS; t += 32) rowS[g.ordS + 1 + t] = (wlen - g.ordS + t >= 0) ? sw[wlen - g.ordS + t] : 0.0;
+        // ---- retire the oldest hop ring entries: they become the new samples of frame k+1
+        if (more) {
+#pragma unroll
+            for (int q = 0; q < AV_NPRE; ++q) {
+                const int j = lane + q * 32;
+                if (j < hop) { int idx = r0 + j; if (idx >= wlen) idx -= wlen; ringV[idx] = nv[q]; ringS[idx] = ns[q]; }
             }
         }
     }
@@ -208,15 +272,15 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
-    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1) {
+    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 && g.hopV <= 32 * AV_NPRE) {
         FS = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
-        const int rawLen = ((AV_BATCH - 1) * g.hopV + g.wlenV + 3) & ~3;
-        const size_t perWarp = (size_t)(2 * FS + rawLen) * sizeof(double);  // rawLen floats x 2 signals = rawLen doubles
+        const int ringLen = (g.wlenV + 3) & ~3;  // floats per signal; two signals = ringLen doubles
+        const size_t smem = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS + ringLen)) * sizeof(double);
         const int batchesPerStream = (g.nFramesV + AV_BATCH - 1) / AV_BATCH;
         const long long warps = (long long)batchesPerStream * S;
         cudaFuncSetAttribute(k_voc_autocorr2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_voc_autocorr2<<<(unsigned)((warps + AV_WARPS - 1) / AV_WARPS), 32 * AV_WARPS, perWarp * AV_WARPS, st>>>(
-            g, tb, voice, synth, rV, rS, segLen, FS, rawLen, batchesPerStream, S);
+        k_voc_autocorr2<<<(unsigned)((warps + AV_WARPS - 1) / AV_WARPS), 32 * AV_WARPS, smem, st>>>(
+            g, tb, voice, synth, rV, rS, segLen, FS, ringLen, batchesPerStream, S);
         return;
     }
     const size_t smem = (size_t)2 * AC_FRAMES * FS * sizeof(double);
@@ -286,7 +350,7 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
     const long long u0 = (long long)k * g.hopV;
     double r[VP_ORDER_MAX + 1], a[VP_ORDER_MAX + 1];
     {
-        const double* rp = rV + (size_t)idx * (g.ordV + 1);
+        const double* rp = rV + (size_t)idx * vp_row(g.ordV);
         for (int m = 0; m <= g.ordV; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordV);
         double* ap = aV + (size_t)idx * (g.ordV + 1);
@@ -294,7 +358,7 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
         EeV[idx] = fir_energy(r, a, g.ordV, g.wlenV, voice + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
     }
     {
-        const double* rp = rS + (size_t)idx * (g.ordS + 1);
+        const double* rp = rS + (size_t)idx * vp_row(g.ordS);
         for (int m = 0; m <= g.ordS; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordS);
         double* ap = aS + (size_t)idx * (g.ordS + 1);
@@ -305,10 +369,11 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
 
 // Register-resident specialisation for a compile-time order: r[], a[] and the frame's last P windowed samples are
 // statically indexed (fully unrolled recursion, no local memory). Same operation order as lev_solve / fir_energy.
+// rp / ap / xt point into SHARED memory (row of this thread, odd stride): the CTA stages them with coalesced,
+// batched global accesses, because 232 registers per thread leave no room to keep dozens of global loads in flight.
 template <int P>
 __device__ __forceinline__ double lev_energy_static(const double* __restrict__ rp, double* __restrict__ ap, int wlen,
-                                                    const float* __restrict__ row, long long u0,
-                                                    const double* __restrict__ w, int lat, long long n) {
+                                                    const double* __restrict__ xts) {
     double r[P + 1], a[P + 1];
     const double dw = (double)wlen, iw = 1.0 / dw;
 #pragma unroll
@@ -344,10 +409,7 @@ __device__ __forceinline__ double lev_energy_static(const double* __restrict__ r
     double E = q * (double)wlen;
     double xt[P];  // xt[t] = windowed sample wlen - P + t
 #pragma unroll
-    for (int t = 0; t < P; ++t) {
-        const int j = wlen - P + t;
-        xt[t] = (j >= 0) ? (double)vp_x(row, u0 + j, lat, n) * w[j] : 0.0;
-    }
+    for (int t = 0; t < P; ++t) xt[t] = xts[t];
     double tail = 0.0;
 #pragma unroll
     for (int d = 0; d < P; ++d) {
@@ -360,29 +422,55 @@ __device__ __forceinline__ double lev_energy_static(const double* __restrict__ r
     return E > 0.0 ? E : 0.0;
 }
 
+#define LV_THREADS 64
+
 template <int PV, int PS>
-__global__ void __launch_bounds__(64) k_voc_levinson_static(VPGeom g, VPTables tb, const float* __restrict__ voice,
-                                                            const float* __restrict__ synth,
-                                                            const double* __restrict__ rV, const double* __restrict__ rS,
-                                                            double* __restrict__ aV, double* __restrict__ aS,
-                                                            double* __restrict__ EeV, double* __restrict__ EeS, int S) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)S * g.nFramesV) return;
-    const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
-    const long long u0 = (long long)k * g.hopV;
-    EeS[idx] = lev_energy_static<PS>(rS + (size_t)idx * (PS + 1), aS + (size_t)idx * (PS + 1), g.wlenV,
-                                     synth + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
-    EeV[idx] = lev_energy_static<PV>(rV + (size_t)idx * (PV + 1), aV + (size_t)idx * (PV + 1), g.wlenV,
-                                     voice + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+__global__ void __launch_bounds__(LV_THREADS) k_voc_levinson_static(VPGeom g, VPTables tb, const float* __restrict__ voice,
+                                                                    const float* __restrict__ synth, const uint8_t* __restrict__ gate,
+                                                                    const double* __restrict__ rV, const double* __restrict__ rS,
+                                                                    double* __restrict__ aV, double* __restrict__ aS,
+                                                                    double* __restrict__ EeV, double* __restrict__ EeS, long long tot) {
+    constexpr int RV = 2 * PV + 1, RSY = 2 * PS + 1;  // workspace rows: lags 0..P then the last P windowed samples
+    constexpr int NR = RV + RSY;
+    constexpr int RS = NR | 1;                        // odd row stride in shared memory
+    extern __shared__ double sm[];
+    double* sR = sm;                                  // [LV_THREADS][RS]  rows in; the coefficient rows go out through it
+    const int tid = threadIdx.x;
+    const long long f0 = (long long)blockIdx.x * LV_THREADS;
+    const int nF = (int)((tot - f0 < LV_THREADS) ? tot - f0 : LV_THREADS);
+    const int wlen = g.wlenV;
+    // ---- coalesced staging (rows of consecutive frames are contiguous in global memory)
+    for (int i = tid; i < nF * RV; i += LV_THREADS) sR[(i / RV) * RS + (i % RV)] = rV[f0 * RV + i];
+    for (int i = tid; i < nF * RSY; i += LV_THREADS) sR[(i / RSY) * RS + RV + (i % RSY)] = rS[f0 * RSY + i];
+    __syncthreads();
+    if (tid < nF) {
+        const long long idx = f0 + tid;
+        const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+        double* row = sR + tid * RS;
+        const double eS = lev_energy_static<PS>(row + RV, row + RV, wlen, row + RV + PS + 1);
+        // a frame skipped by the silence gate (VocoderProcess.cpp:199-204) is marked with EeSynth = -1: the synthesis
+        // kernel then needs no gate lookups for its 10-frame energy history
+        const int b = (int)(((unsigned)k * (unsigned)g.hopV) / (unsigned)g.B);
+        const bool gated = (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) != 0;
+        EeS[idx] = gated ? -1.0 : eS;
+        EeV[idx] = lev_energy_static<PV>(row, row, wlen, row + PV + 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < nF * (PV + 1); i += LV_THREADS) aV[f0 * (PV + 1) + i] = sR[(i / (PV + 1)) * RS + (i % (PV + 1))];
+    for (int i = tid; i < nF * (PS + 1); i += LV_THREADS) aS[f0 * (PS + 1) + i] = sR[(i / (PS + 1)) * RS + RV + (i % (PS + 1))];
 }
 
 void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                             const float* synth, const uint8_t* gate, const double* rV, const double* rS, double* aV,
                             double* aS, double* EeV, double* EeS) {
-    (void)gate;
     const long long tot = (long long)S * g.nFramesV;
     if (g.ordV == 40 && g.ordS == 5 && g.wlenV >= 40)
-        k_voc_levinson_static<40, 5><<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
+    {
+        const size_t smem = (size_t)LV_THREADS * ((vp_row(40) + vp_row(5)) | 1) * sizeof(double);
+        cudaFuncSetAttribute(k_voc_levinson_static<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_voc_levinson_static<40, 5><<<(unsigned)((tot + LV_THREADS - 1) / LV_THREADS), LV_THREADS, smem, st>>>(
+            g, tb, voice, synth, gate, rV, rS, aV, aS, EeV, EeS, tot);
+    }
     else
         k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
 }
@@ -560,6 +648,11 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     for (int i = threadIdx.x; i < 4 * hop; i += blockDim.x) wv[(i / hop) * rowPad + (i % hop)] = tb.wV[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-lane landing zone of the NEXT frame's parameters, filled by cp.async one hop-row ahead of its use:
+    // [0, P] aV row, [P+1, P+PS+1] aS row, then EeV[k-9..k] and EeS[k-9..k] (gain history, VocoderProcess.cpp:264-276)
+    constexpr int CF_AS = P + 1, CF_EV = P + PS + 2, CF_ES = CF_EV + 10, CF_N = CF_ES + 10;
+    constexpr int CF_STRIDE = CF_N | 1;  // odd stride: the 64-bit reads of 32 lanes hit distinct banks
+    double* cf = wv + 4 * rowPad + ((size_t)warp * 32 + lane) * CF_STRIDE;
     const long long wid = (long long)blockIdx.x * VT_WARPS + warp;
     const int groups = (S + 7) / 8;
     if (wid >= (long long)groups * nSeg) return;
@@ -577,7 +670,6 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     const int rowEnd = lastSeg ? (int)((g.n + hop - 1) / hop) : kE;  // rows [kS - 3, rowEnd)
     const float* y = synth + (size_t)s * g.stride;
     float* o = outV + (size_t)s * g.wstride;
-    const uint8_t* gt = gate + (size_t)s * g.nBlocks;
     const double* ev = EeV + (size_t)s * g.nFramesV;
     const double* es = EeS + (size_t)s * g.nFramesV;
     const double gv = (double)g.gainVocF;
@@ -589,28 +681,53 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     int wrow = 0;  // window row of this lane's current frame in the current hop-row
     float xn[4] = {0.f, 0.f, 0.f, 0.f};  // prefetched side-chain samples of the next block of four positions
     bool primed = false;
-    for (int rho = kS - 3; rho < rowEnd; ++rho) {
-        if (rho < 0) continue;
+    auto prefetch = [&](int k) {  // asynchronous copy of frame k's parameters into this lane's landing zone
+        if (k >= 0 && k < g.nFramesV && (k & 3) == phi) {
+            const double* ap = aV + ((size_t)s * g.nFramesV + k) * (P + 1);
+#pragma unroll
+            for (int j = 0; j <= P; ++j) __pipeline_memcpy_async(cf + j, ap + j, 8);
+            const double* sp = aS + ((size_t)s * g.nFramesV + k) * (PS + 1);
+#pragma unroll
+            for (int j = 0; j <= PS; ++j) __pipeline_memcpy_async(cf + CF_AS + j, sp + j, 8);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const int q = k - 9 + j;
+                if (q >= 0) { __pipeline_memcpy_async(cf + CF_EV + j, ev + q, 8); __pipeline_memcpy_async(cf + CF_ES + j, es + q, 8); }
+            }
+        }
+        __pipeline_commit();
+    };
+    const int rho0 = (kS - 3 > 0) ? kS - 3 : 0;
+    prefetch(rho0);
+    for (int rho = rho0; rho < rowEnd; ++rho) {
+        __pipeline_wait_prior(0);
         // ---- frame start for the phase that begins at this row
         if ((rho & 3) == phi) {
-            bool active = rho < g.nFramesV;
-            if (active) {
-                const int b = (int)(((long long)rho * hop) / g.B);
-                if (gt[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) active = false;  // VocoderProcess.cpp:199-204
-            }
 #pragma unroll
             for (int j = 0; j <= P; ++j) st[j] = 0.0;
 #pragma unroll
             for (int j = 0; j <= PS; ++j) t[j] = 0.0;
             double gain = 0.0;
+            // a gated frame carries EeSynth < 0 (written by the Levinson kernel; VocoderProcess.cpp:199-204)
+            const bool active = rho < g.nFramesV && cf[CF_ES + 9] >= 0.0;
             if (active) {
-                gain = voc_gain(g, gt, ev, es, rho);
-                const double* ap = aV + ((size_t)s * g.nFramesV + rho) * (P + 1);
+                if (cf[CF_ES + 9] > 1e-4) {  // gain over the last 10 processed (non-gated) frames, newest to oldest
+                    double sv = 0.0, ss = 0.0;
+                    int cnt = 0;
 #pragma unroll
-                for (int j = 1; j <= P; ++j) a[j] = ap[j];
-                const double* sp = aS + ((size_t)s * g.nFramesV + rho) * (PS + 1);
+                    for (int j = 9; j >= 0; --j) {
+                        if (rho - 9 + j >= 0 && cf[CF_ES + j] >= 0.0) { sv += cf[CF_EV + j]; ss += cf[CF_ES + j]; ++cnt; }
+                    }
+                    for (int q = rho - 10; q >= 0 && cnt < 10; --q) {  // only when gated frames sit inside the window
+                        const double eq = es[q];
+                        if (eq >= 0.0) { sv += ev[q]; ss += eq; ++cnt; }
+                    }
+                    gain = sqrt(sv / ss);
+                }
 #pragma unroll
-                for (int j = 0; j <= PS; ++j) as[j] = gain * sp[j];
+                for (int j = 1; j <= P; ++j) a[j] = cf[j];
+#pragma unroll
+                for (int j = 0; j <= PS; ++j) as[j] = gain * cf[CF_AS + j];
             } else {
 #pragma unroll
                 for (int j = 1; j <= P; ++j) a[j] = 0.0;
@@ -620,6 +737,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
             if (sOk && rho < g.nFramesV && rho >= kS && gOut) gOut[(size_t)s * g.nFramesV + rho] = gain;
             wrow = 0;
         }
+        prefetch(rho + 1);
         const double* wr = wv + wrow * rowPad;
         const long long tBase = (long long)rho * hop;
         const bool emitRow = sOk && rho >= kS;
@@ -756,7 +874,8 @@ void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
         if (segFrames < 16) segFrames = 16;                              // keep the 3-row halo a small fraction
         nSeg = (g.nFramesV + segFrames - 1) / segFrames;
         const int rowPad = g.hopV | 1;
-        const size_t smem = (size_t)4 * rowPad * sizeof(double);
+        const int cfStride = (40 + 1 + 5 + 1 + 20) | 1;
+        const size_t smem = ((size_t)4 * rowPad + (size_t)VT_WARPS * 32 * cfStride) * sizeof(double);
         const long long warps = (long long)groups * nSeg;
         cudaFuncSetAttribute(k_voc_synth_stream<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
