@@ -1014,26 +1014,30 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
         const double* __restrict__ hg = tb.hann + tb.hannOff[T];
         for (int i = tid; i < 2 * T + 1; i += PF_THREADS) hs[i] = __ldg(hg + i);
     }
-    __syncthreads();
-    bool ub = false;
-    // ---- PSOLA, chunk by chunk (PitchProcess.cpp:665-741, :788-870)
+    // ---- PSOLA (PitchProcess.cpp:665-741, :788-870). Grain table first: thread m prepares synthesis mark m -- the
+    // chunk n at which the reference handles it (the first n with stMark - T < (n + 1) c), the look-ahead and residual
+    // extent visible at that chunk, the closest complete analysis mark, the output range -- so that the element loop
+    // below carries no per-grain scalar work.
+    __shared__ int gSt[VP_MAX_MARKS], gCl[VP_MAX_MARKS], gI0[VP_MAX_MARKS], gI1[VP_MAX_MARKS], gEv[VP_MAX_MARKS], gFl[VP_MAX_MARKS];
+    __shared__ double gX0[VP_MAX_MARKS], gX1[VP_MAX_MARKS];
     const double beta = rec->beta;
-    const int stale = rec->anStale;
-    if (T > 0 && T < tauMax) {
-        int stIdx = 0;
-        for (int n = 0; n < 4; ++n) {
+    const bool okT = T > 0 && T < tauMax;
+    if (tid < VP_MAX_MARKS) {
+        int fl = 0;  // 1 = process, 2 = first mark, 4 = last mark, 8 = UB in the reference
+        if (okT && tid < nSt) {
+            const int stMark = sSt[tid];
+            const int d = stMark - T;
+            const int n = (d < c) ? 0 : d / c;
             const long long Pn = p + (long long)n * c;
-            if (Pn >= g.n) break;
-            const int startSample = (int)(Pn % g.B);
-            const int lookahead = g.lat + g.B - startSample;  // bufferIdxMax - startSample (PitchProcess.cpp:800)
-            const int eValid = L + n * c;                     // residual filtered so far
-            while (stIdx < nSt) {
-                const int stMark = sSt[stIdx];
-                if (stMark - T >= (n + 1) * c) break;
+            if (n <= 3 && Pn < g.n) {
+                const int stale = rec->anStale;
+                const int startSample = (int)(Pn % g.B);
+                const int lookahead = g.lat + g.B - startSample;  // bufferIdxMax - startSample (PitchProcess.cpp:800)
+                const int nc = n * c;
                 // getClosestAnMarkIdx (PitchProcess.cpp:788-831)
                 int lo = 0, hi = nAn;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (sAn[mid] < stMark) lo = mid + 1; else hi = mid; }
-                const int idx = lo, nc = n * c;
+                const int idx = lo;
                 int cl;
                 if (idx > 0 && idx < nAn) {
                     if (abs(sAn[idx] - stMark) <= abs(sAn[idx - 1] - stMark) && sAn[idx] + T - nc < lookahead) cl = idx;
@@ -1044,51 +1048,65 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
                 else {
                     if (stale + T - nc < lookahead) cl = idx - 1;  // anMarks[size]: stale storage slot (U1)
                     else if (idx - 2 >= 0) cl = idx - 2;
-                    else { cl = 0; ub = true; }
+                    else { cl = 0; fl |= 8; }
                 }
                 int clAn;
                 if (cl >= 0) clAn = sAn[cl];
-                else { clAn = 0; ub = true; }  // U2: out-of-bounds prevAnMarks read in the reference
-                const bool first = (stIdx == 0), last = (stIdx == nSt - 1);
+                else { clAn = 0; fl |= 8; }  // U2: out-of-bounds prevAnMarks read in the reference
                 const double dSt = (double)stMark;
                 const double x0 = dSt + (double)(-T) / beta;
                 const double xEnd = dSt + (double)(T) / beta;
-                const int startIdx = max(max((int)floor(x0), 0), nc);  // i < nc: chunk already filtered (App. A.4 #6)
-                const int stopIdx = min((int)ceil(xEnd), L);
-                if (x0 >= 0.0 && x0 == floor(x0)) ub = true;  // U5
-                const int eBase = clAn - T + tauMax;           // e index of grain sample j = 0
-                // thread <-> output index i is fixed (i mod PF_THREADS) so that successive grains
-                // accumulate into oE[i] in mark order without synchronisation
-                for (int i = (startIdx / PF_THREADS) * PF_THREADS + tid; i < stopIdx; i += PF_THREADS) {
-                    const double di = (double)i;
-                    if (i < startIdx || !(di >= x0 && di <= xEnd)) continue;
-                    // interp() (PitchProcess.cpp:842-870): lower_bound j over x[j] = stMark + (j - T) / beta, then linear
-                    // interpolation between grain samples j-1 and j. In grain coordinates tg = T + (i - stMark) beta the
-                    // bound is j = ceil(tg) and the weight (i - x[j-1]) / (x[j] - x[j-1]) = tg - (j - 1). The interpolant
-                    // is continuous in tg, so a lower_bound that differs from the reference's when tg is within rounding of
-                    // an integer changes the value by O(1e-13) only.
-                    const double tg = fma(di - dSt, beta, (double)T);
-                    int j = (int)ceil(tg);
-                    j = max(0, min(j, 2 * T));
-                    const int ej = eBase + j;
-                    const int rel = clAn - T + j;  // frame-relative index of grain sample j
-                    double y1 = (ej >= 0 && ej < eLen && rel < eValid) ? e[ej] : 0.0;
-                    const bool w1 = (!first && !last) || (first ? (j >= T) : (j < T));
-                    if (w1) y1 *= hs[j];
-                    double val = y1;
-                    if (j > 0) {
-                        double y0 = (ej - 1 >= 0 && ej - 1 < eLen && rel - 1 < eValid) ? e[ej - 1] : 0.0;
-                        const bool w0 = (!first && !last) || (first ? (j - 1 >= T) : (j - 1 < T));
-                        if (w0) y0 *= hs[j - 1];
-                        const double frac = fmin(fmax(tg - (double)(j - 1), 0.0), 1.0);
-                        val = fma(y1 - y0, frac, y0);
-                    }
-                    oE[i] += val;
-                }
-                ++stIdx;
+                if (x0 >= 0.0 && x0 == floor(x0)) fl |= 8;  // U5
+                gSt[tid] = stMark;
+                gCl[tid] = clAn;
+                gI0[tid] = max(max((int)floor(x0), 0), nc);  // i < nc: chunk already filtered (App. A.4 #6)
+                gI1[tid] = min((int)ceil(xEnd), L);
+                gEv[tid] = L + nc;                            // residual filtered so far
+                gX0[tid] = x0;
+                gX1[tid] = xEnd;
+                fl |= 1 | (tid == 0 ? 2 : 0) | (tid == nSt - 1 ? 4 : 0);
             }
         }
-    } else ub = true;
+        gFl[tid] = fl;
+    }
+    __syncthreads();
+    bool ub = !okT;
+    if (okT) {
+        for (int m = 0; m < nSt; ++m) {
+            const int fl = gFl[m];
+            if (fl & 8) ub = true;
+            if (!(fl & 1)) continue;
+            const bool first = (fl & 2) != 0, last = (fl & 4) != 0, inner = !first && !last;
+            const int clAn = gCl[m], eValid = gEv[m], startIdx = gI0[m], stopIdx = gI1[m];
+            const double dSt = (double)gSt[m], x0 = gX0[m], xEnd = gX1[m];
+            const int eBase = clAn - T + tauMax;  // e index of grain sample j = 0
+            const int jLim = min(eLen - eBase, eValid - (clAn - T));  // grain samples j < jLim exist in the residual so far
+            // thread <-> output index i is fixed (i mod PF_THREADS) so that successive grains
+            // accumulate into oE[i] in mark order without synchronisation
+            for (int i = (startIdx / PF_THREADS) * PF_THREADS + tid; i < stopIdx; i += PF_THREADS) {
+                const double di = (double)i;
+                if (i < startIdx || !(di >= x0 && di <= xEnd)) continue;
+                // interp() (PitchProcess.cpp:842-870): lower_bound j over x[j] = stMark + (j - T) / beta, then linear
+                // interpolation between grain samples j-1 and j. In grain coordinates tg = T + (i - stMark) beta the
+                // bound is j = ceil(tg) and the weight (i - x[j-1]) / (x[j] - x[j-1]) = tg - (j - 1). The interpolant
+                // is continuous in tg, so a lower_bound that differs from the reference's when tg is within rounding of
+                // an integer changes the value by O(1e-13) only.
+                const double tg = fma(di - dSt, beta, (double)T);
+                int j = (int)ceil(tg);
+                j = max(0, min(j, 2 * T));
+                const int ej = eBase + j;
+                double y1 = (ej >= 0 && j < jLim) ? e[ej] : 0.0;
+                if (inner || (first ? (j >= T) : (j < T))) y1 *= hs[j];
+                double val = y1;
+                if (j > 0) {
+                    double y0 = (ej >= 1 && j - 1 < jLim) ? e[ej - 1] : 0.0;
+                    if (inner || (first ? (j - 1 >= T) : (j - 1 < T))) y0 *= hs[j - 1];
+                    val = fma(y1 - y0, tg - (double)(j - 1), y0);
+                }
+                oE[i] += val;
+            }
+        }
+    }
     float* dst = outE + fidx * (size_t)L;
     for (int i = tid; i < L; i += PF_THREADS) dst[i] = (float)oE[i];  // own indices again
     if (ub && tid == 0) rec->flags = flags | VP_PF_UB;
