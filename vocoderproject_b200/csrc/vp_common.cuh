@@ -97,7 +97,8 @@ struct VPTables {
     const int* lutNote;      // per period: snapped note index         Notes.cpp:79-110
 };
 
-void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate);
+void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate,
+                    double* part /* [S][nBlocks][4] scratch */);
 
 void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                             const float* synth, const uint8_t* gate, double* rV, double* rS);

@@ -42,6 +42,7 @@ struct vp_engine {
     int lutKey = -1;
     // workspace (device), sized for Sc streams x maxBlocks
     uint8_t* dGate = nullptr;
+    double* dGatePart = nullptr;
     double *dRV = nullptr, *dRS = nullptr, *dAV = nullptr, *dAS = nullptr, *dEeV = nullptr, *dEeS = nullptr, *dG = nullptr;
     int *dPeriod = nullptr, *dList = nullptr, *dListCount = nullptr;
     uint32_t* dYFlags = nullptr;
@@ -224,7 +225,7 @@ static void free_workspace(vp_engine* e) {
                      (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
                      (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
                      (void**)&e->dOutP, (void**)&e->dFramesAll, (void**)&e->dGateAll, (void**)&e->dEeVAll, (void**)&e->dEeSAll,
-                     (void**)&e->dGAll, (void**)&e->dYinP, (void**)&e->dYinE, (void**)&e->dRP};
+                     (void**)&e->dGAll, (void**)&e->dGatePart, (void**)&e->dYinP, (void**)&e->dYinE, (void**)&e->dRP};
     for (void** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) if (e->hIn[i][j]) { cudaFree(e->hIn[i][j]); e->hIn[i][j] = nullptr; }
@@ -349,7 +350,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     gy.tauMax = z.tauMax; gy.nFramesP = nP;
     const size_t yinP = e->yinDirect ? 0 : (size_t)vp_yin_corr_chunks(gy) * (size_t)vp_yin_corr_lagpad(gy);
     // bytes of intermediates per stream
-    const size_t perStream = (size_t)maxBlocks + (size_t)nV * 8 * (size_t)(3 * (e->prm.lpcVoice + 1) + 3 * (e->prm.lpcSynth + 1) + 3) +
+    const size_t perStream = (size_t)maxBlocks * 33 + (size_t)nV * 8 * (size_t)(3 * (e->prm.lpcVoice + 1) + 3 * (e->prm.lpcSynth + 1) + 3) +
                              (size_t)nP * (8 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
                              (size_t)n * 8 + yinP * 4 + (size_t)(3 * nP + 1) * 8;
     if (workspaceBytes == 0) {
@@ -368,6 +369,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     e->workspace = perStream * (size_t)Sc;
     const size_t fV = (size_t)Sc * nV, fP = (size_t)Sc * nP;
     if ((rc = wsalloc(e, &e->dGate, (size_t)Sc * maxBlocks))) return rc;
+    if ((rc = wsalloc(e, &e->dGatePart, (size_t)Sc * maxBlocks * 4))) return rc;
     if ((rc = wsalloc(e, &e->dRV, fV * vp_row(e->prm.lpcVoice)))) return rc;
     if ((rc = wsalloc(e, &e->dRS, fV * vp_row(e->prm.lpcSynth)))) return rc;
     if ((rc = wsalloc(e, &e->dAV, fV * (e->prm.lpcVoice + 1)))) return rc;
@@ -463,8 +465,8 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     e->passCount++;
     const size_t fV = (size_t)Sp * g.nFramesV, fP = (size_t)Sp * g.nFramesP;
     stage_mark(e, ST_OTHER);
-    vp_launch_gate(st, g, Sp, voice, synthL, e->dGate);
-    e->launches++;
+    vp_launch_gate(st, g, Sp, voice, synthL, e->dGate, e->dGatePart);
+    e->launches += 2;
     stage_mark(e, ST_GATE);
     // Order: YIN -> [side stream: pitch-mark chain, sequential per stream, latency-bound, few warps] running UNDER
     // [main stream: the three vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.

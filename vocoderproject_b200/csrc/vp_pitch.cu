@@ -5,6 +5,8 @@
 // SURVEY.md App. A.4 / App. B describe the semantics that are restated here.
 #include <algorithm>
 
+#include <cuda_pipeline.h>
+
 #include "vp_common.cuh"
 
 // ===========================================================================
@@ -235,57 +237,82 @@ void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float*
 
 #define YC_SUB (4 * YC_R)    // first-level accumulation length (two-level FP32 summation: tighter error bound)
 
-__global__ void __launch_bounds__(32 * YC_CH) k_yin_corr(VPGeom g, const float* __restrict__ voice, float* __restrict__ P,
-                                                          double* __restrict__ Ech, int nChunks, int lagPad) {
-    extern __shared__ float xs[];  // [YC_CH * c + lagPad + 16]
+// Persistent CTAs: each loops over tiles (one stream x YC_CH chunks) with the samples of the NEXT tile arriving through
+// cp.async (zero-filled outside the call's input) into the second of two shared buffers while the current one is
+// being correlated -- the staging latency never reaches the FFMA loop.
+__global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const float* __restrict__ voice, float* __restrict__ P,
+                                                             double* __restrict__ Ech, int nChunks, int lagPad,
+                                                             int tilesPerStream, long long nTiles, int spanPad) {
+    extern __shared__ float xsAll[];  // 2 x [spanPad], spanPad >= YC_CH * c + lagPad + 16
     const int c = g.c, tauMax = g.tauMax;
-    const int s = blockIdx.y;
-    const int m0 = blockIdx.x * YC_CH;
-    const float* v = voice + (size_t)s * g.stride;
-    const long long u0 = (long long)m0 * c - tauMax;  // delayed position of xs[0]
     const int span = YC_CH * c + lagPad + 16;
-    vp_stage<6>(xs, v, u0, span, g.lat, g.n, threadIdx.x, blockDim.x);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = m0 + warp;
-    if (m >= nChunks) return;
-    const float* xa = xs + warp * c;
-    float* out = P + ((size_t)s * nChunks + m) * (size_t)lagPad;
-    {   // chunk energy sum_j x[j]^2 in FP64 (exact products): A and B(k) of the decision kernel build on it
-        double e2 = 0.0;
-        for (int n = lane; n < c; n += 32) { const double x = (double)xa[n]; e2 = fma(x, x, e2); }
-        e2 = vp_warp_sum(e2);
-        if (lane == 0) Ech[(size_t)s * nChunks + m] = e2;
-    }
-    for (int k0 = lane * YC_R; k0 < lagPad; k0 += YC_LAGS) {
-        const float* xw = xa + k0;
-        float acc[YC_R], acc2[YC_R], W[YC_R];
+    auto issue = [&](long long tile, float* dst) {
+        const int s = (int)(tile / tilesPerStream);
+        const int m0 = (int)(tile - (long long)s * tilesPerStream) * YC_CH;
+        const float* v = voice + (size_t)s * g.stride;
+        const long long t0 = (long long)m0 * c - tauMax - g.lat;  // input time of dst[0]
+        for (int j = threadIdx.x; j < span; j += blockDim.x) {
+            const long long t = t0 + j;
+            const bool ok = t >= 0 && t < g.n;
+            __pipeline_memcpy_async(dst + j, v + (ok ? t : 0), 4, ok ? 0 : 4);
+        }
+        __pipeline_commit();
+    };
+    long long tile = blockIdx.x;
+    if (tile >= nTiles) return;
+    int cur = 0;
+    issue(tile, xsAll);
+    for (; tile < nTiles; tile += gridDim.x) {
+        const long long next = tile + gridDim.x;
+        float* xs = xsAll + (size_t)cur * spanPad;
+        if (next < nTiles) { issue(next, xsAll + (size_t)(cur ^ 1) * spanPad); __pipeline_wait_prior(1); }
+        else __pipeline_wait_prior(0);
+        __syncthreads();
+        const int s = (int)(tile / tilesPerStream);
+        const int m = (int)(tile - (long long)s * tilesPerStream) * YC_CH + warp;
+        if (m < nChunks) {
+            const float* xa = xs + warp * c;
+            float* out = P + ((size_t)s * nChunks + m) * (size_t)lagPad;
+            {   // chunk energy sum_j x[j]^2 in FP64 (exact products): A and B(k) of the decision kernel build on it
+                double e2 = 0.0;
+                for (int n = lane; n < c; n += 32) { const double x = (double)xa[n]; e2 = fma(x, x, e2); }
+                e2 = vp_warp_sum(e2);
+                if (lane == 0) Ech[(size_t)s * nChunks + m] = e2;
+            }
+            for (int k0 = lane * YC_R; k0 < lagPad; k0 += YC_LAGS) {
+                const float* xw = xa + k0;
+                float acc[YC_R], acc2[YC_R], W[YC_R];
 #pragma unroll
-        for (int r = 0; r < YC_R; ++r) { acc[r] = 0.0f; acc2[r] = 0.0f; W[r] = xw[r]; }
-        int n = 0;
-        while (n + YC_R <= c) {
-            const int nSub = min(n + YC_SUB, c);
-            for (; n + YC_R <= nSub; n += YC_R) {
+                for (int r = 0; r < YC_R; ++r) { acc[r] = 0.0f; acc2[r] = 0.0f; W[r] = xw[r]; }
+                int n = 0;
+                while (n + YC_R <= c) {
+                    const int nSub = min(n + YC_SUB, c);
+                    for (; n + YC_R <= nSub; n += YC_R) {
 #pragma unroll
-                for (int u = 0; u < YC_R; ++u) {
-                    const float a = xa[n + u];
+                        for (int u = 0; u < YC_R; ++u) {
+                            const float a = xa[n + u];
+#pragma unroll
+                            for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
+                            W[u % YC_R] = xw[n + u + YC_R];
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < YC_R; ++r) { acc2[r] += acc[r]; acc[r] = 0.0f; }
+                }
+#pragma unroll
+                for (int u = 0; u < YC_R; ++u) {  // tail: fewer than YC_R samples left
+                    const float a = (n + u < c) ? xa[n + u] : 0.0f;
 #pragma unroll
                     for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
                     W[u % YC_R] = xw[n + u + YC_R];
                 }
+#pragma unroll
+                for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc2[r] + acc[r];
             }
-#pragma unroll
-            for (int r = 0; r < YC_R; ++r) { acc2[r] += acc[r]; acc[r] = 0.0f; }
         }
-#pragma unroll
-        for (int u = 0; u < YC_R; ++u) {  // tail: fewer than YC_R samples left
-            const float a = (n + u < c) ? xa[n + u] : 0.0f;
-#pragma unroll
-            for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
-            W[u % YC_R] = xw[n + u + YC_R];
-        }
-#pragma unroll
-        for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc2[r] + acc[r];
+        __syncthreads();  // everyone is done with this buffer before the tile after next lands in it
+        cur ^= 1;
     }
 }
 
@@ -558,10 +585,20 @@ int vp_yin_corr_chunks(const VPGeom& g) { return 3 * g.nFramesP + 1; }
 
 void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech) {
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
-    const size_t smem = (size_t)(YC_CH * g.c + lagPad + 16) * sizeof(float);
+    const int spanPad = (YC_CH * g.c + lagPad + 16 + 3) & ~3;
+    const size_t smem = (size_t)2 * spanPad * sizeof(float);
+    const int tilesPerStream = (nChunks + YC_CH - 1) / YC_CH;
+    const long long nTiles = (long long)tilesPerStream * S;
     cudaFuncSetAttribute(k_yin_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    dim3 grid((nChunks + YC_CH - 1) / YC_CH, S);
-    k_yin_corr<<<grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad);
+    int perSM = 4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_yin_corr, 32 * YC_CH, smem);
+    if (perSM < 1) perSM = 1;
+    int dev = 0, nSM = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)nSM * perSM;
+    if (grid > nTiles) grid = nTiles;
+    k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad);
 }
 
 void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,

@@ -4,6 +4,8 @@
 // Source/MyBuffer.cpp:258-261,:299-302.
 #include <cuda_pipeline.h>
 
+#include <type_traits>
+
 #include "vp_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -11,43 +13,64 @@
 // The ring at block b holds input times [(b+1)B - inSize, (b+1)B); zeros
 // before time 0. One CTA per (block, stream); FP64 accumulation.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_gate(VPGeom g, const float* __restrict__ voice,
-                                              const float* __restrict__ synth, uint8_t* __restrict__ gate) {
+// Two steps so that every sample is read once: per host block the sum of squares of the whole block and of its last
+// `rem` samples (inSize = q B + rem); the ring at block b is then blocks b-q+1 .. b plus the tail of block b-q.
+__global__ void __launch_bounds__(128) k_gate_partial(VPGeom g, const float* __restrict__ voice,
+                                                      const float* __restrict__ synth, double* __restrict__ part, int rem) {
     const int b = blockIdx.x, s = blockIdx.y;
-    const float* v = voice + (size_t)s * g.stride;
-    const float* y = synth + (size_t)s * g.stride;
-    long long t1 = (long long)(b + 1) * g.B;
-    long long t0 = t1 - g.inSize;
-    if (t0 < 0) t0 = 0;
-    double sv = 0.0, ss = 0.0;
-    for (long long t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-        double a = (double)__ldg(v + t), c = (double)__ldg(y + t);
-        sv = fma(a, a, sv);
-        ss = fma(c, c, ss);
+    const float* v = voice + (size_t)s * g.stride + (size_t)b * g.B;
+    const float* y = synth + (size_t)s * g.stride + (size_t)b * g.B;
+    double sv = 0.0, ss = 0.0, tv = 0.0, ts = 0.0;
+    const int tail0 = g.B - rem;
+    for (int t = threadIdx.x; t < g.B; t += blockDim.x) {
+        const double a = (double)__ldg(v + t), c = (double)__ldg(y + t);
+        const double a2 = a * a, c2 = c * c;
+        sv += a2;
+        ss += c2;
+        if (t >= tail0) { tv += a2; ts += c2; }
     }
-    sv = vp_warp_sum(sv);
-    ss = vp_warp_sum(ss);
-    __shared__ double red[2][4];
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sv; red[1][threadIdx.x >> 5] = ss; }
+    sv = vp_warp_sum(sv); ss = vp_warp_sum(ss); tv = vp_warp_sum(tv); ts = vp_warp_sum(ts);
+    __shared__ double red[4][4];
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        red[0][w] = sv; red[1][w] = ss; red[2][w] = tv; red[3][w] = ts;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sv = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-        ss = red[1][0] + red[1][1] + red[1][2] + red[1][3];
-        // juce::Decibels::gainToDecibels(rms) < -60 (VocoderProcess.cpp:199-204)
-        double rv = sqrt(sv / (double)g.inSize), rs = sqrt(ss / (double)g.inSize);
-        double dv = rv > 0.0 ? fmax(-100.0, log10(rv) * 20.0) : -100.0;
-        double ds = rs > 0.0 ? fmax(-100.0, log10(rs) * 20.0) : -100.0;
-        uint8_t f = 0;
-        if (dv < -60.0) f |= VP_GATE_VOICE;
-        if (ds < -60.0) f |= VP_GATE_SYNTH;
-        if (fabs(dv + 60.0) < 1e-7 || fabs(ds + 60.0) < 1e-7) f |= VP_GATE_NEAR;
-        gate[(size_t)s * g.nBlocks + b] = f;
+    if (threadIdx.x < 4) {
+        const int q = threadIdx.x;
+        part[((size_t)s * g.nBlocks + b) * 4 + q] = (red[q][0] + red[q][1]) + (red[q][2] + red[q][3]);
     }
 }
 
-void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate) {
+__global__ void __launch_bounds__(128) k_gate_decide(VPGeom g, const double* __restrict__ part, uint8_t* __restrict__ gate,
+                                                     int q, long long tot) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= tot) return;
+    const int s = (int)(idx / g.nBlocks), b = (int)(idx - (long long)s * g.nBlocks);
+    const double* ps = part + (size_t)s * g.nBlocks * 4;
+    double sv = 0.0, ss = 0.0;
+    if (b - q >= 0) { sv = ps[(size_t)(b - q) * 4 + 2]; ss = ps[(size_t)(b - q) * 4 + 3]; }  // oldest: tail of block b - q
+    for (int j = q - 1; j >= 0; --j) {
+        if (b - j >= 0) { sv += ps[(size_t)(b - j) * 4 + 0]; ss += ps[(size_t)(b - j) * 4 + 1]; }
+    }
+    // juce::Decibels::gainToDecibels(rms) < -60 (VocoderProcess.cpp:199-204, MyBuffer.cpp:258-261, :299-302)
+    const double rv = sqrt(sv / (double)g.inSize), rs = sqrt(ss / (double)g.inSize);
+    const double dv = rv > 0.0 ? fmax(-100.0, log10(rv) * 20.0) : -100.0;
+    const double ds = rs > 0.0 ? fmax(-100.0, log10(rs) * 20.0) : -100.0;
+    uint8_t f = 0;
+    if (dv < -60.0) f |= VP_GATE_VOICE;
+    if (ds < -60.0) f |= VP_GATE_SYNTH;
+    if (fabs(dv + 60.0) < 1e-7 || fabs(ds + 60.0) < 1e-7) f |= VP_GATE_NEAR;
+    gate[idx] = f;
+}
+
+void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate,
+                    double* part) {
+    const int q = g.inSize / g.B, rem = g.inSize - q * g.B;
     dim3 grid(g.nBlocks, S);
-    k_gate<<<grid, 128, 0, st>>>(g, voice, synth, gate);
+    k_gate_partial<<<grid, 128, 0, st>>>(g, voice, synth, part, rem);
+    const long long tot = (long long)S * g.nBlocks;
+    k_gate_decide<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, part, gate, q, tot);
 }
 
 // ---------------------------------------------------------------------------
@@ -150,7 +173,7 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 // runs lane = (segment of 8) x (lag group of 4: voice lags 0-13, 14-27, 28-41, side-chain lags 0-13) with the same
 // register-window task as above. Only warp-level synchronisation.
 // ---------------------------------------------------------------------------
-#define AV_WARPS 4
+#define AV_WARPS 7   // 7 x 14.4 KB + window: two CTAs per SM = 14 warps
 #define AV_BATCH 32  // consecutive frames per warp: the initial ring fill is paid once per batch
 #define AV_NPRE 8    // prefetch registers per lane and signal: hop <= 32 * AV_NPRE
 
@@ -679,7 +702,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
 #pragma unroll
     for (int j = 0; j <= PS; ++j) { as[j] = 0.0; t[j] = 0.0; }
     int wrow = 0;  // window row of this lane's current frame in the current hop-row
-    float xn[4] = {0.f, 0.f, 0.f, 0.f};  // prefetched side-chain samples of the next block of four positions
+    float xA[4] = {0.f, 0.f, 0.f, 0.f}, xB[4] = {0.f, 0.f, 0.f, 0.f};  // side-chain samples of the next block / the one after
     bool primed = false;
     auto prefetch = [&](int k) {  // asynchronous copy of frame k's parameters into this lane's landing zone
         if (k >= 0 && k < g.nFramesV && (k & 3) == phi) {
@@ -741,50 +764,113 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
         const double* wr = wv + wrow * rowPad;
         const long long tBase = (long long)rho * hop;
         const bool emitRow = sOk && rho >= kS;
-        if (!primed) { vt_load4(y, tBase, g.lat, g.n, xn); primed = true; }
-        for (int i0 = 0; i0 < hop; i0 += 4) {
-            float xc[4];
-            double wc[4];
+        // Software pipeline inside a row (blocks of 4 positions): while block b runs its 4 x P dependent-on-one-value
+        // DFMA batches, the whitening FIR of block b+1 and the overlap-add shuffles + store of block b-1 are issued
+        // from the same straight-line code, so their latencies hide under the FP64 pipe. Samples are fetched two
+        // blocks ahead. The pipeline drains at the end of a row (a new frame may start at the next one).
+        const int nblk = (hop + 3) >> 2;
+        if (!primed) {
+            vt_load4(y, tBase, g.lat, g.n, xA);
+            vt_load4(y, (4 < hop) ? tBase + 4 : tBase + hop, g.lat, g.n, xB);
+            primed = true;
+        }
+        double eN[4], wN[4];
+        {   // FIR of block 0 (not overlapped: once per row)
+            const int nb0 = min(4, hop);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { xc[j] = xn[j]; wc[j] = wr[min(i0 + j, hop - 1)]; }
-            // software prefetch: the samples of the next block (positions are contiguous across rows)
-            vt_load4(y, (i0 + 4 < hop) ? tBase + i0 + 4 : tBase + hop, g.lat, g.n, xn);
-            const int nb = min(4, hop - i0);
-            // ---- all FP64 work of the block first (straight-line, so the scheduler can overlap the steps) ...
-            double e[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {  // whitening FIR of the side-chain, transposed form (independent of the IIR state)
-                e[j] = 0.0;
-                if (j < nb) {
-                    const double x = (double)xc[j] * wc[j];
-                    e[j] = fma(as[0], x, t[0]);
+            for (int j = 0; j < 4; ++j) {
+                wN[j] = wr[min(j, hop - 1)];
+                eN[j] = 0.0;
+                if (j < nb0) {
+                    const double x = (double)xA[j] * wN[j];
+                    eN[j] = fma(as[0], x, t[0]);
 #pragma unroll
                     for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xA[j] = xB[j];
+            // samples of block 2 of this row, or of the first block(s) of the next row
+            vt_load4(y, (8 < hop) ? tBase + 8 : ((4 < hop) ? tBase + hop : tBase + hop + 4), g.lat, g.n, xB);
+        }
+        float cP[4] = {0.f, 0.f, 0.f, 0.f};
+        long long tP = 0;
+        int nbP = 0;
+        // FULL: block b and block b+1 are both complete blocks of this row -> no guards, one basic block
+        auto blockStep = [&](auto fullTag, int b) {
+            constexpr bool FULL = decltype(fullTag)::value;
+            const int i0 = b << 2;
+            const int nb = FULL ? 4 : min(4, hop - i0);
+            double e[4], wc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { e[j] = eN[j]; wc[j] = wN[j]; }
+            // ---- FIR of block b+1 (same row only)
+            if (FULL || b + 1 < nblk) {
+                const int i1 = i0 + 4, nb1 = FULL ? 4 : min(4, hop - i1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    wN[j] = FULL ? wr[i1 + j] : wr[min(i1 + j, hop - 1)];
+                    eN[j] = 0.0;
+                    if (FULL || j < nb1) {
+                        const double x = (double)xA[j] * wN[j];
+                        eN[j] = fma(as[0], x, t[0]);
+#pragma unroll
+                        for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xA[j] = xB[j];
+                // start of the block three ahead in the global block sequence (rows are contiguous in position)
+                const int i3 = i0 + 12;
+                long long tn;
+                if (i3 < hop) tn = tBase + i3;
+                else if (i0 + 8 < hop) tn = tBase + hop;          // block b+2 is the row's last: b+3 = next row, block 0
+                else tn = tBase + hop + 4;                        // block b+1 is the row's last: b+3 = next row, block 1
+                vt_load4(y, tn, g.lat, g.n, xB);
+            }
+            // ---- all-pole recursion of block b
             float c[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (j < nb) {
+                if (FULL || j < nb) {
                     const double ov = e[j] + st[0];
 #pragma unroll
                     for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
                     c[j] = (float)(gv * ov * wc[j]);
                 } else c[j] = 0.0f;
             }
-            // ---- ... then the overlap-add of the 4 phase lanes for the 4 positions: transpose-reduce, 3 shuffles.
-            // lane phi ends with sum over the group of c[phi].
+            // ---- overlap-add of the 4 phase lanes for the 4 positions of block b-1: transpose-reduce, 3 shuffles;
+            // lane phi ends with the sum over the group of cP[phi] (block -1 of a row: zeros, nbP = 0 -> no store)
             {
                 const bool hi = (phi & 2) != 0, od = (phi & 1) != 0;
-                const float s0 = hi ? c[0] : c[2], s1 = hi ? c[1] : c[3];   // send the pair the partner (xor 2) is responsible for
-                const float k0 = hi ? c[2] : c[0], k1 = hi ? c[3] : c[1];   // keep the own pair
+                const float s0 = hi ? cP[0] : cP[2], s1 = hi ? cP[1] : cP[3];   // send the pair the partner (xor 2) owns
+                const float k0 = hi ? cP[2] : cP[0], k1 = hi ? cP[3] : cP[1];   // keep the own pair
                 const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
                 const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
                 const float snd = od ? r0 : r1, kp = od ? r1 : r0;
                 const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
-                const long long tp = tBase + i0 + phi;
-                if (emitRow && phi < nb && tp >= emit0 && tp < emit1) o[tp] = tot;
+                const long long tp = tP + phi;
+                if (emitRow && phi < nbP && tp >= emit0 && tp < emit1) o[tp] = tot;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cP[j] = c[j];
+            tP = tBase + i0;
+            nbP = nb;
+        };
+        const int nFullPairs = (hop >> 2) - 1;  // blocks b with b and b+1 both full: b < hop/4 - 1
+        int b = 0;
+        for (; b < nFullPairs; ++b) blockStep(std::true_type{}, b);
+        for (; b < nblk; ++b) blockStep(std::false_type{}, b);
+        {   // drain: the row's last block
+            const bool hi = (phi & 2) != 0, od = (phi & 1) != 0;
+            const float s0 = hi ? cP[0] : cP[2], s1 = hi ? cP[1] : cP[3];
+            const float k0 = hi ? cP[2] : cP[0], k1 = hi ? cP[3] : cP[1];
+            const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+            const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+            const float snd = od ? r0 : r1, kp = od ? r1 : r0;
+            const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+            const long long tp = tP + phi;
+            if (emitRow && phi < nbP && tp >= emit0 && tp < emit1) o[tp] = tot;
         }
         ++wrow;
     }
