@@ -212,7 +212,9 @@ def run_engine(args, wl, group):
     sampler = ClockSampler(dev)
 
     # ---- device-resident: W warm-up + K timed steps, barrier + sync on both sides
+    # every step = prepareToPlay + the whole batch: reset() rewinds the streams (consecutive calls would continue them)
     for _ in range(args.warmup):
+        eng.reset()
         eng.process_device(nBlocks, dv, dl, None, do, None, n, sync=False)
     eng.sync()
     l0 = eng.stats()["kernel_launches"]
@@ -221,6 +223,7 @@ def run_engine(args, wl, group):
     t0 = time.time()
     eng.timer_record(0)
     for _ in range(args.steps):
+        eng.reset()
         eng.process_device(nBlocks, dv, dl, None, do, None, n, sync=False)
     eng.timer_record(1)
     eng.sync()
@@ -246,10 +249,12 @@ def run_engine(args, wl, group):
         dv = dl = do = None
         we = max(1, min(args.warmup, 2))
         for _ in range(we):
+            eng.reset()
             eng.process_host_ptrs(nBlocks, hv.ptr, hl.ptr, None, ho.ptr, None, n)
         group.barrier()
         te0 = time.time()
         for _ in range(args.steps):
+            eng.reset()
             eng.process_host_ptrs(nBlocks, hv.ptr, hl.ptr, None, ho.ptr, None, n)  # returns with outputs in host memory
         te = time.time() - te0
         group.barrier()

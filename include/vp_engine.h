@@ -9,9 +9,9 @@
  * ABI; INTEGRATION.md shows the PluginProcessor-side binding.
  *
  * Semantics. One "stream" is one plug-in instance (1 mono voice + stereo
- * side-chain in, stereo out). vp_engine_process* is equivalent, per stream,
- * to: construct the plug-in, set the parameters, prepareToPlay(sampleRate,
- * samplesPerBlock), then nBlocks consecutive processBlock calls. Results do
+ * side-chain in, stereo out). vp_engine_prepare is prepareToPlay(sampleRate,
+ * samplesPerBlock) for every stream; each vp_engine_process* call is, per
+ * stream, nBlocks further consecutive processBlock calls. Results do
  * depend (sparsely) on samplesPerBlock exactly as in the reference (whole-ring
  * RMS gate, MyBuffer.cpp:258-261; PSOLA look-ahead test, PitchProcess.cpp:
  * 799-803), hence the "virtual block size" argument of vp_engine_prepare.
@@ -110,6 +110,12 @@ int vp_engine_prepare(vp_engine* e, double sampleRate, int samplesPerBlock, int 
                       size_t workspaceBytes);
 int vp_engine_set_params(vp_engine* e, const vp_params* p);
 int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out);
+
+/* Back to the state right after vp_engine_prepare (= prepareToPlay): rings cleared, histories and pitch marks
+ * forgotten, block counter 0. Consecutive vp_engine_process_* calls otherwise CONTINUE the streams: calling with
+ * nBlocks = a then nBlocks = b gives the output of one call with nBlocks = a + b (the carried per-stream state is what
+ * MyBuffer / VocoderProcess / PitchProcess keep between processBlock calls). */
+int vp_engine_reset(vp_engine* e);
 
 /* ---- processing ----------------------------------------------------------- */
 /* Device-resident batch. Layouts (row stride = strideSamples floats):

@@ -173,6 +173,7 @@ def test_shard_pass_and_path_invariance_bitwise(vp):
         e4.h2d(dv, voice); e4.h2d(dl, sl)
         c = np.zeros((S, n), np.float32)
         for _ in range(2):
+            e4.reset()  # consecutive calls continue the streams; reset = prepareToPlay again
             e4.process_device(n // B, dv, dl, None, do, None, n)
             e4.d2h(c, do)
             assert np.array_equal(c, outL)
@@ -186,6 +187,65 @@ def test_shard_pass_and_path_invariance_bitwise(vp):
             e4.device_free(p)
     finally:
         e4.close()
+
+
+@pytest.mark.parametrize("fs,B,pieces,params", [
+    (44100.0, 1024, (7, 1, 16, 24), dict(keyPitch=3)),
+    (48000.0, 1024, (1, 1, 2, 3, 5, 36), dict()),
+    (44100.0, 1000, (5, 43), dict(gainVoice=-6.0, gainSynth=-12.0)),
+    (44100.0, 512, (30, 30, 36), dict(lpcVoice=24, lpcSynth=8, lpcPitch=20)),   # generic-order kernels
+])
+def test_consecutive_calls_continue_the_streams(vp, fs, B, pieces, params):
+    """nBlocks = a then b then ... must give exactly the output of one call with the sum: the engine carries what
+    MyBuffer / VocoderProcess / PitchProcess keep between processBlock calls (rings, energy histories, pitch marks)."""
+    S, nb = 5, sum(pieces)
+    n = nb * B
+    voice, sl, sr = vp.synth_host(fs, S, n, flavour=0, first_stream=300)
+    ref = vp.Engine(fs, B, S, nb, params=vp.default_params(**params))
+    refL, refR = ref.process(voice, sl, sr)
+    ref_frames = [(f.flags, f.period, f.note, list(f.anMarks[:f.nAn]), list(f.stMarks[:f.nSt])) for f in ref.pitch_frames(2)]
+    ref.close()
+    eng = vp.Engine(fs, B, S, max(pieces), params=vp.default_params(**params))
+    try:
+        outL, outR, frames, b0 = [], [], [], 0
+        for k in pieces:
+            sl_ = slice(b0 * B, (b0 + k) * B)
+            l, r = eng.process(voice[:, sl_], sl[:, sl_], sr[:, sl_])
+            outL.append(l); outR.append(r)
+            frames += [(f.flags, f.period, f.note, list(f.anMarks[:f.nAn]), list(f.stMarks[:f.nSt])) for f in eng.pitch_frames(2)]
+            b0 += k
+        outL, outR = np.concatenate(outL, axis=1), np.concatenate(outR, axis=1)
+        assert frames == ref_frames
+        if "lpcVoice" in params:
+            # generic-order fallback kernels: the overlap-add groups its float partial sums by tile, and the tiling
+            # follows the call boundaries -> equal up to float rounding of the sum order
+            assert np.abs(outL - refL).max() <= 4e-7 and np.abs(outR - refR).max() <= 4e-7
+        else:
+            assert np.array_equal(outL, refL) and np.array_equal(outR, refR)  # bit-exact
+        eng.reset()  # and reset really is prepareToPlay
+        l, r = eng.process(voice[:, :pieces[0] * B], sl[:, :pieces[0] * B], sr[:, :pieces[0] * B])
+        assert np.abs(l - refL[:, :pieces[0] * B]).max() <= (4e-7 if "lpcVoice" in params else 0.0)
+    finally:
+        eng.close()
+
+
+def test_block_by_block_streaming_matches_oracle(vp, oracle):
+    """Config-5 style: one call per host block of 128 samples (what processBlock is), 1.5 s, vs the oracle's run."""
+    fs, B, S = 44100.0, 128, 3
+    nb = int(fs * 1.5) // B
+    voice, sl, sr = vp.synth_host(fs, S, nb * B, flavour=0, first_stream=500)
+    eng = vp.Engine(fs, B, S, 1, params=vp.default_params())
+    try:
+        out = np.zeros((S, nb * B), np.float32)
+        for b in range(nb):
+            sl_ = slice(b * B, (b + 1) * B)
+            l, _ = eng.process(voice[:, sl_], sl[:, sl_], None, want_right=False)
+            out[:, sl_] = l
+    finally:
+        eng.close()
+    for s in range(S):
+        r = oracle.run(fs, B, voice[s], sl[s], params=refbind.default_params())
+        assert_audio(r["outL"], out[s], "stream %d" % s)
 
 
 def test_many_streams_spot_parity(vp, oracle):

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "vp_engine_get_voc_frames", "vp_engine_get_stats", "vp_engine_last_timing", "vp_stage_name",
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
-    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2",
+    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset",
 ]
 
 
@@ -100,6 +100,7 @@ def load_library(path=None):
         "vp_synth_device": (i, [vp, dbl, i, i, i, sz, sz, fp, fp, fp]),
         "vp_measure_peaks": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "vp_engine_timing_reset": (i, [vp, i]),
+        "vp_engine_reset": (i, [vp]),
         "vp_measure_peaks2": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "vp_engine_last_timing_counts": (i, [vp, C.POINTER(i)]),
         "vp_engine_timer_record": (i, [vp, i]),
@@ -217,6 +218,10 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def reset(self):
+        """prepareToPlay again: forget every stream's history; the next process call starts at block 0."""
+        self._check(self.lib.vp_engine_reset(self.h))
 
     def set_params(self, params):
         self._check(self.lib.vp_engine_set_params(self.h, C.byref(params)))

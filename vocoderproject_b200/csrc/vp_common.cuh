@@ -26,38 +26,78 @@ struct VPGeom {
     float gainVocF, gainPitchF, gainVoiceF, gainSynthF;  // decibelsToGain<float>(dB, -59)
     int vocOn, pitchOn, dryOn, synthOn;
     double yinEps;  // relative margin below which the FP32 YIN decision is re-done in FP64
+    // ---- continuation (consecutive process calls = consecutive processBlock calls). Kernels work in CALL-LOCAL
+    // coordinates: delayed position 0 = first output sample of this call (global position u0 = blocks done * B).
+    const float* histV;  // [S][H] the H input samples that precede this call, per stream (zeros before time 0)
+    const float* histS;  //        same for side-chain channel 0
+    const float* histR;  //        same for side-chain channel 1 (only when the dry side-chain is mixed in)
+    int H;               // history length in samples (>= latency + frameLenP + 3 chunk + max LPC order)
+    int offV, offP;      // local position of the first vocoder / pitch frame that starts inside this call
+    int kV0, fP0;        // global index of that frame (frames before it belong to earlier calls)
+    int hasPrev;         // 1 = an earlier call exists (carry rows / pending pitch frame are valid)
 };
 
 // Per-frame row of the vocoder's autocorrelation workspace: lags 0..order (raw sums) followed by the frame's last
 // `order` windowed samples (the Levinson kernel's residual-energy correction reads them instead of re-gathering).
-__host__ __device__ inline int vp_row(int order) { return 2 * order + 1; }
+__host__ __device__ inline int vp_rowlen(int order) { return 2 * order + 1; }
 
 // gate flags per (stream, block)
 #define VP_GATE_VOICE 1
 #define VP_GATE_SYNTH 2
 #define VP_GATE_NEAR 4
 
-// Voice / synth sample at delayed position u of a stream row (MyBuffer.cpp:142-172).
-__device__ __forceinline__ float vp_x(const float* __restrict__ row, long long u, int lat, long long n) {
-    long long t = u - lat;
-    return (t >= 0 && t < n) ? __ldg(row + t) : 0.0f;
+// Frame-indexed vocoder workspace (coefficient rows, energies, gains): per stream VP_VC carry rows (the last frames
+// of the previous call: they still overlap this call's first output positions) followed by this call's frames.
+#define VP_VC 4
+__host__ __device__ inline size_t vp_vrow(const VPGeom& g, int s, int k) { return (size_t)s * (size_t)(g.nFramesV + VP_VC) + VP_VC + k; }
+// Pitch frames: two carry slots (the last two frames of earlier calls can still own output positions of this call:
+// frame length 4 chunks, hop 3 chunks), then this call's frames.
+#define VP_PC 2
+__host__ __device__ inline size_t vp_prow(const VPGeom& g, int s, int f) { return (size_t)s * (size_t)(g.nFramesP + VP_PC) + VP_PC + f; }
+
+// PitchProcess state that survives from one frame to the next (PitchProcess.cpp:76-92, :415-425) and therefore from one
+// call to the next: pitch history, and the STORAGE of the analysis / synthesis mark vectors (slot values survive clear()).
+struct VPMarkState {
+    int period, prevPeriod, prevVoicedPeriod, periodNew, voiced, prevVoiced, nAn, nSt;
+    double beta;
+    int an[VP_SLOTS], st[VP_SLOTS];
+};
+
+// One stream's input as seen by a call: x = the samples handed to this call, h = the H samples before them.
+struct VPRow {
+    const float* x;
+    const float* h;
+};
+__device__ __forceinline__ VPRow vp_row(const float* base, const float* hist, int s, const VPGeom& g) {
+    VPRow r;
+    r.x = base + (size_t)s * g.stride;
+    r.h = hist + (size_t)s * g.H;
+    return r;
 }
 
-// Cooperative staging of `count` consecutive samples (delayed positions u0 .. u0+count-1) of a stream row into shared
+// Voice / synth sample at (call-local) delayed position u of a stream (MyBuffer.cpp:142-172): input index u - latency;
+// negative indices reach into the carried history (the ring's samplesToKeep + latency part), zeros beyond it.
+__device__ __forceinline__ float vp_x(const VPRow& row, long long u, const VPGeom& g) {
+    const long long t = u - g.lat;
+    if (t >= 0) return (t < g.n) ? __ldg(row.x + t) : 0.0f;
+    return (t >= -(long long)g.H) ? __ldg(row.h + g.H + t) : 0.0f;
+}
+
+// Cooperative staging of `count` consecutive samples (delayed positions u0 .. u0+count-1) of a stream into shared
 // memory by `nthr` threads. Loads are issued in batches of UN per thread BEFORE the first store, so a thread has UN
 // global loads in flight instead of one (a plain `for (...) dst[j] = vp_x(...)` loop serialises on the load latency).
 template <int UN, typename T>
-__device__ __forceinline__ void vp_stage(T* __restrict__ dst, const float* __restrict__ row, long long u0, int count,
-                                         int lat, long long n, int tid, int nthr) {
-    const long long t0 = u0 - lat;
-    const bool inside = t0 >= 0 && t0 + count <= n;
+__device__ __forceinline__ void vp_stage(T* __restrict__ dst, const VPRow& row, long long u0, int count, const VPGeom& g,
+                                         int tid, int nthr) {
+    const long long t0 = u0 - g.lat;
+    const bool inside = t0 >= 0 && t0 + count <= g.n;
     for (int base = tid; base < count; base += nthr * UN) {
         float tmp[UN];
 #pragma unroll
         for (int k = 0; k < UN; ++k) {
             const int j = base + k * nthr;
-            if (inside) tmp[k] = (j < count) ? __ldg(row + t0 + j) : 0.0f;
-            else { const long long t = t0 + j; tmp[k] = (j < count && t >= 0 && t < n) ? __ldg(row + t) : 0.0f; }
+            if (inside) tmp[k] = (j < count) ? __ldg(row.x + t0 + j) : 0.0f;
+            else tmp[k] = (j < count) ? vp_x(row, u0 + j, g) : 0.0f;
         }
 #pragma unroll
         for (int k = 0; k < UN; ++k) {
@@ -97,8 +137,11 @@ struct VPTables {
     const int* lutNote;      // per period: snapped note index         Notes.cpp:79-110
 };
 
+int vp_gate_carry_rows(const VPGeom& g);
 void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate,
-                    double* part /* [S][nBlocks][4] scratch */);
+                    double* part /* [S][partRows][4]: carry rows then this call's blocks */, int partRows);
+void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G,
+                        double* hist /* [S][20] carried energy histories */);
 
 void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                             const float* synth, const uint8_t* gate, double* rV, double* rS);
@@ -107,8 +150,7 @@ void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb
                             double* aS, double* EeV, double* EeS);
 bool vp_voc_synth_needs_clear(const VPGeom& g);  // false: the kernel writes every output position itself
 void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
-                         const uint8_t* gate, const double* aV, const double* aS, const double* EeV,
-                         const double* EeS, double* gOut, float* outV);
+                         const double* aV, const double* aS, const double* EeS, const double* G, float* outV);
 
 void vp_launch_yin(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                    uint32_t* yflags, int* recheckList, int* recheckCount, int maxList);
@@ -121,7 +163,8 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
 void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                            uint32_t* yflags, const int* recheckList, const int* recheckCount, int maxList);
 void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
-                     const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames);
+                     const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames,
+                     VPMarkState* carry);
 void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* voice, const vp_pitch_frame* frames,
                          double* rP, double* aP);
 void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
@@ -130,6 +173,12 @@ void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
                          const double* aP, const float* outE, float* outP);
 void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
                    const float* synthR, const float* outV, const float* outP, float* outL, float* outR);
+
+void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int rowBytes, int C, long long wsRowsPerStream);
+void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int rowBytes, int C, long long nNew,
+                         long long wsRowsPerStream);
+void vp_launch_hist_update(cudaStream_t st, float* hNew, const float* hOld, const float* x, int S, int H, long long n,
+                           long long stride);
 
 void vp_launch_synth(cudaStream_t st, const void* streams, int nStreams, long long nSamples, long long stride,
                      float* voice, float* synthL, float* synthR);

@@ -43,6 +43,15 @@ struct vp_engine {
     // workspace (device), sized for Sc streams x maxBlocks
     uint8_t* dGate = nullptr;
     double* dGatePart = nullptr;
+    // ---- state carried from call to call, for all S streams (vp_engine_reset zeroes it = prepareToPlay)
+    long long blocksDone = 0;          // host blocks processed since prepare / reset
+    int H = 0;                         // input history length
+    int gateCarry = 0;                 // carried gate block partials per stream (inSize / B + 1)
+    int histCur = 0;                   // which of the two history buffers is current
+    float* cHist[2][3] = {{nullptr}};  // [buffer][voice, synth ch0, synth ch1][S][H]
+    double *cGate = nullptr, *cAV = nullptr, *cAS = nullptr, *cEeS = nullptr, *cG = nullptr, *cGainHist = nullptr;
+    vp_pitch_frame* cFrames = nullptr; // [S][VP_PC]
+    VPMarkState* cMarks = nullptr;     // [S]
     double *dRV = nullptr, *dRS = nullptr, *dAV = nullptr, *dAS = nullptr, *dEeV = nullptr, *dEeS = nullptr, *dG = nullptr;
     int *dPeriod = nullptr, *dList = nullptr, *dListCount = nullptr;
     uint32_t* dYFlags = nullptr;
@@ -60,6 +69,7 @@ struct vp_engine {
     double *dEeVAll = nullptr, *dEeSAll = nullptr, *dGAll = nullptr;
     bool keepDecisions = true;
     int lastBlocks = 0;
+    VPGeom lastG;  // geometry of the most recent process call (frame counts depend on where the timeline stood)
     // host-path staging (device), 3 slices
     int Sh = 0;
     float* hIn[3][3] = {{nullptr}};
@@ -221,6 +231,10 @@ static int build_tables(vp_engine* e) {
 }
 
 static void free_workspace(vp_engine* e) {
+    void** cptrs[] = {(void**)&e->cGate, (void**)&e->cAV, (void**)&e->cAS, (void**)&e->cEeS, (void**)&e->cG, (void**)&e->cGainHist,
+                      (void**)&e->cFrames, (void**)&e->cMarks};
+    for (void** p : cptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) if (e->cHist[i][j]) { cudaFree(e->cHist[i][j]); e->cHist[i][j] = nullptr; }
     void** ptrs[] = {(void**)&e->dGate, (void**)&e->dRV, (void**)&e->dRS, (void**)&e->dAV, (void**)&e->dAS, (void**)&e->dEeV,
                      (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
                      (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
@@ -325,6 +339,36 @@ static void frame_counts(const vp_sizes& z, long long n, int* nV, int* nP) {
     *nP = (int)((n + z.hopP - 1) / z.hopP);
 }
 
+// prepareToPlay state: rings cleared (MyBuffer.cpp:56-58), histories zero, no marks, beta = 1 (PitchProcess.cpp:76-92)
+static int reset_state(vp_engine* e) {
+    const size_t S = (size_t)e->S;
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) VP_CUDA_OK(cudaMemsetAsync(e->cHist[i][j], 0, S * e->H * sizeof(float), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cGate, 0, S * e->gateCarry * 4 * sizeof(double), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cAV, 0, S * VP_VC * (e->capV + 1) * sizeof(double), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cAS, 0, S * VP_VC * (e->capS + 1) * sizeof(double), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cEeS, 0, S * VP_VC * sizeof(double), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cG, 0, S * VP_VC * sizeof(double), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cGainHist, 0, S * 20 * sizeof(double), e->st));
+    VP_CUDA_OK(cudaMemsetAsync(e->cFrames, 0, S * VP_PC * sizeof(vp_pitch_frame), e->st));
+    std::vector<VPMarkState> ms(S);
+    memset(ms.data(), 0, S * sizeof(VPMarkState));
+    for (size_t i = 0; i < S; ++i) ms[i].beta = 1.0;
+    VP_CUDA_OK(cudaMemcpyAsync(e->cMarks, ms.data(), S * sizeof(VPMarkState), cudaMemcpyHostToDevice, e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    e->blocksDone = 0;
+    e->histCur = 0;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_reset(vp_engine* e) {
+    if (!e) return VP_E_ARG;
+    if (!e->prepared) return vp_err(e, VP_E_STATE, "vp_engine_prepare has not been called");
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st2));
+    return reset_state(e);
+}
+
 extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxBlocks, size_t workspaceBytes) {
     if (!e) return VP_E_ARG;
     if (S <= 0 || maxBlocks <= 0 || B <= 0) return vp_err(e, VP_E_ARG, "nStreams, maxBlocks, samplesPerBlock must be > 0");
@@ -368,25 +412,28 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     e->Sc = (int)Sc;
     e->workspace = perStream * (size_t)Sc;
     const size_t fV = (size_t)Sc * nV, fP = (size_t)Sc * nP;
+    const size_t fVc = (size_t)Sc * (nV + VP_VC), fPc = (size_t)Sc * (nP + VP_PC);  // with the carry rows in front
+    e->gateCarry = z.inSize / B + 1;
+    e->H = (z.latency + z.frameLenP + 3 * z.chunk + VP_ORDER_MAX + 3) & ~3;
     if ((rc = wsalloc(e, &e->dGate, (size_t)Sc * maxBlocks))) return rc;
-    if ((rc = wsalloc(e, &e->dGatePart, (size_t)Sc * maxBlocks * 4))) return rc;
-    if ((rc = wsalloc(e, &e->dRV, fV * vp_row(e->prm.lpcVoice)))) return rc;
-    if ((rc = wsalloc(e, &e->dRS, fV * vp_row(e->prm.lpcSynth)))) return rc;
-    if ((rc = wsalloc(e, &e->dAV, fV * (e->prm.lpcVoice + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dAS, fV * (e->prm.lpcSynth + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dEeV, fV))) return rc;
-    if ((rc = wsalloc(e, &e->dEeS, fV))) return rc;
-    if ((rc = wsalloc(e, &e->dG, fV))) return rc;
+    if ((rc = wsalloc(e, &e->dGatePart, (size_t)Sc * (maxBlocks + e->gateCarry) * 4))) return rc;
+    if ((rc = wsalloc(e, &e->dRV, fV * vp_rowlen(e->prm.lpcVoice)))) return rc;
+    if ((rc = wsalloc(e, &e->dRS, fV * vp_rowlen(e->prm.lpcSynth)))) return rc;
+    if ((rc = wsalloc(e, &e->dAV, fVc * (e->prm.lpcVoice + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dAS, fVc * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dEeV, fVc))) return rc;
+    if ((rc = wsalloc(e, &e->dEeS, fVc))) return rc;
+    if ((rc = wsalloc(e, &e->dG, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dPeriod, fP))) return rc;
     if ((rc = wsalloc(e, &e->dYFlags, fP))) return rc;
     e->maxList = (int)std::min<size_t>(fP, (size_t)1 << 22);
     if ((rc = wsalloc(e, &e->dList, (size_t)e->maxList))) return rc;
     if ((rc = wsalloc(e, &e->dListCount, 1024))) return rc;
     VP_CUDA_OK(cudaMemset(e->dListCount, 0, 1024 * sizeof(int)));
-    if ((rc = wsalloc(e, &e->dFrames, fP))) return rc;
-    if ((rc = wsalloc(e, &e->dAP, fP * (e->prm.lpcPitch + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dRP, fP * (e->prm.lpcPitch + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dOutE, fP * (size_t)z.frameLenP))) return rc;
+    if ((rc = wsalloc(e, &e->dFrames, fPc))) return rc;
+    if ((rc = wsalloc(e, &e->dAP, fPc * (e->prm.lpcPitch + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dRP, fPc * (e->prm.lpcPitch + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dOutE, fPc * (size_t)z.frameLenP))) return rc;
     if ((rc = wsalloc(e, &e->dYinP, (size_t)Sc * yinP))) return rc;
     if ((rc = wsalloc(e, &e->dYinE, e->yinDirect ? 1 : (size_t)Sc * vp_yin_corr_chunks(gy)))) return rc;
     if ((rc = wsalloc(e, &e->dOutV, (size_t)Sc * n))) return rc;
@@ -401,6 +448,18 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
         if ((rc = wsalloc(e, &e->dEeSAll, (size_t)S * nV))) return rc;
         if ((rc = wsalloc(e, &e->dGAll, (size_t)S * nV))) return rc;
     }
+    // carried state, all S streams
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) if ((rc = wsalloc(e, &e->cHist[i][j], (size_t)S * e->H))) return rc;
+    if ((rc = wsalloc(e, &e->cGate, (size_t)S * e->gateCarry * 4))) return rc;
+    if ((rc = wsalloc(e, &e->cAV, (size_t)S * VP_VC * (e->prm.lpcVoice + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->cAS, (size_t)S * VP_VC * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->cEeS, (size_t)S * VP_VC))) return rc;
+    if ((rc = wsalloc(e, &e->cG, (size_t)S * VP_VC))) return rc;
+    if ((rc = wsalloc(e, &e->cGainHist, (size_t)S * 20))) return rc;
+    if ((rc = wsalloc(e, &e->cFrames, (size_t)S * VP_PC))) return rc;
+    if ((rc = wsalloc(e, &e->cMarks, (size_t)S))) return rc;
+    e->capV = e->prm.lpcVoice; e->capS = e->prm.lpcSynth; e->capP = e->prm.lpcPitch;
+    if ((rc = reset_state(e))) return rc;
     e->launches = e->yinRechecked = e->yinFrames = 0;
     e->capV = e->prm.lpcVoice; e->capS = e->prm.lpcSynth; e->capP = e->prm.lpcPitch;
     e->prepared = true;
@@ -444,7 +503,17 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     g->tauMin = z.tauMin; g->tauMax = z.tauMax; g->lat = z.latency; g->keep = z.keep; g->inSize = z.inSize; g->anCap = z.anCap;
     g->nBlocks = nBlocks; g->n = (long long)nBlocks * e->B; g->stride = (long long)stride;
     g->wstride = (long long)e->maxBlocks * e->B;
-    frame_counts(z, g->n, &g->nFramesV, &g->nFramesP);
+    {   // call-local frame grid: the timeline continues where the previous call ended
+        const long long u0 = e->blocksDone * (long long)e->B;
+        g->offV = (int)((z.hopV - (u0 % z.hopV)) % z.hopV);
+        g->offP = (int)((z.hopP - (u0 % z.hopP)) % z.hopP);
+        g->kV0 = (int)((u0 + z.hopV - 1) / z.hopV);
+        g->fP0 = (int)((u0 + z.hopP - 1) / z.hopP);
+        g->nFramesV = (g->n > g->offV) ? (int)((g->n - g->offV + z.hopV - 1) / z.hopV) : 0;
+        g->nFramesP = (g->n > g->offP) ? (int)((g->n - g->offP + z.hopP - 1) / z.hopP) : 0;
+        g->hasPrev = e->blocksDone > 0;
+        g->H = e->H;
+    }
     g->ordV = e->prm.lpcVoice; g->ordS = e->prm.lpcSynth; g->ordP = e->prm.lpcPitch;
     g->gainVocF = db_to_gain(e->prm.gainVoc); g->gainPitchF = db_to_gain(e->prm.gainPitch);
     g->gainVoiceF = db_to_gain(e->prm.gainVoice); g->gainSynthF = db_to_gain(e->prm.gainSynth);
@@ -455,65 +524,88 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     return VP_OK;
 }
 
-// One pass over Sc' <= Sc streams whose I/O rows start at the given pointers.
+// One pass over Sc' <= Sc streams whose I/O rows start at the given pointers. streamBase = index of the pass's first
+// stream in the engine's batch (selects its carried state).
 static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, const float* voice, const float* synthL,
                     const float* synthR, float* outL, float* outR) {
     cudaStream_t st = e->st;
     VPTables tb = {e->dWV, e->dStP, e->dHann, e->dHannOff, e->dLutBeta, e->dLutPeriodNew, e->dLutNote};
-    const VPGeom& g = gIO;
+    VPGeom g = gIO;
+    const int hc = e->histCur;
+    const size_t sb = (size_t)streamBase;
+    g.histV = e->cHist[hc][0] + sb * e->H;
+    g.histS = e->cHist[hc][1] + sb * e->H;
+    g.histR = e->cHist[hc][2] + sb * e->H;
     int* listCount = e->dListCount + (e->passCount % 1024);
     e->passCount++;
-    const size_t fV = (size_t)Sp * g.nFramesV, fP = (size_t)Sp * g.nFramesP;
+    const size_t fP = (size_t)Sp * g.nFramesP;
+    const int ordV1 = g.ordV + 1, ordS1 = g.ordS + 1;
+    const long long rowsV = g.nFramesV + VP_VC, rowsP = g.nFramesP + VP_PC, rowsG = g.nBlocks + e->gateCarry;
     stage_mark(e, ST_OTHER);
-    vp_launch_gate(st, g, Sp, voice, synthL, e->dGate, e->dGatePart);
+    // ---- carried rows of the previous call in front of this call's rows
+    vp_launch_carry_in(st, e->dGatePart, e->cGate + sb * e->gateCarry * 4, Sp, 32, e->gateCarry, rowsG);
+    if (g.vocOn) {
+        vp_launch_carry_in(st, e->dAV, e->cAV + sb * VP_VC * ordV1, Sp, 8 * ordV1, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dAS, e->cAS + sb * VP_VC * ordS1, Sp, 8 * ordS1, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dEeS, e->cEeS + sb * VP_VC, Sp, 8, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dG, e->cG + sb * VP_VC, Sp, 8, VP_VC, rowsV);
+    }
+    if (g.pitchOn) vp_launch_carry_in(st, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
+    vp_launch_gate(st, g, Sp, voice, synthL, e->dGate, e->dGatePart, (int)rowsG);
     e->launches += 2;
     stage_mark(e, ST_GATE);
     // Order: YIN -> [side stream: pitch-mark chain, sequential per stream, latency-bound, few warps] running UNDER
-    // [main stream: the three vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.
+    // [main stream: the vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.
     bool forked = false;
     if (g.pitchOn) {
-        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.n * sizeof(float), st));
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), st));
         VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
         stage_mark(e, ST_CLEAR);
-        if (e->yinDirect) {
-            vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-            stage_mark(e, ST_YIN);
-        } else {
-            vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE);
-            stage_mark(e, ST_YIN);
-            vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-            stage_mark(e, ST_YIN_DECIDE);
+        if (g.nFramesP > 0) {
+            if (e->yinDirect) {
+                vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+                stage_mark(e, ST_YIN);
+            } else {
+                vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE);
+                stage_mark(e, ST_YIN);
+                vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+                stage_mark(e, ST_YIN_DECIDE);
+                e->launches++;
+            }
+            vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
+            stage_mark(e, ST_YIN64);
+            e->launches += 2;
+            if (e->overlapMarks && g.vocOn) {
+                VP_CUDA_OK(cudaEventRecord(e->evFork, st));
+                VP_CUDA_OK(cudaStreamWaitEvent(e->st2, e->evFork, 0));
+                side_mark(e);
+                vp_launch_marks(e->st2, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames, e->cMarks + sb);
+                side_mark(e);
+                VP_CUDA_OK(cudaEventRecord(e->evJoin, e->st2));
+                forked = true;
+            } else {
+                vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames, e->cMarks + sb);
+                stage_mark(e, ST_MARKS);
+            }
             e->launches++;
         }
-        vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-        stage_mark(e, ST_YIN64);
-        e->launches += 2;
-        if (e->overlapMarks && g.vocOn) {
-            VP_CUDA_OK(cudaEventRecord(e->evFork, st));
-            VP_CUDA_OK(cudaStreamWaitEvent(e->st2, e->evFork, 0));
-            side_mark(e);
-            vp_launch_marks(e->st2, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
-            side_mark(e);
-            VP_CUDA_OK(cudaEventRecord(e->evJoin, e->st2));
-            forked = true;
-        } else {
-            vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames);
-            stage_mark(e, ST_MARKS);
-        }
-        e->launches++;
     }
     if (g.vocOn) {
         if (vp_voc_synth_needs_clear(g)) {
-            VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.n * sizeof(float), st));
+            VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.wstride * sizeof(float), st));
             stage_mark(e, ST_CLEAR);
         }
-        vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
-        stage_mark(e, ST_VOC_AC);
-        vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
-        stage_mark(e, ST_VOC_LEV);
-        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dGate, e->dAV, e->dAS, e->dEeV, e->dEeS, e->dG, e->dOutV);
+        if (g.nFramesV > 0) {
+            vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
+            stage_mark(e, ST_VOC_AC);
+            vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
+            vp_launch_voc_gain(st, g, Sp, e->dEeV, e->dEeS, e->dG, e->cGainHist + sb * 20);
+            stage_mark(e, ST_VOC_LEV);
+            e->launches += 3;
+        }
+        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dAV, e->dAS, e->dEeS, e->dG, e->dOutV);
         stage_mark(e, ST_VOC_SYN);
-        e->launches += 3;
+        e->launches += 1;
     }
     if (g.pitchOn) {
         if (forked) {
@@ -532,21 +624,40 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     vp_launch_mix(st, g, Sp, voice, synthL, synthR, e->dOutV, e->dOutP, outL, outR);
     e->launches++;
     stage_mark(e, ST_MIX);
+    // ---- state for the next call: last rows of (carry ++ new), and the last H input samples
+    vp_launch_carry_out(st, e->cGate + sb * e->gateCarry * 4, e->dGatePart, Sp, 32, e->gateCarry, g.nBlocks, rowsG);
+    if (g.vocOn) {
+        vp_launch_carry_out(st, e->cAV + sb * VP_VC * ordV1, e->dAV, Sp, 8 * ordV1, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cAS + sb * VP_VC * ordS1, e->dAS, Sp, 8 * ordS1, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cEeS + sb * VP_VC, e->dEeS, Sp, 8, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cG + sb * VP_VC, e->dG, Sp, 8, VP_VC, g.nFramesV, rowsV);
+    }
+    if (g.pitchOn) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
+    vp_launch_hist_update(st, e->cHist[hc ^ 1][0] + sb * e->H, g.histV, voice, Sp, e->H, g.n, g.stride);
+    vp_launch_hist_update(st, e->cHist[hc ^ 1][1] + sb * e->H, g.histS, synthL, Sp, e->H, g.n, g.stride);
+    if (g.synthOn && synthR) vp_launch_hist_update(st, e->cHist[hc ^ 1][2] + sb * e->H, g.histR, synthR, Sp, e->H, g.n, g.stride);
     if (e->keepDecisions && streamBase >= 0) {
-        if (g.pitchOn)
-            VP_CUDA_OK(cudaMemcpyAsync(e->dFramesAll + (size_t)streamBase * g.nFramesP, e->dFrames, fP * sizeof(vp_pitch_frame),
-                                       cudaMemcpyDeviceToDevice, st));
-        VP_CUDA_OK(cudaMemcpyAsync(e->dGateAll + (size_t)streamBase * g.nBlocks, e->dGate, (size_t)Sp * g.nBlocks,
-                                   cudaMemcpyDeviceToDevice, st));
-        if (g.vocOn) {
-            VP_CUDA_OK(cudaMemcpyAsync(e->dEeVAll + (size_t)streamBase * g.nFramesV, e->dEeV, fV * 8, cudaMemcpyDeviceToDevice, st));
-            VP_CUDA_OK(cudaMemcpyAsync(e->dEeSAll + (size_t)streamBase * g.nFramesV, e->dEeS, fV * 8, cudaMemcpyDeviceToDevice, st));
-            VP_CUDA_OK(cudaMemcpyAsync(e->dGAll + (size_t)streamBase * g.nFramesV, e->dG, fV * 8, cudaMemcpyDeviceToDevice, st));
+        if (g.pitchOn && g.nFramesP > 0)
+            VP_CUDA_OK(cudaMemcpy2DAsync(e->dFramesAll + sb * g.nFramesP, (size_t)g.nFramesP * sizeof(vp_pitch_frame),
+                                         e->dFrames + VP_PC, (size_t)rowsP * sizeof(vp_pitch_frame),
+                                         (size_t)g.nFramesP * sizeof(vp_pitch_frame), Sp, cudaMemcpyDeviceToDevice, st));
+        VP_CUDA_OK(cudaMemcpyAsync(e->dGateAll + sb * g.nBlocks, e->dGate, (size_t)Sp * g.nBlocks, cudaMemcpyDeviceToDevice, st));
+        if (g.vocOn && g.nFramesV > 0) {
+            const size_t w = (size_t)g.nFramesV * 8, sp = (size_t)rowsV * 8;
+            VP_CUDA_OK(cudaMemcpy2DAsync(e->dEeVAll + sb * g.nFramesV, w, e->dEeV + VP_VC, sp, w, Sp, cudaMemcpyDeviceToDevice, st));
+            VP_CUDA_OK(cudaMemcpy2DAsync(e->dEeSAll + sb * g.nFramesV, w, e->dEeS + VP_VC, sp, w, Sp, cudaMemcpyDeviceToDevice, st));
+            VP_CUDA_OK(cudaMemcpy2DAsync(e->dGAll + sb * g.nFramesV, w, e->dG + VP_VC, sp, w, Sp, cudaMemcpyDeviceToDevice, st));
         }
         stage_mark(e, ST_OTHER);
     }
     VP_CUDA_OK(cudaGetLastError());
     return VP_OK;
+}
+
+// after the last pass of a call: the timeline has advanced
+static void finish_call(vp_engine* e, int nBlocks) {
+    e->blocksDone += nBlocks;
+    e->histCur ^= 1;
 }
 
 static int check_process_args(vp_engine* e, int nBlocks, const float* voice, const float* synthL, const float* synthR,
@@ -568,6 +679,7 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
     VPGeom g;
     make_geom(e, nBlocks, stride, &g);
     e->lastBlocks = nBlocks;
+    e->lastG = g;
     e->passCount = 0;
     if (!e->timingOpen) { e->evUsed = 0; e->evSideUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
     for (int s0 = 0; s0 < e->S; s0 += e->Sc) {
@@ -577,6 +689,7 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
                       outR ? outR + off : nullptr);
         if (rc) return rc;
     }
+    finish_call(e, nBlocks);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
     return VP_OK;
 }
@@ -615,6 +728,7 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     VPGeom g;
     make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense
     e->lastBlocks = nBlocks;
+    e->lastG = g;
     e->passCount = 0;
     const size_t rowB = (size_t)n * sizeof(float);
     int slice = 0;
@@ -642,6 +756,7 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
                                          cudaMemcpyDeviceToHost, e->stOut));
         VP_CUDA_OK(cudaEventRecord(e->evOut[bi], e->stOut));
     }
+    finish_call(e, nBlocks);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
     return vp_engine_sync(e);
 }
@@ -651,8 +766,7 @@ extern "C" int vp_engine_get_pitch_frames(vp_engine* e, int stream, vp_pitch_fra
     if (!e->prepared || e->lastBlocks == 0 || !e->keepDecisions) return VP_E_STATE;
     if (stream >= e->S) return VP_E_ARG;
     VP_CUDA_OK(cudaSetDevice(e->device));
-    VPGeom g;
-    make_geom(e, e->lastBlocks, 0, &g);
+    const VPGeom& g = e->lastG;
     const int nP = g.pitchOn ? g.nFramesP : 0;
     if (nFrames) *nFrames = nP;
     if (out && cap > 0 && nP > 0) {
@@ -669,8 +783,7 @@ extern "C" int vp_engine_get_voc_frames(vp_engine* e, int stream, int cap, int* 
     if (!e->prepared || e->lastBlocks == 0 || !e->keepDecisions) return VP_E_STATE;
     if (stream >= e->S) return VP_E_ARG;
     VP_CUDA_OK(cudaSetDevice(e->device));
-    VPGeom g;
-    make_geom(e, e->lastBlocks, 0, &g);
+    const VPGeom& g = e->lastG;
     const int nV = g.vocOn ? g.nFramesV : 0;
     if (nFrames) *nFrames = nV;
     const int m = std::min(cap, nV);
@@ -684,7 +797,7 @@ extern "C" int vp_engine_get_voc_frames(vp_engine* e, int stream, int cap, int* 
         std::vector<uint8_t> gb(g.nBlocks);
         VP_CUDA_OK(cudaMemcpy(gb.data(), e->dGateAll + (size_t)stream * g.nBlocks, (size_t)g.nBlocks, cudaMemcpyDeviceToHost));
         for (int k = 0; k < m; ++k) {
-            const int b = (int)(((long long)k * g.hopV) / g.B);
+            const int b = (int)(((long long)k * g.hopV + g.offV) / g.B);
             gated[k] = (gb[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) ? 1 : 0;
         }
     }

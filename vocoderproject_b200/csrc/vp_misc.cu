@@ -1,4 +1,6 @@
 // Mix/egress, synthetic-input generation and issue-rate microbenchmarks.
+#include <algorithm>
+
 #include "vp_common.cuh"
 #include "vp_synth.h"
 
@@ -19,12 +21,12 @@ __global__ void __launch_bounds__(256) k_mix(VPGeom g, const float* __restrict__
         if (g.pitchOn) l += outP[wrow + u];
         float r = l;
         if (g.dryOn) {
-            const float d = g.gainVoiceF * vp_x(voice + row, u, g.lat, g.n);
+            const float d = g.gainVoiceF * vp_x(vp_row(voice, g.histV, s, g), u, g);
             l += d; r += d;
         }
         if (g.synthOn) {
-            l += g.gainSynthF * vp_x(synthL + row, u, g.lat, g.n);
-            r += g.gainSynthF * vp_x((synthR ? synthR : synthL) + row, u, g.lat, g.n);
+            l += g.gainSynthF * vp_x(vp_row(synthL, g.histS, s, g), u, g);
+            r += g.gainSynthF * (synthR ? vp_x(vp_row(synthR, g.histR, s, g), u, g) : vp_x(vp_row(synthL, g.histS, s, g), u, g));
         }
         outL[row + u] = l;
         if (outR) outR[row + u] = r;
@@ -37,6 +39,61 @@ void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, 
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, S);
     k_mix<<<grid, 256, 0, st>>>(g, voice, synthL, synthR, outV, outP, outL, outR);
+}
+
+// ---------------------------------------------------------------------------
+// Carried per-stream state between calls (consecutive process calls = consecutive processBlock calls).
+// A frame-indexed workspace array holds, per stream, C carry rows followed by the rows of this call. carry_in copies the
+// stream's C stored rows in front; carry_out stores the LAST C rows of (carry ++ new) = rows [nNew, nNew + C).
+// Rows are counted in 4-byte words.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_carry_in(uint32_t* __restrict__ ws, const uint32_t* __restrict__ carry, int S,
+                                                  int rowWords, int C, long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * rowWords;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / ((long long)C * rowWords));
+        const long long r = i - (long long)s * C * rowWords;
+        ws[(size_t)s * wsRowsPerStream * rowWords + r] = carry[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_carry_out(uint32_t* __restrict__ carry, const uint32_t* __restrict__ ws, int S,
+                                                   int rowWords, int C, long long nNew, long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * rowWords;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / ((long long)C * rowWords));
+        const long long r = i - (long long)s * C * rowWords;
+        carry[i] = ws[((size_t)s * wsRowsPerStream + nNew) * rowWords + r];
+    }
+}
+void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int rowBytes, int C, long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * (rowBytes / 4);
+    if (tot <= 0) return;
+    k_carry_in<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)ws, (const uint32_t*)carry, S,
+                                                                                       rowBytes / 4, C, wsRowsPerStream);
+}
+void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int rowBytes, int C, long long nNew,
+                         long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * (rowBytes / 4);
+    if (tot <= 0) return;
+    k_carry_out<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)carry, (const uint32_t*)ws, S,
+                                                                                        rowBytes / 4, C, nNew, wsRowsPerStream);
+}
+
+// history update: the H input samples that precede the NEXT call = the last H of (old history ++ this call's input)
+__global__ void __launch_bounds__(256) k_hist_update(float* __restrict__ hNew, const float* __restrict__ hOld,
+                                                     const float* __restrict__ x, int S, int H, long long n, long long stride) {
+    const long long tot = (long long)S * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / H);
+        const int j = (int)(i - (long long)s * H);
+        const long long t = n - H + j;
+        hNew[i] = (t >= 0) ? __ldg(x + (size_t)s * stride + t) : hOld[(size_t)s * H + H + t];
+    }
+}
+void vp_launch_hist_update(cudaStream_t st, float* hNew, const float* hOld, const float* x, int S, int H, long long n,
+                           long long stride) {
+    const long long tot = (long long)S * H;
+    k_hist_update<<<(unsigned)std::min<long long>((tot + 255) / 256, 8192), 256, 0, st>>>(hNew, hOld, x, S, H, n, stride);
 }
 
 // ---------------------------------------------------------------------------

@@ -68,17 +68,17 @@ __global__ void __launch_bounds__(512) k_yin(VPGeom g, const float* __restrict__
             fidx = (long long)blockIdx.y * g.nFramesP + item;
         }
         const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
-        const long long p = (long long)f * g.hopP;
+        const long long p = (long long)f * g.hopP + g.offP;
         const int b = (int)(p / g.B);
         if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {  // gated: yin() is not run (PitchProcess.cpp:208-214)
             if (threadIdx.x == 0) { period[fidx] = 0; yflags[fidx] = 0; }
             if (!fromList) return;
             continue;
         }
-        const float* v = voice + (size_t)s * g.stride;
+        const VPRow v = vp_row(voice, g.histV, s, g);
         const long long q = p - tauMax;
         __syncthreads();
-        for (int j = threadIdx.x; j < xsLen; j += blockDim.x) xs[j] = (j < L + tauMax) ? vp_x(v, q + j, g.lat, g.n) : 0.0f;
+        for (int j = threadIdx.x; j < xsLen; j += blockDim.x) xs[j] = (j < L + tauMax) ? vp_x(v, q + j, g) : 0.0f;
         __syncthreads();
         {
             const int lt = threadIdx.x % LT, ig = threadIdx.x / LT;
@@ -250,12 +250,13 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
     auto issue = [&](long long tile, float* dst) {
         const int s = (int)(tile / tilesPerStream);
         const int m0 = (int)(tile - (long long)s * tilesPerStream) * YC_CH;
-        const float* v = voice + (size_t)s * g.stride;
-        const long long t0 = (long long)m0 * c - tauMax - g.lat;  // input time of dst[0]
+        const VPRow v = vp_row(voice, g.histV, s, g);
+        const long long t0 = (long long)m0 * c + g.offP - tauMax - g.lat;  // (call-local) input index of dst[0]
         for (int j = threadIdx.x; j < span; j += blockDim.x) {
             const long long t = t0 + j;
-            const bool ok = t >= 0 && t < g.n;
-            __pipeline_memcpy_async(dst + j, v + (ok ? t : 0), 4, ok ? 0 : 4);
+            const bool ok = t >= -(long long)g.H && t < g.n;
+            const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);  // this call's samples / carried history
+            __pipeline_memcpy_async(dst + j, src, 4, ok ? 0 : 4);
         }
         __pipeline_commit();
     };
@@ -338,22 +339,22 @@ __global__ void __launch_bounds__(32 * YD_WARPS) k_yin_decide(VPGeom g, const fl
     float* xhi = xlo + tauPad;                                                               // x[q + L + i]
     const int tauMax = g.tauMax, L = g.L, c = g.c;
     const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
-    const long long p = (long long)f * g.hopP;
+    const long long p = (long long)f * g.hopP + g.offP;
     const int b = (int)(p / g.B);
     if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {  // gated: yin() is not run (PitchProcess.cpp:208-214)
         if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; }
         return;
     }
-    const float* v = voice + (size_t)s * g.stride;
+    const VPRow v = vp_row(voice, g.histV, s, g);
     const long long q = p - tauMax;
     // ---- A = sum x[q+i]^2 (exact products in double), edge samples for the running B(k)
     double A = 0.0;
     for (int i = lane; i < L; i += 32) {
-        const float x = vp_x(v, q + i, g.lat, g.n);
+        const float x = vp_x(v, q + i, g);
         A = fma((double)x, (double)x, A);
         if (i < tauMax) xlo[i] = x;
     }
-    for (int i = lane; i < tauMax; i += 32) xhi[i] = vp_x(v, q + L + i, g.lat, g.n);
+    for (int i = lane; i < tauMax; i += 32) xhi[i] = vp_x(v, q + L + i, g);
     A = vp_warp_sum(A);
     // ---- C(k) = four chunk partials
     const float* P0 = P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad;
@@ -457,13 +458,13 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     if (fidx >= (long long)S * g.nFramesP) return;
     const int tauMax = g.tauMax, L = g.L;
     const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
-    const long long p = (long long)f * g.hopP;
+    const long long p = (long long)f * g.hopP + g.offP;
     const int b = (int)(p / g.B);
     if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {
         if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; }
         return;
     }
-    const float* v = voice + (size_t)s * g.stride;
+    const VPRow v = vp_row(voice, g.histV, s, g);
     const long long q = p - tauMax;
     const double* Ec = Ech + (size_t)s * nChunks + (size_t)3 * f;
     const double A = (Ec[0] + Ec[1]) + (Ec[2] + Ec[3]);
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         const int k = kA + j;
         double dl = 0.0;
         if (k < tauMax) {
-            const double h = (double)vp_x(v, q + L + k, g.lat, g.n), l = (double)vp_x(v, q + k, g.lat, g.n);
+            const double h = (double)vp_x(v, q + L + k, g), l = (double)vp_x(v, q + k, g);
             dl = h * h - l * l;
         }
         en[j] = dl;  // delta for now
@@ -647,21 +648,22 @@ __device__ __forceinline__ int marks_argmin(const float* __restrict__ fr, int i0
 __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                const uint8_t* __restrict__ gate, const int* __restrict__ periodArr,
                                                const uint32_t* __restrict__ yflags, vp_pitch_frame* __restrict__ frames,
-                                               int S) {
+                                               VPMarkState* __restrict__ carry, int S) {
     extern __shared__ float smarks[];  // [warps][L] the current frame's samples (argExt searches hit shared memory)
     float* fsm = smarks + (size_t)(threadIdx.x >> 5) * g.L;
     const int lane = threadIdx.x & 31;
     const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     if (s >= S) return;
-    const float* v = voice + (size_t)s * g.stride;
+    const VPRow v = vp_row(voice, g.histV, s, g);
     const uint8_t* gt = gate + (size_t)s * g.nBlocks;
     const int L = g.L, hop = g.hopP, cap = g.anCap;
-    // PitchProcess state (PitchProcess.cpp:76-92)
-    int period = 0, prevPeriod = 0, prevVoicedPeriod = 0, periodNew = 0;
-    bool voiced = false, prevVoiced = false;
-    double beta = 1.0;
-    int an = 0, pan = 0, st = 0, pst = 0;  // this lane's storage slot of each vector
-    int nAn = 0, nPan = 0, nSt = 0, nPst = 0;
+    // PitchProcess state (PitchProcess.cpp:76-92), carried from the previous call of this stream
+    VPMarkState* cs = carry + s;
+    int period = cs->period, prevPeriod = cs->prevPeriod, prevVoicedPeriod = cs->prevVoicedPeriod, periodNew = cs->periodNew;
+    bool voiced = cs->voiced != 0, prevVoiced = cs->prevVoiced != 0;
+    double beta = cs->beta;
+    int an = cs->an[lane], pan = 0, st = cs->st[lane], pst = 0;  // this lane's storage slot of each vector
+    int nAn = cs->nAn, nPan = 0, nSt = cs->nSt, nPst = 0;
 #define SLOT(arr, i) __shfl_sync(0xffffffffu, (arr), (i))
 #define AN_PUSH(val)                                   \
     do {                                               \
@@ -674,10 +676,10 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
         if (nSt < VP_SLOTS - 1) { if (lane == nSt) st = (val); ++nSt; } \
     } while (0)
     for (int f = 0; f < g.nFramesP; ++f) {
-        const long long p = (long long)f * hop;
+        const long long p = (long long)f * hop + g.offP;
         const int b = (int)(p / g.B);
         const size_t fidx = (size_t)s * g.nFramesP + f;
-        vp_pitch_frame* rec = frames + fidx;
+        vp_pitch_frame* rec = frames + vp_prow(g, s, f);
         unsigned flags = 0;
         bool ub = false;
         int note = -1, nAnOv = 0;
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
             voiced = period > 0;
             if (voiced) {  // only voiced frames search the waveform
                 __syncwarp();
-                vp_stage<12>(fsm, v, p, L, g.lat, g.n, lane, 32);
+                vp_stage<12>(fsm, v, p, L, g, lane, 32);
                 __syncwarp();
             }
             const uint32_t yf = yflags[fidx];
@@ -843,17 +845,27 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
             rec->beta = beta;
         }
     }
+    __syncwarp();
+    cs->an[lane] = an;
+    cs->st[lane] = st;
+    if (lane == 0) {
+        cs->period = period; cs->prevPeriod = prevPeriod; cs->prevVoicedPeriod = prevVoicedPeriod; cs->periodNew = periodNew;
+        cs->voiced = voiced ? 1 : 0; cs->prevVoiced = prevVoiced ? 1 : 0;
+        cs->nAn = nAn; cs->nSt = nSt;
+        cs->beta = beta;
+    }
 #undef SLOT
 #undef AN_PUSH
 #undef ST_PUSH
 }
 
 void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
-                     const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames) {
+                     const uint8_t* gate, const int* period, const uint32_t* yflags, vp_pitch_frame* frames,
+                     VPMarkState* carry) {
     const int threads = 128;
     const long long tot = (long long)S * 32;
     k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * g.L * sizeof(float), st>>>(
-        g, tb, voice, gate, period, yflags, frames, S);
+        g, tb, voice, gate, period, yflags, frames, carry, S);
 }
 
 // ===========================================================================
@@ -873,21 +885,37 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
 #define PA_SEGS 16
 #define PA_R 8
 
+// Frame slots of the pitch synthesis kernels: slot index = f + VP_PC; f < 0 are the last frames of earlier calls (their
+// records are carried): the reference adds a chunk's samples into the output ring when the chunk is handled, also
+// beyond the current block, so such a frame still owns output positions of this call. Returns false for frames that
+// are gated, have no marks, or have no processed chunk reaching into [0, n).
+__device__ __forceinline__ bool pf_live(const VPGeom& g, const vp_pitch_frame* rec, int f) {
+    const unsigned flags = rec->flags;
+    if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return false;
+    if (f >= 0) return true;
+    if (!g.hasPrev) return false;
+    const long long p = (long long)f * g.hopP + g.offP;
+    for (int n = 0; n < 4; ++n) {
+        const long long q = p + (long long)n * g.c;
+        if (q < g.n && q + g.c > 0) return true;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, const float* __restrict__ voice,
                                                                   const vp_pitch_frame* __restrict__ frames,
                                                                   double* __restrict__ rP, int segLen, int xdLen, long long nFramesTot) {
     extern __shared__ double smd[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long fidx = (long long)blockIdx.x * PA_WARPS + warp;
+    const long long fidx = (long long)blockIdx.x * PA_WARPS + warp;  // slot index over [S][nFramesP + VP_PC]
     if (fidx >= nFramesTot) return;
-    const unsigned flags = frames[fidx].flags;
-    if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return;
-    const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
+    const int s = (int)(fidx / (g.nFramesP + VP_PC)), f = (int)(fidx - (long long)s * (g.nFramesP + VP_PC)) - VP_PC;
+    if (!pf_live(g, frames + fidx, f)) return;
     const int L = g.L, ord = g.ordP;
     double* xd = smd + (size_t)warp * xdLen;  // frame samples as double, zero beyond L (rectangular window, LPC.cpp:44-97)
-    const float* v = voice + (size_t)s * g.stride;
-    const long long p = (long long)f * g.hopP;
-    vp_stage<8>(xd, v, p, L, g.lat, g.n, lane, 32);
+    const VPRow v = vp_row(voice, g.histV, s, g);
+    const long long p = (long long)f * g.hopP + g.offP;
+    vp_stage<8>(xd, v, p, L, g, lane, 32);
     for (int j = L + lane; j < xdLen; j += 32) xd[j] = 0.0;
     __syncwarp();
     const int seg = lane & (PA_SEGS - 1), half = lane >> 4;
@@ -922,10 +950,12 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
 template <int P>
 __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch_frame* __restrict__ frames,
                                                         const double* __restrict__ rP, double* __restrict__ aP, long long nFramesTot) {
-    const long long fidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long fidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // slot index over [S][nFramesP + VP_PC]
     if (fidx >= nFramesTot) return;
-    const unsigned flags = frames[fidx].flags;
-    if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return;
+    {
+        const int s = (int)(fidx / (g.nFramesP + VP_PC)), f = (int)(fidx - (long long)s * (g.nFramesP + VP_PC)) - VP_PC;
+        if (!pf_live(g, frames + fidx, f)) return;
+    }
     constexpr int PM = (P > 0) ? P : VP_ORDER_MAX;
     const int ord = (P > 0) ? P : g.ordP;
     double r[PM + 1], a[PM + 1];
@@ -998,11 +1028,11 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
                                                             const double* __restrict__ aP, float* __restrict__ outE,
                                                             int xLen, int eLen) {
     extern __shared__ double smd[];
-    const int f = blockIdx.x, s = blockIdx.y;
-    const size_t fidx = (size_t)s * g.nFramesP + f;
+    const int f = (int)blockIdx.x - VP_PC, s = blockIdx.y;  // f = -1: the previous call's last frame
+    const size_t fidx = vp_prow(g, s, f);
     vp_pitch_frame* rec = frames + fidx;
     const unsigned flags = rec->flags;
-    if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return;
+    if (!pf_live(g, rec, f)) return;
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
     double* e = smd;                    // [eLen] residual, e[j] <-> frame-relative idx j - tauMax
@@ -1010,11 +1040,11 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
     float* xf = (float*)(hs + 2 * tauMax + 2);  // [xLen] floats; dead after the residual -> reused as oE [L] doubles
     double* oE = (double*)xf;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
-    const float* v = voice + (size_t)s * g.stride;
-    const long long p = (long long)f * g.hopP;
+    const VPRow v = vp_row(voice, g.histV, s, g);
+    const long long p = (long long)f * g.hopP + g.offP;
     const int tid = threadIdx.x;
 
-    vp_stage<8>(xf, v, p - X0, xLen, g.lat, g.n, tid, PF_THREADS);
+    vp_stage<8>(xf, v, p - X0, xLen, g, tid, PF_THREADS);
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
     if (tid == 0) sAn[VP_MAX_MARKS] = 0;
     const double* ap = aP + fidx * (size_t)(ord + 1);
@@ -1068,7 +1098,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
             const long long Pn = p + (long long)n * c;
             if (n <= 3 && Pn < g.n) {
                 const int stale = rec->anStale;
-                const int startSample = (int)(Pn % g.B);
+                const int startSample = (int)(((Pn % g.B) + g.B) % g.B);  // Pn < 0: a chunk emitted by an earlier call
                 const int lookahead = g.lat + g.B - startSample;  // bufferIdxMax - startSample (PitchProcess.cpp:800)
                 const int nc = n * c;
                 // getClosestAnMarkIdx (PitchProcess.cpp:788-831)
@@ -1151,7 +1181,7 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
 
 void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* voice, const vp_pitch_frame* frames,
                          double* rP, double* aP) {
-    const long long tot = (long long)S * g.nFramesP;
+    const long long tot = (long long)S * (g.nFramesP + VP_PC);
     int segLen = (g.L + PA_SEGS - 1) / PA_SEGS;
     if ((segLen & 1) == 0) ++segLen;  // odd -> the 16 segments of a half-warp hit 16 distinct 64-bit banks
     const int groups = (g.ordP + 1 + 2 * PA_R - 1) / (2 * PA_R);
@@ -1170,7 +1200,7 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
     xLen = (xLen + 3) & ~3;
     const size_t smem = (size_t)(eLen + 2 * g.tauMax + 2) * sizeof(double) + (size_t)xLen * sizeof(float);
-    dim3 grid(g.nFramesP, S);
+    dim3 grid(g.nFramesP + VP_PC, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         k_pitch_psola<15><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen);
@@ -1206,13 +1236,12 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
     const int order = (P > 0) ? P : g.ordP;
     bool active = false;
     int s = 0, f = 0, nSteps = 0;
-    if (fidx < nFramesTot) {
-        s = (int)(fidx / g.nFramesP);
-        f = (int)(fidx - (long long)s * g.nFramesP);
-        const unsigned fl = frames[fidx].flags;
-        active = !(fl & VP_PF_GATED) && (fl & VP_PF_HAS_MARKS);
-        const long long p = (long long)f * g.hopP;
-        for (int n = 0; n < 4; ++n) if (p + (long long)n * c < g.n) nSteps += c;  // chunks processed in this run
+    if (fidx < nFramesTot) {  // slot index over [S][nFramesP + VP_PC]
+        s = (int)(fidx / (g.nFramesP + VP_PC));
+        f = (int)(fidx - (long long)s * (g.nFramesP + VP_PC)) - VP_PC;
+        active = pf_live(g, frames + fidx, f);
+        const long long p = (long long)f * g.hopP + g.offP;
+        for (int n = 0; n < 4; ++n) if (p + (long long)n * c < g.n) nSteps += c;  // chunks handled up to the end of this call
     }
     if (!active) nSteps = 0;
     constexpr int PA = (P > 0) ? P : VP_ORDER_MAX;
@@ -1223,7 +1252,7 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
         for (int k = 0; k <= order; ++k) a[k] = ap[k];
     }
     // per-lane metadata shared through shuffles for the cooperative slab moves
-    const long long myP = (long long)f * g.hopP;
+    const long long myP = (long long)f * g.hopP + g.offP;
     const double gp = (double)g.gainPitchF;
     const int nSlabs = (L + 31) / 32;
     int maxSteps = nSteps;
@@ -1263,7 +1292,7 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
             const int i = i0 + lane;
             if (i < steps) {
                 const long long u = pf + i;
-                if (u < g.n) {
+                if (u >= 0 && u < g.n) {  // positions before 0 went out with an earlier call, beyond n go out with a later one
                     float* o = outP + (size_t)sf * g.wstride + u;
                     const float val = tout[warp][fr][lane];
                     if (i < c || i >= 3 * c) atomicAdd(o, val);
@@ -1277,7 +1306,7 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
 
 void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const vp_pitch_frame* frames,
                          const double* aP, const float* outE, float* outP) {
-    const long long tot = (long long)S * g.nFramesP;
+    const long long tot = (long long)S * (g.nFramesP + VP_PC);
     const unsigned grid = (unsigned)((tot + 32 * PI_WARPS - 1) / (32 * PI_WARPS));
     if (g.ordP == 15) k_pitch_iir<15><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot);
     else k_pitch_iir<0><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot);

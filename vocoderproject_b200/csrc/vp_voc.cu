@@ -16,7 +16,9 @@
 // Two steps so that every sample is read once: per host block the sum of squares of the whole block and of its last
 // `rem` samples (inSize = q B + rem); the ring at block b is then blocks b-q+1 .. b plus the tail of block b-q.
 __global__ void __launch_bounds__(128) k_gate_partial(VPGeom g, const float* __restrict__ voice,
-                                                      const float* __restrict__ synth, double* __restrict__ part, int rem) {
+                                                      const float* __restrict__ synth, double* __restrict__ part, int rem,
+                                                      int carry, int partRows) {
+    // part rows per stream: `carry` = q + 1 blocks of the previous calls, then this call's blocks
     const int b = blockIdx.x, s = blockIdx.y;
     const float* v = voice + (size_t)s * g.stride + (size_t)b * g.B;
     const float* y = synth + (size_t)s * g.stride + (size_t)b * g.B;
@@ -38,21 +40,18 @@ __global__ void __launch_bounds__(128) k_gate_partial(VPGeom g, const float* __r
     __syncthreads();
     if (threadIdx.x < 4) {
         const int q = threadIdx.x;
-        part[((size_t)s * g.nBlocks + b) * 4 + q] = (red[q][0] + red[q][1]) + (red[q][2] + red[q][3]);
+        part[((size_t)s * partRows + carry + b) * 4 + q] = (red[q][0] + red[q][1]) + (red[q][2] + red[q][3]);
     }
 }
 
 __global__ void __launch_bounds__(128) k_gate_decide(VPGeom g, const double* __restrict__ part, uint8_t* __restrict__ gate,
-                                                     int q, long long tot) {
+                                                     int q, long long tot, int carry, int partRows) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= tot) return;
     const int s = (int)(idx / g.nBlocks), b = (int)(idx - (long long)s * g.nBlocks);
-    const double* ps = part + (size_t)s * g.nBlocks * 4;
-    double sv = 0.0, ss = 0.0;
-    if (b - q >= 0) { sv = ps[(size_t)(b - q) * 4 + 2]; ss = ps[(size_t)(b - q) * 4 + 3]; }  // oldest: tail of block b - q
-    for (int j = q - 1; j >= 0; --j) {
-        if (b - j >= 0) { sv += ps[(size_t)(b - j) * 4 + 0]; ss += ps[(size_t)(b - j) * 4 + 1]; }
-    }
+    const double* ps = part + ((size_t)s * partRows + carry) * 4;  // row 0 = this call's block 0; rows -carry..-1 carried (zeros before time 0)
+    double sv = ps[(ptrdiff_t)(b - q) * 4 + 2], ss = ps[(ptrdiff_t)(b - q) * 4 + 3];  // oldest: tail of block b - q
+    for (int j = q - 1; j >= 0; --j) { sv += ps[(ptrdiff_t)(b - j) * 4 + 0]; ss += ps[(ptrdiff_t)(b - j) * 4 + 1]; }
     // juce::Decibels::gainToDecibels(rms) < -60 (VocoderProcess.cpp:199-204, MyBuffer.cpp:258-261, :299-302)
     const double rv = sqrt(sv / (double)g.inSize), rs = sqrt(ss / (double)g.inSize);
     const double dv = rv > 0.0 ? fmax(-100.0, log10(rv) * 20.0) : -100.0;
@@ -64,13 +63,16 @@ __global__ void __launch_bounds__(128) k_gate_decide(VPGeom g, const double* __r
     gate[idx] = f;
 }
 
+int vp_gate_carry_rows(const VPGeom& g) { return g.inSize / g.B + 1; }
+
 void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate,
-                    double* part) {
+                    double* part, int partRows) {
     const int q = g.inSize / g.B, rem = g.inSize - q * g.B;
+    const int carry = q + 1;
     dim3 grid(g.nBlocks, S);
-    k_gate_partial<<<grid, 128, 0, st>>>(g, voice, synth, part, rem);
+    k_gate_partial<<<grid, 128, 0, st>>>(g, voice, synth, part, rem, carry, partRows);
     const long long tot = (long long)S * g.nBlocks;
-    k_gate_decide<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, part, gate, q, tot);
+    k_gate_decide<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, part, gate, q, tot, carry, partRows);
 }
 
 // ---------------------------------------------------------------------------
@@ -112,17 +114,16 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
     double* sw = sm + AC_FRAMES * FS;  // [AC_FRAMES][FS] synth ch0 * window
     const int s = blockIdx.y;
     const int k0 = blockIdx.x * AC_FRAMES;
-    const float* v = voice + (size_t)s * g.stride;
-    const float* y = synth + (size_t)s * g.stride;
+    const VPRow v = vp_row(voice, g.histV, s, g), y = vp_row(synth, g.histS, s, g);
     for (int i = threadIdx.x; i < AC_FRAMES * FS; i += blockDim.x) {
         const int f = i / FS, j = i - f * FS;
         const int k = k0 + f;
         double a = 0.0, c = 0.0;
         if (j < g.wlenV && k < g.nFramesV) {
-            const long long u = (long long)k * g.hopV + j;
+            const long long u = (long long)k * g.hopV + g.offV + j;
             const double w = tb.wV[j];
-            a = (double)vp_x(v, u, g.lat, g.n) * w;
-            c = (double)vp_x(y, u, g.lat, g.n) * w;
+            a = (double)vp_x(v, u, g) * w;
+            c = (double)vp_x(y, u, g) * w;
         }
         xw[i] = a;
         sw[i] = c;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
     }
     const int k = k0 + f;
     if (seg == 0 && k < g.nFramesV) {
-        double* r = (isVoice ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)vp_row(order);
+        double* r = (isVoice ? rV : rS) + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(order);
 #pragma unroll
         for (int j = 0; j < AC_R; ++j) {
             const int m = grp * AC_R + j;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
         const bool tv = t < g.ordV;
         const int ord = tv ? g.ordV : g.ordS, tt = tv ? t : t - g.ordV;
         const int j = g.wlenV - ord + tt;
-        double* r = (tv ? rV : rS) + ((size_t)s * g.nFramesV + kk) * (size_t)vp_row(ord);
+        double* r = (tv ? rV : rS) + ((size_t)s * g.nFramesV + kk) * (size_t)vp_rowlen(ord);
         r[ord + 1 + tt] = (j >= 0) ? (tv ? xw : sw)[ff * FS + j] : 0.0;
     }
 }
@@ -199,8 +200,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
     double* sw = xw + FS;                                                     // [FS] synth ch0 * window
     float* ringV = (float*)(sw + FS);                                         // [wlen]
     float* ringS = ringV + ringLen;                                           // [wlen]   (2 * ringLen floats = ringLen doubles)
-    const float* v = voice + (size_t)s * g.stride;
-    const float* y = synth + (size_t)s * g.stride;
+    const VPRow v = vp_row(voice, g.histV, s, g), y = vp_row(synth, g.histS, s, g);
     for (int j = wlen + lane; j < FS; j += 32) { xw[j] = 0.0; sw[j] = 0.0; }
     const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;  // grp 0..2: voice lag groups, grp 3: side-chain
     const double* sig = (grp < 3 ? xw : sw);
@@ -210,16 +210,16 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
     const int order = (grp < 3) ? g.ordV : g.ordS;
     // ---- initial fill: frame k0 occupies ring positions (k0 hop + j) mod wlen
     {
-        const long long u0 = (long long)k0 * hop;
-        const int r0 = (int)(u0 % wlen);
+        const long long u0 = (long long)k0 * hop + g.offV;
+        const int r0 = (int)(((long long)k0 * hop) % wlen);
         // positions are contiguous modulo the ring: stage linearly, then the index wraps
         for (int base = lane; base < wlen; base += 32 * 6) {
             float tv[6], ts[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 const int j = base + q * 32;
-                tv[q] = (j < wlen) ? vp_x(v, u0 + j, g.lat, g.n) : 0.0f;
-                ts[q] = (j < wlen) ? vp_x(y, u0 + j, g.lat, g.n) : 0.0f;
+                tv[q] = (j < wlen) ? vp_x(v, u0 + j, g) : 0.0f;
+                ts[q] = (j < wlen) ? vp_x(y, u0 + j, g) : 0.0f;
             }
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
@@ -231,16 +231,16 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
     for (int fb = 0; fb < AV_BATCH; ++fb) {
         const int k = k0 + fb;
         if (k >= g.nFramesV) break;
-        const long long u0 = (long long)k * hop;
-        const int r0 = (int)(u0 % wlen);
+        const long long u0 = (long long)k * hop + g.offV;
+        const int r0 = (int)(((long long)k * hop) % wlen);
         // ---- prefetch the hop new samples of frame k+1 (positions u0 + wlen .. u0 + wlen + hop)
         float nv[AV_NPRE], ns[AV_NPRE];
         const bool more = (fb + 1 < AV_BATCH) && (k + 1 < g.nFramesV);
 #pragma unroll
         for (int q = 0; q < AV_NPRE; ++q) {
             const int j = lane + q * 32;
-            nv[q] = (more && j < hop) ? vp_x(v, u0 + wlen + j, g.lat, g.n) : 0.0f;
-            ns[q] = (more && j < hop) ? vp_x(y, u0 + wlen + j, g.lat, g.n) : 0.0f;
+            nv[q] = (more && j < hop) ? vp_x(v, u0 + wlen + j, g) : 0.0f;
+            ns[q] = (more && j < hop) ? vp_x(y, u0 + wlen + j, g) : 0.0f;
         }
         __syncwarp();
         // ---- windowed FP64 copies from the ring
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
             a += __shfl_xor_sync(0xffffffffu, a, 4);
             acc[j] = a;
         }
-        double* rowV = rV + ((size_t)s * g.nFramesV + k) * (size_t)vp_row(g.ordV);
-        double* rowS = rS + ((size_t)s * g.nFramesV + k) * (size_t)vp_row(g.ordS);
+        double* rowV = rV + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordV);
+        double* rowS = rS + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordS);
         if (seg == 0) {
             double* r = (grp < 3) ? rowV : rowS;
 #pragma unroll
@@ -343,8 +343,9 @@ __device__ void lev_solve(const double* r, double* a, int order) {
     for (int i = 1; i <= order; ++i) a[i] = -a[i];
 }
 
-__device__ double fir_energy(const double* r, const double* a, int order, int wlen, const float* __restrict__ row,
-                             long long u0, const double* __restrict__ w, int lat, long long n) {
+// residual energy of the zero-state FIR over the frame in closed form (see above); xt = the frame's last `order`
+// windowed samples (appended to the autocorrelation row by the autocorr kernels)
+__device__ double fir_energy(const double* r, const double* a, int order, int wlen, const double* __restrict__ xt) {
     double q = r[0];
     for (int k = 1; k <= order; ++k) q = fma(a[k], r[k], q);
     double E = q * (double)wlen;
@@ -352,46 +353,44 @@ __device__ double fir_energy(const double* r, const double* a, int order, int wl
     double tail = 0.0;
     for (int d = 0; d < order; ++d) {
         double e = 0.0;
-        for (int k = d + 1; k <= order; ++k) {
-            const int j = wlen + d - k;
-            if (j >= 0) e = fma(a[k], (double)vp_x(row, u0 + j, lat, n) * w[j], e);
-        }
+        for (int k = d + 1; k <= order; ++k) e = fma(a[k], xt[order + d - k], e);
         tail = fma(e, e, tail);
     }
     E -= tail;
     return E > 0.0 ? E : 0.0;
 }
 
-__global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, const float* __restrict__ voice,
-                                                      const float* __restrict__ synth,
+__global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, const uint8_t* __restrict__ gate,
                                                       const double* __restrict__ rV, const double* __restrict__ rS,
                                                       double* __restrict__ aV, double* __restrict__ aS,
                                                       double* __restrict__ EeV, double* __restrict__ EeS, int S) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)S * g.nFramesV) return;
     const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
-    const long long u0 = (long long)k * g.hopV;
+    const size_t row = vp_vrow(g, s, k);
     double r[VP_ORDER_MAX + 1], a[VP_ORDER_MAX + 1];
     {
-        const double* rp = rV + (size_t)idx * vp_row(g.ordV);
+        const double* rp = rV + (size_t)idx * vp_rowlen(g.ordV);
         for (int m = 0; m <= g.ordV; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordV);
-        double* ap = aV + (size_t)idx * (g.ordV + 1);
+        double* ap = aV + row * (g.ordV + 1);
         for (int m = 0; m <= g.ordV; ++m) ap[m] = a[m];
-        EeV[idx] = fir_energy(r, a, g.ordV, g.wlenV, voice + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+        EeV[row] = fir_energy(r, a, g.ordV, g.wlenV, rp + g.ordV + 1);
     }
     {
-        const double* rp = rS + (size_t)idx * vp_row(g.ordS);
+        const double* rp = rS + (size_t)idx * vp_rowlen(g.ordS);
         for (int m = 0; m <= g.ordS; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordS);
-        double* ap = aS + (size_t)idx * (g.ordS + 1);
+        double* ap = aS + row * (g.ordS + 1);
         for (int m = 0; m <= g.ordS; ++m) ap[m] = a[m];
-        EeS[idx] = fir_energy(r, a, g.ordS, g.wlenV, synth + (size_t)s * g.stride, u0, tb.wV, g.lat, g.n);
+        const double eS = fir_energy(r, a, g.ordS, g.wlenV, rp + g.ordS + 1);
+        // a frame skipped by the silence gate (VocoderProcess.cpp:199-204) is marked with EeSynth = -1
+        const int b = (int)(((unsigned)k * (unsigned)g.hopV + (unsigned)g.offV) / (unsigned)g.B);
+        const bool gated = (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) != 0;
+        EeS[row] = gated ? -1.0 : eS;
     }
 }
 
-// Register-resident specialisation for a compile-time order: r[], a[] and the frame's last P windowed samples are
-// statically indexed (fully unrolled recursion, no local memory). Same operation order as lev_solve / fir_energy.
 // rp / ap / xt point into SHARED memory (row of this thread, odd stride): the CTA stages them with coalesced,
 // batched global accesses, because 232 registers per thread leave no room to keep dozens of global loads in flight.
 template <int P>
@@ -469,18 +468,29 @@ __global__ void __launch_bounds__(LV_THREADS) k_voc_levinson_static(VPGeom g, VP
     if (tid < nF) {
         const long long idx = f0 + tid;
         const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+        const size_t orow = vp_vrow(g, s, k);
         double* row = sR + tid * RS;
         const double eS = lev_energy_static<PS>(row + RV, row + RV, wlen, row + RV + PS + 1);
         // a frame skipped by the silence gate (VocoderProcess.cpp:199-204) is marked with EeSynth = -1: the synthesis
         // kernel then needs no gate lookups for its 10-frame energy history
-        const int b = (int)(((unsigned)k * (unsigned)g.hopV) / (unsigned)g.B);
+        const int b = (int)(((unsigned)k * (unsigned)g.hopV + (unsigned)g.offV) / (unsigned)g.B);
         const bool gated = (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) != 0;
-        EeS[idx] = gated ? -1.0 : eS;
-        EeV[idx] = lev_energy_static<PV>(row, row, wlen, row + PV + 1);
+        EeS[orow] = gated ? -1.0 : eS;
+        EeV[orow] = lev_energy_static<PV>(row, row, wlen, row + PV + 1);
     }
     __syncthreads();
-    for (int i = tid; i < nF * (PV + 1); i += LV_THREADS) aV[f0 * (PV + 1) + i] = sR[(i / (PV + 1)) * RS + (i % (PV + 1))];
-    for (int i = tid; i < nF * (PS + 1); i += LV_THREADS) aS[f0 * (PS + 1) + i] = sR[(i / (PS + 1)) * RS + RV + (i % (PS + 1))];
+    for (int i = tid; i < nF * (PV + 1); i += LV_THREADS) {
+        const int fi = i / (PV + 1), m = i % (PV + 1);
+        const long long idx = f0 + fi;
+        const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+        aV[vp_vrow(g, s, k) * (PV + 1) + m] = sR[fi * RS + m];
+    }
+    for (int i = tid; i < nF * (PS + 1); i += LV_THREADS) {
+        const int fi = i / (PS + 1), m = i % (PS + 1);
+        const long long idx = f0 + fi;
+        const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+        aS[vp_vrow(g, s, k) * (PS + 1) + m] = sR[fi * RS + RV + m];
+    }
 }
 
 void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
@@ -489,13 +499,13 @@ void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb
     const long long tot = (long long)S * g.nFramesV;
     if (g.ordV == 40 && g.ordS == 5 && g.wlenV >= 40)
     {
-        const size_t smem = (size_t)LV_THREADS * ((vp_row(40) + vp_row(5)) | 1) * sizeof(double);
+        const size_t smem = (size_t)LV_THREADS * ((vp_rowlen(40) + vp_rowlen(5)) | 1) * sizeof(double);
         cudaFuncSetAttribute(k_voc_levinson_static<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         k_voc_levinson_static<40, 5><<<(unsigned)((tot + LV_THREADS - 1) / LV_THREADS), LV_THREADS, smem, st>>>(
             g, tb, voice, synth, gate, rV, rS, aV, aS, EeV, EeS, tot);
     }
     else
-        k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, voice, synth, rV, rS, aV, aS, EeV, EeS, S);
+        k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, gate, rV, rS, aV, aS, EeV, EeS, S);
 }
 
 // ---------------------------------------------------------------------------
@@ -515,122 +525,53 @@ __device__ __forceinline__ int vs_idx(int lane, int i, int hop, int sk) {
 }
 __device__ __forceinline__ int vs_skew(int pos, int hop, int sk) { return pos + sk * (pos / hop); }
 
-// gain of frame k (VocoderProcess.cpp:264-276): sums over the last 10 processed
-// (non-gated) frames, newest to oldest.
-__device__ double voc_gain(const VPGeom& g, const uint8_t* __restrict__ gate, const double* __restrict__ EeV,
-                           const double* __restrict__ EeS, int k) {
-    const double es = EeS[k];
-    if (!(es > 1e-4)) return 0.0;
-    double sv = 0.0, ss = 0.0;
-    int cnt = 0;
-    for (int q = k; q >= 0 && cnt < 10; --q) {
-        const int b = (int)(((unsigned)q * (unsigned)g.hopV) / (unsigned)g.B);  // frame start < 2^31 samples
-        if (gate[b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) continue;
-        sv += EeV[q];
-        ss += EeS[q];
-        ++cnt;
+// Gain of every frame (VocoderProcess.cpp:264-276, :301-327): g = sqrt(sum EeVoice / sum EeSynth) over the last 10
+// PROCESSED frames, newest first (a gated frame -- EeSynth < 0 -- neither shifts the histories nor gets a gain).
+// One thread per frame scans back over this call's frames and, if the call started fewer than 10 processed frames
+// ago, continues into the stream's carried histories hist[s] = {EeVoice[10], EeSynth[10]} (newest first).
+__global__ void __launch_bounds__(128) k_voc_gain(VPGeom g, const double* __restrict__ EeV, const double* __restrict__ EeS,
+                                                  double* __restrict__ G, const double* __restrict__ hist, long long tot) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= tot) return;
+    const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
+    const size_t row0 = vp_vrow(g, s, 0);
+    const double es = EeS[row0 + k];
+    double gain = 0.0;
+    if (es > 1e-4) {
+        double sv = 0.0, ss = 0.0;
+        int cnt = 0;
+        for (int q = k; q >= 0 && cnt < 10; --q) {
+            const double eq = EeS[row0 + q];
+            if (eq >= 0.0) { sv += EeV[row0 + q]; ss += eq; ++cnt; }
+        }
+        const double* h = hist + (size_t)s * 20;
+        for (int i = 0; cnt < 10; ++i, ++cnt) { sv += h[i]; ss += h[10 + i]; }  // zero entries = "never processed"
+        gain = sqrt(sv / ss);
     }
-    return sqrt(sv / ss);
+    G[row0 + k] = gain;
 }
 
-// All-pole recursion in TRANSPOSED direct form II: with states s_k,
-//   o[i] = g e[i] + s_1,   s_k <- s_{k+1} - a[k] o[i]  (k = 1..P, s_{P+1} = 0)
-// which is algebraically the reference's o[i] = g e[i] - sum_k a[k] o[i-k] (zero initial state) but turns the P-term
-// dot product per sample into P INDEPENDENT DFMAs (one per state register, updated in place): the only chain from one
-// sample to the next is DADD -> DFMA(s_1), so a single warp keeps the FP64 pipe busy. The order-PS whitening FIR of
-// the side-chain runs in the same form (t_q <- t_{q+1} + as[q] x). No history rotation, no unroll-by-order.
-template <int P, int PS>
-__global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables tb, const float* __restrict__ synth,
-                                                             const uint8_t* __restrict__ gate,
-                                                             const double* __restrict__ aV,
-                                                             const double* __restrict__ aS,
-                                                             const double* __restrict__ EeV,
-                                                             const double* __restrict__ EeS, double* __restrict__ gOut,
-                                                             float* __restrict__ outV, int tilesPerStream, int S,
-                                                             int spanPad, int sk) {
-    extern __shared__ double smd[];
-    const int hop = g.hopV, wlen = g.wlenV;
-    double* wv = smd;                                    // [wlen] synthesis window (uniform reads: broadcast)
-    float* smf = (float*)(smd + ((wlen + 1) & ~1));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < wlen; i += blockDim.x) wv[i] = tb.wV[i];
-    const long long tile = (long long)blockIdx.x * VS_WARPS + warp;
-    const bool live = tile < (long long)tilesPerStream * S;
-    const int s = live ? (int)(tile / tilesPerStream) : 0;
-    const int k0 = live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0;
-    float* sbuf = smf + (size_t)warp * 2 * spanPad;  // side-chain samples, skewed, origin = u(k0)
-    float* obuf = sbuf + spanPad;                    // overlap-add accumulator, skewed, origin = u(k0)
-    const int span = 31 * hop + wlen;                // samples covered by the tile
-    const float* y = synth + (size_t)s * g.stride;
-    const long long uBase = (long long)k0 * hop;
-    if (live) {
-        for (int i = lane; i < span; i += 32) {
-            const int q = vs_skew(i, hop, sk);
-            sbuf[q] = vp_x(y, uBase + i, g.lat, g.n);
-            obuf[q] = 0.0f;
-        }
+// the carried histories after this call: the 10 newest processed frames of (old history ++ this call's frames)
+__global__ void __launch_bounds__(64) k_voc_gain_carry(VPGeom g, const double* __restrict__ EeV, const double* __restrict__ EeS,
+                                                       double* __restrict__ hist, int S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const size_t row0 = vp_vrow(g, s, 0);
+    double hv[10], hs[10];
+    int cnt = 0;
+    for (int q = g.nFramesV - 1; q >= 0 && cnt < 10; --q) {
+        const double eq = EeS[row0 + q];
+        if (eq >= 0.0) { hv[cnt] = EeV[row0 + q]; hs[cnt] = eq; ++cnt; }
     }
-    __syncthreads();
-    const int k = k0 + lane;
-    const size_t fidx = (size_t)s * g.nFramesV + k;
-    bool active = live && k < g.nFramesV;
-    if (active) {
-        const int b = (int)(((long long)k * hop) / g.B);
-        if (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) active = false;
-    }
-    double gain = 0.0;
-    double a[P + 1], as[PS + 1];
-#pragma unroll
-    for (int j = 0; j <= P; ++j) a[j] = 0.0;
-#pragma unroll
-    for (int j = 0; j <= PS; ++j) as[j] = 0.0;
-    if (active) {
-        gain = voc_gain(g, gate + (size_t)s * g.nBlocks, EeV + (size_t)s * g.nFramesV, EeS + (size_t)s * g.nFramesV, k);
-        const double* ap = aV + fidx * (P + 1);
-#pragma unroll
-        for (int j = 0; j <= P; ++j) a[j] = ap[j];
-        const double* sp = aS + fidx * (PS + 1);
-#pragma unroll
-        for (int j = 0; j <= PS; ++j) as[j] = gain * sp[j];  // gain folded into the FIR taps: g sum(as x) = sum((g as) x)
-    }
-    if (live && k < g.nFramesV && gOut) gOut[fidx] = gain;
-    if (__ballot_sync(0xffffffffu, active) != 0u) {
-        const double gv = (double)g.gainVocF;
-        double st[P + 1], t[PS + 1];  // st[k] = s_{k+1}: st[P] stays 0; t likewise
-#pragma unroll
-        for (int j = 0; j <= P; ++j) st[j] = 0.0;
-#pragma unroll
-        for (int j = 0; j <= PS; ++j) t[j] = 0.0;
-        const int base = lane * hop + sk * lane;
-        int q = base, nextHop = hop;
-#pragma unroll 2
-        for (int i = 0; i < wlen; ++i) {
-            if (i == nextHop) { q += sk; nextHop += hop; }
-            const double w = wv[i];
-            const double x = (double)sbuf[q] * w;
-            const double o = fma(as[0], x, t[0]) + st[0];
-#pragma unroll
-            for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
-#pragma unroll
-            for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], o, st[kk + 1]);
-            if (active) obuf[q] += (float)(gv * o * w);
-            ++q;
-        }
-    }
-    __syncwarp();
-    if (live) {
-        // interior of the tile: plain stores; first/last (wlen - hop) samples are shared with the
-        // neighbouring tiles: exactly two contributors -> float atomics stay deterministic.
-        float* o = outV + (size_t)s * g.wstride;
-        const int ov = wlen - hop;
-        for (int i = lane; i < span; i += 32) {
-            const long long u = uBase + i;
-            if (u >= g.n) break;
-            const float v = obuf[vs_skew(i, hop, sk)];
-            if (i < ov || i >= 32 * hop) atomicAdd(o + u, v);
-            else o[u] = v;
-        }
-    }
+    double* h = hist + (size_t)s * 20;
+    for (int i = 0; cnt < 10; ++i, ++cnt) { hv[cnt] = h[i]; hs[cnt] = h[10 + i]; }
+    for (int i = 0; i < 10; ++i) { h[i] = hv[i]; h[10 + i] = hs[i]; }
+}
+
+void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G, double* hist) {
+    const long long tot = (long long)S * g.nFramesV;
+    if (tot > 0) k_voc_gain<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, EeV, EeS, G, hist, tot);
+    k_voc_gain_carry<<<(S + 63) / 64, 64, 0, st>>>(g, EeV, EeS, hist, S);
 }
 
 // ---------------------------------------------------------------------------
@@ -647,24 +588,23 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth(VPGeom g, VPTables 
 // ---------------------------------------------------------------------------
 #define VT_WARPS 2
 
-// four consecutive side-chain samples at delayed positions t .. t+3 (zero outside the call's input)
-__device__ __forceinline__ void vt_load4(const float* __restrict__ row, long long t, int lat, long long n, float* x) {
-    const long long i0 = t - lat;
-    if (i0 >= 0 && i0 + 4 <= n) {
+// four consecutive side-chain samples at delayed positions t .. t+3 (history before the call, zero beyond its input)
+__device__ __forceinline__ void vt_load4(const VPRow& row, long long t, const VPGeom& g, float* x) {
+    const long long i0 = t - g.lat;
+    if (i0 >= 0 && i0 + 4 <= g.n) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = __ldg(row + i0 + j);
+        for (int j = 0; j < 4; ++j) x[j] = __ldg(row.x + i0 + j);
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = (i0 + j >= 0 && i0 + j < n) ? __ldg(row + i0 + j) : 0.0f;
+        for (int j = 0; j < 4; ++j) x[j] = vp_x(row, t + j, g);
     }
 }
 
 template <int P, int PS>
 __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VPTables tb, const float* __restrict__ synth,
-                                                                    const uint8_t* __restrict__ gate,
                                                                     const double* __restrict__ aV, const double* __restrict__ aS,
-                                                                    const double* __restrict__ EeV, const double* __restrict__ EeS,
-                                                                    double* __restrict__ gOut, float* __restrict__ outV, int S,
+                                                                    const double* __restrict__ EeS, const double* __restrict__ G,
+                                                                    float* __restrict__ outV, int S,
                                                                     int nSeg, int segFrames, int rowPad) {
     extern __shared__ double wv[];  // window rows: wv[r * rowPad + i] = w[r * hop + i] (row stride odd: 4 phases, 4 banks)
     const int hop = g.hopV;
@@ -672,8 +612,8 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per-lane landing zone of the NEXT frame's parameters, filled by cp.async one hop-row ahead of its use:
-    // [0, P] aV row, [P+1, P+PS+1] aS row, then EeV[k-9..k] and EeS[k-9..k] (gain history, VocoderProcess.cpp:264-276)
-    constexpr int CF_AS = P + 1, CF_EV = P + PS + 2, CF_ES = CF_EV + 10, CF_N = CF_ES + 10;
+    // [0, P] aV row, [P+1, P+PS+1] aS row, then the frame's gain and its EeSynth (< 0 marks a gated frame)
+    constexpr int CF_AS = P + 1, CF_G = P + PS + 2, CF_ES = CF_G + 1, CF_N = CF_ES + 1;
     constexpr int CF_STRIDE = CF_N | 1;  // odd stride: the 64-bit reads of 32 lanes hit distinct banks
     double* cf = wv + 4 * rowPad + ((size_t)warp * 32 + lane) * CF_STRIDE;
     const long long wid = (long long)blockIdx.x * VT_WARPS + warp;
@@ -684,17 +624,18 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     int s = grp * 8 + (lane >> 2);
     const bool sOk = s < S;
     if (!sOk) s = S - 1;  // idle group: runs along on a valid stream, stores are masked
+    // Rows: row rho = the hop positions [rho hop + offV, (rho + 1) hop + offV) (call-local); frame rho starts at its row.
+    // Rows < 0 belong to frames of the previous call (carry rows of the workspace) that still reach into this one.
     const int kS = seg * segFrames;
-    if (kS >= g.nFramesV) return;
-    const bool lastSeg = (seg == nSeg - 1) || (kS + segFrames >= g.nFramesV);
-    const int kE = lastSeg ? g.nFramesV : kS + segFrames;
-    const long long emit0 = (long long)kS * hop;
-    const long long emit1 = lastSeg ? g.n : (long long)kE * hop;
-    const int rowEnd = lastSeg ? (int)((g.n + hop - 1) / hop) : kE;  // rows [kS - 3, rowEnd)
-    const float* y = synth + (size_t)s * g.stride;
+    const int nRowsAll = (int)((g.n - g.offV + hop - 1) / hop);  // rows that start before the end of the call
+    if (seg > 0 && kS >= nRowsAll) return;
+    const bool lastSeg = (seg == nSeg - 1) || (kS + segFrames >= nRowsAll);
+    const int kE = lastSeg ? nRowsAll : kS + segFrames;
+    const long long emit0 = (seg == 0) ? 0 : (long long)kS * hop + g.offV;
+    const long long emit1 = lastSeg ? g.n : (long long)kE * hop + g.offV;
+    const int rho0 = (seg == 0) ? -VP_VC : kS - 3;  // a position is covered by 4 frames; 4 carry rows when offV > 0
+    const VPRow y = vp_row(synth, g.histS, s, g);
     float* o = outV + (size_t)s * g.wstride;
-    const double* ev = EeV + (size_t)s * g.nFramesV;
-    const double* es = EeS + (size_t)s * g.nFramesV;
     const double gv = (double)g.gainVocF;
     double a[P + 1], as[PS + 1], st[P + 1], t[PS + 1];
 #pragma unroll
@@ -704,85 +645,68 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     int wrow = 0;  // window row of this lane's current frame in the current hop-row
     float xA[4] = {0.f, 0.f, 0.f, 0.f}, xB[4] = {0.f, 0.f, 0.f, 0.f};  // side-chain samples of the next block / the one after
     bool primed = false;
+    auto frameOk = [&](int k) { return k + g.kV0 >= 0 && k < g.nFramesV; };  // frame exists (global index >= 0, starts inside)
     auto prefetch = [&](int k) {  // asynchronous copy of frame k's parameters into this lane's landing zone
-        if (k >= 0 && k < g.nFramesV && (k & 3) == phi) {
-            const double* ap = aV + ((size_t)s * g.nFramesV + k) * (P + 1);
+        if (frameOk(k) && ((k + 4 * VP_VC) & 3) == phi) {
+            const size_t row = vp_vrow(g, s, k);
+            const double* ap = aV + row * (P + 1);
 #pragma unroll
             for (int j = 0; j <= P; ++j) __pipeline_memcpy_async(cf + j, ap + j, 8);
-            const double* sp = aS + ((size_t)s * g.nFramesV + k) * (PS + 1);
+            const double* sp = aS + row * (PS + 1);
 #pragma unroll
             for (int j = 0; j <= PS; ++j) __pipeline_memcpy_async(cf + CF_AS + j, sp + j, 8);
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const int q = k - 9 + j;
-                if (q >= 0) { __pipeline_memcpy_async(cf + CF_EV + j, ev + q, 8); __pipeline_memcpy_async(cf + CF_ES + j, es + q, 8); }
-            }
+            __pipeline_memcpy_async(cf + CF_G, G + row, 8);
+            __pipeline_memcpy_async(cf + CF_ES, EeS + row, 8);
         }
         __pipeline_commit();
     };
-    const int rho0 = (kS - 3 > 0) ? kS - 3 : 0;
     prefetch(rho0);
-    for (int rho = rho0; rho < rowEnd; ++rho) {
+    for (int rho = rho0; rho < kE; ++rho) {
         __pipeline_wait_prior(0);
         // ---- frame start for the phase that begins at this row
-        if ((rho & 3) == phi) {
+        if (((rho + 4 * VP_VC) & 3) == phi) {
 #pragma unroll
             for (int j = 0; j <= P; ++j) st[j] = 0.0;
 #pragma unroll
             for (int j = 0; j <= PS; ++j) t[j] = 0.0;
-            double gain = 0.0;
             // a gated frame carries EeSynth < 0 (written by the Levinson kernel; VocoderProcess.cpp:199-204)
-            const bool active = rho < g.nFramesV && cf[CF_ES + 9] >= 0.0;
+            const bool active = frameOk(rho) && cf[CF_ES] >= 0.0;
             if (active) {
-                if (cf[CF_ES + 9] > 1e-4) {  // gain over the last 10 processed (non-gated) frames, newest to oldest
-                    double sv = 0.0, ss = 0.0;
-                    int cnt = 0;
-#pragma unroll
-                    for (int j = 9; j >= 0; --j) {
-                        if (rho - 9 + j >= 0 && cf[CF_ES + j] >= 0.0) { sv += cf[CF_EV + j]; ss += cf[CF_ES + j]; ++cnt; }
-                    }
-                    for (int q = rho - 10; q >= 0 && cnt < 10; --q) {  // only when gated frames sit inside the window
-                        const double eq = es[q];
-                        if (eq >= 0.0) { sv += ev[q]; ss += eq; ++cnt; }
-                    }
-                    gain = sqrt(sv / ss);
-                }
+                const double gain = cf[CF_G];
 #pragma unroll
                 for (int j = 1; j <= P; ++j) a[j] = cf[j];
 #pragma unroll
-                for (int j = 0; j <= PS; ++j) as[j] = gain * cf[CF_AS + j];
+                for (int j = 0; j <= PS; ++j) as[j] = gain * cf[CF_AS + j];  // gain folded into the FIR taps
             } else {
 #pragma unroll
                 for (int j = 1; j <= P; ++j) a[j] = 0.0;
 #pragma unroll
                 for (int j = 0; j <= PS; ++j) as[j] = 0.0;
             }
-            if (sOk && rho < g.nFramesV && rho >= kS && gOut) gOut[(size_t)s * g.nFramesV + rho] = gain;
             wrow = 0;
         }
         prefetch(rho + 1);
         const double* wr = wv + wrow * rowPad;
-        const long long tBase = (long long)rho * hop;
-        const bool emitRow = sOk && rho >= kS;
+        const long long tBase = (long long)rho * hop + g.offV;
+        const bool emitRow = sOk;
         // Software pipeline inside a row (blocks of 4 positions): while block b runs its 4 x P dependent-on-one-value
         // DFMA batches, the whitening FIR of block b+1 and the overlap-add shuffles + store of block b-1 are issued
         // from the same straight-line code, so their latencies hide under the FP64 pipe. Samples are fetched two
         // blocks ahead. The pipeline drains at the end of a row (a new frame may start at the next one).
         const int nblk = (hop + 3) >> 2;
         if (!primed) {
-            vt_load4(y, tBase, g.lat, g.n, xA);
-            vt_load4(y, (4 < hop) ? tBase + 4 : tBase + hop, g.lat, g.n, xB);
+            vt_load4(y, tBase, g, xA);
+            vt_load4(y, (4 < hop) ? tBase + 4 : tBase + hop, g, xB);
             primed = true;
         }
-        double eN[4], wN[4];
+        double eN[4];
         {   // FIR of block 0 (not overlapped: once per row)
             const int nb0 = min(4, hop);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                wN[j] = wr[min(j, hop - 1)];
                 eN[j] = 0.0;
                 if (j < nb0) {
-                    const double x = (double)xA[j] * wN[j];
+                    const double x = (double)xA[j] * wr[j];
                     eN[j] = fma(as[0], x, t[0]);
 #pragma unroll
                     for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
@@ -791,7 +715,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
 #pragma unroll
             for (int j = 0; j < 4; ++j) xA[j] = xB[j];
             // samples of block 2 of this row, or of the first block(s) of the next row
-            vt_load4(y, (8 < hop) ? tBase + 8 : ((4 < hop) ? tBase + hop : tBase + hop + 4), g.lat, g.n, xB);
+            vt_load4(y, (8 < hop) ? tBase + 8 : ((4 < hop) ? tBase + hop : tBase + hop + 4), g, xB);
         }
         float cP[4] = {0.f, 0.f, 0.f, 0.f};
         long long tP = 0;
@@ -801,18 +725,17 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
             constexpr bool FULL = decltype(fullTag)::value;
             const int i0 = b << 2;
             const int nb = FULL ? 4 : min(4, hop - i0);
-            double e[4], wc[4];
+            double e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { e[j] = eN[j]; wc[j] = wN[j]; }
+            for (int j = 0; j < 4; ++j) e[j] = eN[j];
             // ---- FIR of block b+1 (same row only)
             if (FULL || b + 1 < nblk) {
                 const int i1 = i0 + 4, nb1 = FULL ? 4 : min(4, hop - i1);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    wN[j] = FULL ? wr[i1 + j] : wr[min(i1 + j, hop - 1)];
                     eN[j] = 0.0;
                     if (FULL || j < nb1) {
-                        const double x = (double)xA[j] * wN[j];
+                        const double x = (double)xA[j] * wr[i1 + j];
                         eN[j] = fma(as[0], x, t[0]);
 #pragma unroll
                         for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
@@ -826,7 +749,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
                 if (i3 < hop) tn = tBase + i3;
                 else if (i0 + 8 < hop) tn = tBase + hop;          // block b+2 is the row's last: b+3 = next row, block 0
                 else tn = tBase + hop + 4;                        // block b+1 is the row's last: b+3 = next row, block 1
-                vt_load4(y, tn, g.lat, g.n, xB);
+                vt_load4(y, tn, g, xB);
             }
             // ---- all-pole recursion of block b
             float c[4];
@@ -836,7 +759,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
                     const double ov = e[j] + st[0];
 #pragma unroll
                     for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
-                    c[j] = (float)(gv * ov * wc[j]);
+                    c[j] = (float)(gv * ov * wr[i0 + j]);  // window re-read from shared memory: cheaper than 8 live registers
                 } else c[j] = 0.0f;
             }
             // ---- overlap-add of the 4 phase lanes for the 4 positions of block b-1: transpose-reduce, 3 shuffles;
@@ -879,42 +802,35 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
 // Generic-order fallback (orders other than the plug-in defaults): same tiling,
 // histories in local memory.
 __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, VPTables tb, const float* __restrict__ synth,
-                                                                     const uint8_t* __restrict__ gate,
                                                                      const double* __restrict__ aV,
                                                                      const double* __restrict__ aS,
-                                                                     const double* __restrict__ EeV,
                                                                      const double* __restrict__ EeS,
-                                                                     double* __restrict__ gOut, float* __restrict__ outV,
+                                                                     const double* __restrict__ G, float* __restrict__ outV,
                                                                      int tilesPerStream, int S, int spanPad, int sk) {
     extern __shared__ float smf[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tile = (long long)blockIdx.x * VS_WARPS + warp;
     const bool live = tile < (long long)tilesPerStream * S;
     const int s = live ? (int)(tile / tilesPerStream) : 0;
-    const int k0 = live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0;
+    // tiles start VP_VC frames early: the previous call's last frames (carry rows) still reach into this call
+    const int k0 = (live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0) - VP_VC;
     const int P = g.ordV, PS = g.ordS;
     float* sbuf = smf + (size_t)warp * 2 * spanPad;
     float* obuf = sbuf + spanPad;
     const int hop = g.hopV, wlen = g.wlenV;
     const int span = 31 * hop + wlen;
-    const float* y = synth + (size_t)s * g.stride;
-    const long long uBase = (long long)k0 * hop;
+    const VPRow y = vp_row(synth, g.histS, s, g);
+    const long long uBase = (long long)k0 * hop + g.offV;
     if (live) {
-        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop, sk)] = vp_x(y, uBase + i, g.lat, g.n);
+        for (int i = lane; i < span; i += 32) sbuf[vs_skew(i, hop, sk)] = vp_x(y, uBase + i, g);
         for (int i = lane; i < span; i += 32) obuf[vs_skew(i, hop, sk)] = 0.0f;
     }
     __syncwarp();
     const int k = k0 + lane;
-    const size_t fidx = (size_t)s * g.nFramesV + k;
-    bool active = live && k < g.nFramesV;
-    if (active) {
-        const int b = (int)(((long long)k * hop) / g.B);
-        if (gate[(size_t)s * g.nBlocks + b] & (VP_GATE_VOICE | VP_GATE_SYNTH)) active = false;
-    }
-    double gain = 0.0;
-    if (active)
-        gain = voc_gain(g, gate + (size_t)s * g.nBlocks, EeV + (size_t)s * g.nFramesV, EeS + (size_t)s * g.nFramesV, k);
-    if (live && k < g.nFramesV && gOut) gOut[fidx] = gain;
+    const size_t fidx = vp_vrow(g, s, k);
+    bool active = live && k < g.nFramesV && k + g.kV0 >= 0;
+    if (active && EeS[fidx] < 0.0) active = false;  // gated frame (marked by the Levinson kernel)
+    const double gain = active ? G[fidx] : 0.0;
     const double* ap = aV + fidx * (size_t)(P + 1);
     const double* sp = aS + fidx * (size_t)(PS + 1);
     double h[VP_ORDER_MAX];
@@ -941,6 +857,7 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
         for (int i = lane; i < span; i += 32) {
             const long long u = uBase + i;
             if (u >= g.n) break;
+            if (u < 0) continue;
             const float v = obuf[vs_skew(i, hop, sk)];
             if (i < ov || i >= 32 * hop) atomicAdd(o + u, v);
             else o[u] = v;
@@ -951,24 +868,24 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
 bool vp_voc_synth_needs_clear(const VPGeom& g) { return !(g.ordV == 40 && g.ordS == 5); }
 
 void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
-                         const uint8_t* gate, const double* aV, const double* aS, const double* EeV,
-                         const double* EeS, double* gOut, float* outV) {
+                         const double* aV, const double* aS, const double* EeS, const double* G, float* outV) {
     if (g.ordV == 40 && g.ordS == 5) {
         const int groups = (S + 7) / 8;
         int nSeg = (148 * 16 + groups - 1) / groups;                    // ~16 warps per SM in flight over the grid
         int segFrames = (g.nFramesV + nSeg - 1) / nSeg;
         if (segFrames < 16) segFrames = 16;                              // keep the 3-row halo a small fraction
         nSeg = (g.nFramesV + segFrames - 1) / segFrames;
+        if (nSeg < 1) nSeg = 1;                                          // no new frame: the carried frames still emit
         const int rowPad = g.hopV | 1;
-        const int cfStride = (40 + 1 + 5 + 1 + 20) | 1;
+        const int cfStride = (40 + 1 + 5 + 1 + 2) | 1;
         const size_t smem = ((size_t)4 * rowPad + (size_t)VT_WARPS * 32 * cfStride) * sizeof(double);
         const long long warps = (long long)groups * nSeg;
         cudaFuncSetAttribute(k_voc_synth_stream<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
-            g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV, S, nSeg, segFrames, rowPad);
+            g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, rowPad);
         return;
     }
-    const int tilesPerStream = (g.nFramesV + 31) / 32;
+    const int tilesPerStream = (g.nFramesV + VP_VC + 31) / 32;
     const int span = 31 * g.hopV + g.wlenV + VP_ORDER_MAX;
     const int sk = (g.hopV & 1) ? 0 : 1;
     int spanPad = span + span / g.hopV + 8;
@@ -977,6 +894,5 @@ void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
     const unsigned grid = (unsigned)((tiles + VS_WARPS - 1) / VS_WARPS);
     const size_t smem = (size_t)VS_WARPS * 2 * spanPad * sizeof(float);
     cudaFuncSetAttribute(k_voc_synth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, gate, aV, aS, EeV, EeS, gOut, outV,
-                                                           tilesPerStream, S, spanPad, sk);
+    k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, aV, aS, EeS, G, outV, tilesPerStream, S, spanPad, sk);
 }
