@@ -45,5 +45,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(LIBDIR, "vp_host")
+
+
+def build_host(force=False):
+    """Headless C++ host (csrc/vp_host.cpp over csrc/vp_facade.hpp), linked to libvp_engine.so through the C ABI."""
+    src = [os.path.join(CSRC, "vp_host.cpp"), os.path.join(CSRC, "vp_facade.hpp"), LIB]
+    if not force and os.path.exists(HOST) and all(os.path.getmtime(f) <= os.path.getmtime(HOST) for f in src):
+        return HOST
+    cxx = shutil.which("g++") or "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", HOST, os.path.join(CSRC, "vp_host.cpp"), "-L" + LIBDIR, "-lvp_engine",
+                           "-Wl,-rpath,$ORIGIN"], cwd=CSRC)
+    return HOST
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))
