@@ -332,8 +332,49 @@ def run_engine(args, wl, group):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
     eng.close()
+    if group.rank == 0:
+        if group.world == 1 and not args.no_stream and not args.streams:
+            try:
+                line["streaming"] = run_streaming(args, group)
+            except Exception as ex:  # the throughput line must not depend on the latency sub-test
+                line["streaming"] = {"error": str(ex)}
+        print(json.dumps(line), flush=True)
+
+
+def run_streaming(args, group):
+    """BASELINE configs[4]: 4096 concurrent streams, block 128 @ 44.1 kHz, one CUDA-graph launch per block; latency of
+    vp_engine_stream_block = enqueue -> the block's outputs visible in pinned host memory."""
+    import vocoderproject_b200 as vp
+    fs, B, S = 44100.0, 128, args.streams or 4096
+    nb = args.stream_blocks
+    eng = vp.Engine(fs, B, S, 1, params=vp.default_params(), device=group.local_rank)
+    hv, hs, ho = eng.stream_buffers()
+    # a few seconds of distinct input per stream would not fit the point of the test: cycle 64 pre-generated blocks
+    nsrc = 64
+    src_v, src_s, _ = vp.synth_host(fs, min(S, 64), nsrc * B, flavour=0, first_stream=0)
+    reps = (S + src_v.shape[0] - 1) // src_v.shape[0]
+    src_v = np.tile(src_v, (reps, 1))[:S]
+    src_s = np.tile(src_s, (reps, 1))[:S]
+    lat = []
+    for b in range(nb + 32):
+        k = b % nsrc
+        hv[:] = src_v[:, k * B:(k + 1) * B]
+        hs[:] = src_s[:, k * B:(k + 1) * B]
+        t0 = time.perf_counter()
+        eng.stream_block()
+        t1 = time.perf_counter()
+        if b >= 32:  # graphs of all block phases captured during the first 32 blocks
+            lat.append((t1 - t0) * 1e3)
+    st = eng.stream_stats()
+    eng.close()
+    lat = np.array(lat)
+    res = {"workload": "streaming: %d concurrent streams, block %d @ 44.1 kHz, full chain, CUDA graph per block" % (S, B),
+           "blocks_timed": int(len(lat)), "block_period_ms": 1e3 * B / fs, "p50_ms": float(np.percentile(lat, 50)),
+           "p99_ms": float(np.percentile(lat, 99)), "max_ms": float(lat.max()), "mean_ms": float(lat.mean()),
+           "realtime_margin_p99": float(1e3 * B / fs / np.percentile(lat, 99)), "graph_captures": st["graph_captures"],
+           "timer": "host perf_counter around vp_engine_stream_block (pinned H2D + graph + pinned D2H + sync)"}
+    return res
 
 
 def main():
@@ -349,6 +390,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-streams", type=int, default=0)
     ap.add_argument("--ref-streams", type=int, default=0)
+    ap.add_argument("--stream-blocks", type=int, default=1500, help="blocks timed by the streaming latency test")
+    ap.add_argument("--no-stream", action="store_true", help="skip the streaming (p99 block latency) sub-test")
+    ap.add_argument("--stream-only", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         print("note: --warmup < 3 breaks the timing rules; use it for smoke runs only", file=sys.stderr)
@@ -376,6 +420,10 @@ def main():
         return subprocess.call(cmd)
     group = Group()
     try:
+        if args.stream_only:
+            if group.rank == 0:
+                print(json.dumps({"metric": "p99 block latency", "unit": "ms", "higher_is_better": False, **run_streaming(args, group)}), flush=True)
+            return 0
         run_engine(args, wl, group)
     finally:
         group.close()

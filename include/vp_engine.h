@@ -136,6 +136,15 @@ int vp_engine_process_host(vp_engine* e, int nBlocks, const float* voice, const 
 
 int vp_engine_sync(vp_engine* e);
 
+/* Low-latency streaming, one host block per call (BASELINE config 5). The engine owns pinned host buffers
+ * voice / synthL / outL, each float[nStreams][samplesPerBlock]: fill the inputs, call vp_engine_stream_block, read
+ * outL when it returns (L == R; gainSynth must be off; synthR is not carried). Equivalent to
+ * vp_engine_process_host(e, 1, ...). The block's H2D copies, kernels and D2H copy are replayed from a CUDA graph
+ * captured the first time each block phase (position of the block on the frame grids) occurs. */
+int vp_engine_stream_buffers(vp_engine* e, float** voice, float** synthL, float** outL);
+int vp_engine_stream_block(vp_engine* e);
+int vp_engine_stream_stats(const vp_engine* e, uint64_t* graphLaunches, uint64_t* graphCaptures);
+
 /* Decisions of the most recent process call for one stream: up to cap
  * records, *nFrames = frames available. */
 int vp_engine_get_pitch_frames(vp_engine* e, int stream, vp_pitch_frame* out, int cap, int* nFrames);

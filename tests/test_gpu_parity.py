@@ -248,6 +248,29 @@ def test_block_by_block_streaming_matches_oracle(vp, oracle):
         assert_audio(r["outL"], out[s], "stream %d" % s)
 
 
+def test_graph_streaming_equals_host_calls(vp):
+    """vp_engine_stream_block (pinned buffers + one CUDA graph per block phase) == vp_engine_process_host per block."""
+    fs, B, S, nb = 44100.0, 128, 9, 120
+    voice, sl, _ = vp.synth_host(fs, S, nb * B, flavour=0, first_stream=900)
+    ref = vp.Engine(fs, B, S, nb, params=vp.default_params(keyPitch=3))
+    refL, _ = ref.process(voice, sl, None, want_right=False)
+    ref.close()
+    eng = vp.Engine(fs, B, S, 1, params=vp.default_params(keyPitch=3))
+    try:
+        hv, hs, ho = eng.stream_buffers()
+        out = np.zeros_like(refL)
+        for b in range(nb):
+            hv[:] = voice[:, b * B:(b + 1) * B]
+            hs[:] = sl[:, b * B:(b + 1) * B]
+            eng.stream_block()
+            out[:, b * B:(b + 1) * B] = ho
+        st = eng.stream_stats()
+        assert st["graph_launches"] == nb and st["graph_captures"] <= 16  # 6 block phases x 2 history buffers (+ first blocks)
+        assert np.array_equal(out, refL)
+    finally:
+        eng.close()
+
+
 def test_many_streams_spot_parity(vp, oracle):
     """A batch wide enough to fill the GPU (1024 streams x 2 s, chain); the oracle checks a spread of streams."""
     fs, B, S = 44100.0, 1024, 1024

@@ -4,7 +4,7 @@
 TAG=${1:-q}; RX=${2:-none}; shift; shift
 O=gpurun_out; mkdir -p $O
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu_$TAG.log
-timeout 900 python bench.py --no-e2e --no-cpu "$@" > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc=$?"
+timeout 900 python bench.py --no-e2e --no-cpu --no-stream "$@" > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:

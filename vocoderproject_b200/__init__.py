@@ -27,7 +27,8 @@ ABI_SYMBOLS = [
     "vp_engine_get_voc_frames", "vp_engine_get_stats", "vp_engine_last_timing", "vp_stage_name",
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
-    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset",
+    "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset", "vp_engine_stream_buffers", "vp_engine_stream_block",
+    "vp_engine_stream_stats",
 ]
 
 
@@ -101,6 +102,9 @@ def load_library(path=None):
         "vp_measure_peaks": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "vp_engine_timing_reset": (i, [vp, i]),
         "vp_engine_reset": (i, [vp]),
+        "vp_engine_stream_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "vp_engine_stream_block": (i, [vp]),
+        "vp_engine_stream_stats": (i, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "vp_measure_peaks2": (i, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "vp_engine_last_timing_counts": (i, [vp, C.POINTER(i)]),
         "vp_engine_timer_record": (i, [vp, i]),
@@ -222,6 +226,26 @@ class Engine:
     def reset(self):
         """prepareToPlay again: forget every stream's history; the next process call starts at block 0."""
         self._check(self.lib.vp_engine_reset(self.h))
+
+    # ---- low-latency streaming: one host block per call through pinned buffers and a CUDA graph per block phase ----
+    def stream_buffers(self):
+        """(voice, synthL, outL): numpy views [S][B] of the engine's pinned host buffers."""
+        pv, ps, po = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.vp_engine_stream_buffers(self.h, C.byref(pv), C.byref(ps), C.byref(po)))
+        shape = (self.n_streams, self.block)
+
+        def view(p):
+            buf = (C.c_float * (shape[0] * shape[1])).from_address(p.value)
+            return np.frombuffer(buf, dtype=np.float32).reshape(shape)
+        return view(pv), view(ps), view(po)
+
+    def stream_block(self):
+        self._check(self.lib.vp_engine_stream_block(self.h))
+
+    def stream_stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.vp_engine_stream_stats(self.h, C.byref(a), C.byref(b)))
+        return {"graph_launches": a.value, "graph_captures": b.value}
 
     def set_params(self, params):
         self._check(self.lib.vp_engine_set_params(self.h, C.byref(params)))

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -70,6 +71,11 @@ struct vp_engine {
     bool keepDecisions = true;
     int lastBlocks = 0;
     VPGeom lastG;  // geometry of the most recent process call (frame counts depend on where the timeline stood)
+    // ---- low-latency streaming (one host block per call): pinned host I/O, fixed device I/O, one CUDA graph per block phase
+    float *sHostV = nullptr, *sHostS = nullptr, *sHostO = nullptr;  // pinned [S][B]
+    float *sDevV = nullptr, *sDevS = nullptr, *sDevO = nullptr;     // device [S][B]
+    std::map<std::vector<long long>, cudaGraphExec_t> graphs;
+    uint64_t graphLaunches = 0, graphCaptures = 0;
     // host-path staging (device), 3 slices
     int Sh = 0;
     float* hIn[3][3] = {{nullptr}};
@@ -246,6 +252,14 @@ static void free_workspace(vp_engine* e) {
         for (int j = 0; j < 2; ++j) if (e->hOut[i][j]) { cudaFree(e->hOut[i][j]); e->hOut[i][j] = nullptr; }
     }
     e->Sh = 0;
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    e->graphs.clear();
+    if (e->sHostV) { cudaFreeHost(e->sHostV); e->sHostV = nullptr; }
+    if (e->sHostS) { cudaFreeHost(e->sHostS); e->sHostS = nullptr; }
+    if (e->sHostO) { cudaFreeHost(e->sHostO); e->sHostO = nullptr; }
+    if (e->sDevV) { cudaFree(e->sDevV); e->sDevV = nullptr; }
+    if (e->sDevS) { cudaFree(e->sDevS); e->sDevS = nullptr; }
+    if (e->sDevO) { cudaFree(e->sDevO); e->sDevO = nullptr; }
 }
 
 extern "C" int vp_engine_create(vp_engine** out, int device) {
@@ -319,6 +333,10 @@ extern "C" int vp_engine_set_params(vp_engine* e, const vp_params* p) {
     // LPC orders size the workspace; lpcPitch is read in prepare only in the reference too (PitchProcess.cpp:70)
     if (e->prepared && (p->lpcVoice > e->capV || p->lpcSynth > e->capS || p->lpcPitch != e->capP))
         return vp_err(e, VP_E_STATE, "LPC order beyond what vp_engine_prepare sized (lpcPitch is fixed at prepare): set params before prepare");
+    if (memcmp(&e->prm, p, sizeof *p) != 0) {  // kernel arguments are baked into the captured graphs
+        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+        e->graphs.clear();
+    }
     e->prm = *p;
     if (e->prepared && (keyChanged || e->lutKey != p->keyPitch)) {
         cudaSetDevice(e->device);
@@ -759,6 +777,83 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     finish_call(e, nBlocks);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
     return vp_engine_sync(e);
+}
+
+// ---- low-latency streaming --------------------------------------------------------------------------------------
+extern "C" int vp_engine_stream_buffers(vp_engine* e, float** voice, float** synthL, float** outL) {
+    if (!e) return VP_E_ARG;
+    if (!e->prepared) return vp_err(e, VP_E_STATE, "vp_engine_prepare has not been called");
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)e->S * e->B * sizeof(float);
+    if (!e->sHostV) {
+        VP_CUDA_OK(cudaHostAlloc((void**)&e->sHostV, bytes, cudaHostAllocDefault));
+        VP_CUDA_OK(cudaHostAlloc((void**)&e->sHostS, bytes, cudaHostAllocDefault));
+        VP_CUDA_OK(cudaHostAlloc((void**)&e->sHostO, bytes, cudaHostAllocDefault));
+        VP_CUDA_OK(cudaMalloc((void**)&e->sDevV, bytes));
+        VP_CUDA_OK(cudaMalloc((void**)&e->sDevS, bytes));
+        VP_CUDA_OK(cudaMalloc((void**)&e->sDevO, bytes));
+        memset(e->sHostV, 0, bytes); memset(e->sHostS, 0, bytes); memset(e->sHostO, 0, bytes);
+    }
+    if (voice) *voice = e->sHostV;
+    if (synthL) *synthL = e->sHostS;
+    if (outL) *outL = e->sHostO;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_stream_block(vp_engine* e) {
+    if (!e) return VP_E_ARG;
+    if (!e->prepared || !e->sHostV) return vp_err(e, VP_E_STATE, "call vp_engine_prepare and vp_engine_stream_buffers first");
+    if (e->prm.gainSynth > -59.0f) return vp_err(e, VP_E_ARG, "streaming mode carries side-chain channel 0 only: gainSynth must be off");
+    VP_CUDA_OK(cudaSetDevice(e->device));
+    VPGeom g;
+    make_geom(e, 1, (size_t)e->B, &g);
+    e->lastBlocks = 1;
+    e->lastG = g;
+    // everything that shapes the launch sequence or is baked into kernel arguments
+    const std::vector<long long> key = {e->blocksDone > 0 ? 1 : 0, e->histCur, g.offV, g.offP, g.nFramesV, g.nFramesP, g.kV0 < VP_VC ? g.kV0 : VP_VC};
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        const bool st = e->stageTiming;
+        e->stageTiming = false;  // event queries make no sense inside a graph
+        const size_t bytes = (size_t)e->S * e->B * sizeof(float);
+        cudaGraph_t graph = nullptr;
+        VP_CUDA_OK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeGlobal));
+        int rc = VP_OK;
+        cudaError_t ce = cudaMemcpyAsync(e->sDevV, e->sHostV, bytes, cudaMemcpyHostToDevice, e->st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->sDevS, e->sHostS, bytes, cudaMemcpyHostToDevice, e->st);
+        if (ce == cudaSuccess) {
+            for (int s0 = 0; s0 < e->S && rc == VP_OK; s0 += e->Sc) {
+                const int Sp = std::min(e->Sc, e->S - s0);
+                const size_t off = (size_t)s0 * e->B;
+                e->passCount = 0;
+                rc = run_pass(e, g, Sp, s0, e->sDevV + off, e->sDevS + off, nullptr, e->sDevO + off, nullptr);
+            }
+            if (rc == VP_OK) ce = cudaMemcpyAsync(e->sHostO, e->sDevO, bytes, cudaMemcpyDeviceToHost, e->st);
+        }
+        cudaError_t ce2 = cudaStreamEndCapture(e->st, &graph);
+        e->stageTiming = st;
+        if (rc != VP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return vp_fail(e, ce, "stream capture", __FILE__, __LINE__); }
+        if (ce2 != cudaSuccess) return vp_fail(e, ce2, "cudaStreamEndCapture", __FILE__, __LINE__);
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return vp_fail(e, ce, "cudaGraphInstantiate", __FILE__, __LINE__);
+        it = e->graphs.emplace(key, exec).first;
+        e->graphCaptures++;
+    }
+    VP_CUDA_OK(cudaGraphLaunch(it->second, e->st));
+    e->graphLaunches++;
+    finish_call(e, 1);
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    return VP_OK;
+}
+
+extern "C" int vp_engine_stream_stats(const vp_engine* e, uint64_t* graphLaunches, uint64_t* graphCaptures) {
+    if (!e) return VP_E_ARG;
+    if (graphLaunches) *graphLaunches = e->graphLaunches;
+    if (graphCaptures) *graphCaptures = e->graphCaptures;
+    return VP_OK;
 }
 
 extern "C" int vp_engine_get_pitch_frames(vp_engine* e, int stream, vp_pitch_frame* out, int cap, int* nFrames) {
