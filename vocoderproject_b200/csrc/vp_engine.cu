@@ -731,17 +731,26 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     const long long n = (long long)nBlocks * e->B;
     const bool synthOn = e->prm.gainSynth > -59.0f;
     if (e->Sh == 0) {
-        // slice = at most Sc streams and at most ~1 GiB per array
-        long long Sh = std::max<long long>(1, ((long long)1 << 28) / ((long long)e->maxBlocks * e->B));
+        // slice = at most Sc streams and at most ~3 GiB per array: large enough that a slice's vocoder kernels outlast
+        // its (latency-bound, side-stream) pitch-mark chain, small enough that pipeline fill / drain stay short
+        long long Sh = std::max<long long>(1, ((long long)3 << 28) / ((long long)e->maxBlocks * e->B));
+        if (Sh > 32) Sh &= ~31LL;
         Sh = std::min<long long>(Sh, e->Sc);
         Sh = std::min<long long>(Sh, (e->S + 2) / 3 > 0 ? (e->S + 2) / 3 : 1);
         if (Sh < 1) Sh = 1;
         const size_t cnt = (size_t)Sh * (size_t)e->maxBlocks * e->B;
         for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) if ((rc = wsalloc(e, &e->hIn[i][j], cnt))) return rc;
-            for (int j = 0; j < 2; ++j) if ((rc = wsalloc(e, &e->hOut[i][j], cnt))) return rc;
+            for (int j = 0; j < 2; ++j) if ((rc = wsalloc(e, &e->hIn[i][j], cnt))) return rc;
+            if ((rc = wsalloc(e, &e->hOut[i][0], cnt))) return rc;
         }
         e->Sh = (int)Sh;
+    }
+    if (synthOn && !e->hIn[0][2]) {  // the right side-chain / right output only travel when the dry side-chain is mixed in
+        const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
+        for (int i = 0; i < 3; ++i) {
+            if ((rc = wsalloc(e, &e->hIn[i][2], cnt))) return rc;
+            if ((rc = wsalloc(e, &e->hOut[i][1], cnt))) return rc;
+        }
     }
     VPGeom g;
     make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense

@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     const double* Ec = Ech + (size_t)s * nChunks + (size_t)3 * f;
     const double A = (Ec[0] + Ec[1]) + (Ec[2] + Ec[3]);
     const int kA = lane * PER;
+    const long long tq = q - g.lat;                                     // input index of x[q]
+    const bool inside = tq >= 0 && tq + L + tauMax <= g.n;              // common case: no history, no end of input
     const float* P0 = P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad + kA;
     double dn[PER], en[PER];
     double locDelta = 0.0;
@@ -477,7 +479,9 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         const int k = kA + j;
         double dl = 0.0;
         if (k < tauMax) {
-            const double h = (double)vp_x(v, q + L + k, g), l = (double)vp_x(v, q + k, g);
+            double h, l;
+            if (inside) { h = (double)__ldg(v.x + tq + L + k); l = (double)__ldg(v.x + tq + k); }
+            else { h = (double)vp_x(v, q + L + k, g); l = (double)vp_x(v, q + k, g); }
             dl = h * h - l * l;
         }
         en[j] = dl;  // delta for now

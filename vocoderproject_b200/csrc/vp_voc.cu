@@ -236,11 +236,23 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
         // ---- prefetch the hop new samples of frame k+1 (positions u0 + wlen .. u0 + wlen + hop)
         float nv[AV_NPRE], ns[AV_NPRE];
         const bool more = (fb + 1 < AV_BATCH) && (k + 1 < g.nFramesV);
+        {
+            const long long t0 = u0 + wlen - g.lat;  // input index of the first new sample
+            if (more && t0 >= 0 && t0 + hop <= g.n) {  // common case: entirely inside this call's input
 #pragma unroll
-        for (int q = 0; q < AV_NPRE; ++q) {
-            const int j = lane + q * 32;
-            nv[q] = (more && j < hop) ? vp_x(v, u0 + wlen + j, g) : 0.0f;
-            ns[q] = (more && j < hop) ? vp_x(y, u0 + wlen + j, g) : 0.0f;
+                for (int q = 0; q < AV_NPRE; ++q) {
+                    const int j = lane + q * 32;
+                    nv[q] = (j < hop) ? __ldg(v.x + t0 + j) : 0.0f;
+                    ns[q] = (j < hop) ? __ldg(y.x + t0 + j) : 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < AV_NPRE; ++q) {
+                    const int j = lane + q * 32;
+                    nv[q] = (more && j < hop) ? vp_x(v, u0 + wlen + j, g) : 0.0f;
+                    ns[q] = (more && j < hop) ? vp_x(y, u0 + wlen + j, g) : 0.0f;
+                }
+            }
         }
         __syncwarp();
         // ---- windowed FP64 copies from the ring
