@@ -1266,11 +1266,15 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
         const int i0 = sl * 32;
         if (i0 >= maxSteps) break;
         // load: row fr of the tile <- outE[frame f0+fr][i0 .. i0+32)
-        for (int fr = 0; fr < 32; ++fr) {
-            const int steps = __shfl_sync(0xffffffffu, nSteps, fr);
-            float val = 0.0f;
-            if (i0 + lane < steps) val = outE[(size_t)(f0 + fr) * L + i0 + lane];
-            tin[warp][fr][lane] = val;
+        for (int fr0 = 0; fr0 < 32; fr0 += 8) {  // 8 independent loads in flight per lane
+            float val[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int steps = __shfl_sync(0xffffffffu, nSteps, fr0 + q);
+                val[q] = (i0 + lane < steps) ? __ldg(outE + (size_t)(f0 + fr0 + q) * L + i0 + lane) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tin[warp][fr0 + q][lane] = val[q];
         }
         __syncwarp();
         for (int j = 0; j < 32; ++j) {

@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(LV_THREADS) k_voc_levinson_static(VPGeom g, VP
     constexpr int NR = RV + RSY;
     constexpr int RS = NR | 1;                        // odd row stride in shared memory
     extern __shared__ double sm[];
+    __shared__ size_t sRow[LV_THREADS];
     double* sR = sm;                                  // [LV_THREADS][RS]  rows in; the coefficient rows go out through it
     const int tid = threadIdx.x;
     const long long f0 = (long long)blockIdx.x * LV_THREADS;
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(LV_THREADS) k_voc_levinson_static(VPGeom g, VP
         const long long idx = f0 + tid;
         const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
         const size_t orow = vp_vrow(g, s, k);
+        sRow[tid] = orow;
         double* row = sR + tid * RS;
         const double eS = lev_energy_static<PS>(row + RV, row + RV, wlen, row + RV + PS + 1);
         // a frame skipped by the silence gate (VocoderProcess.cpp:199-204) is marked with EeSynth = -1: the synthesis
@@ -491,17 +493,14 @@ __global__ void __launch_bounds__(LV_THREADS) k_voc_levinson_static(VPGeom g, VP
         EeV[orow] = lev_energy_static<PV>(row, row, wlen, row + PV + 1);
     }
     __syncthreads();
+    // coalesced coefficient rows out; the workspace row of each frame (carry rows per stream in front) was noted by its thread
     for (int i = tid; i < nF * (PV + 1); i += LV_THREADS) {
         const int fi = i / (PV + 1), m = i % (PV + 1);
-        const long long idx = f0 + fi;
-        const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
-        aV[vp_vrow(g, s, k) * (PV + 1) + m] = sR[fi * RS + m];
+        aV[sRow[fi] * (PV + 1) + m] = sR[fi * RS + m];
     }
     for (int i = tid; i < nF * (PS + 1); i += LV_THREADS) {
         const int fi = i / (PS + 1), m = i % (PS + 1);
-        const long long idx = f0 + fi;
-        const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
-        aS[vp_vrow(g, s, k) * (PS + 1) + m] = sR[fi * RS + RV + m];
+        aS[sRow[fi] * (PS + 1) + m] = sR[fi * RS + RV + m];
     }
 }
 

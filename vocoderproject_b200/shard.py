@@ -32,7 +32,9 @@ class Group:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29511")
             if backend is None:
-                backend = "nccl" if torch.cuda.is_available() else "gloo"
+                # scalars only (barrier, max / sum of per-rank timings): gloo on the host is all it takes, and it keeps
+                # NCCL (and its banner on stdout) out of a path that has no collective
+                backend = "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
                 self.device = torch.device("cuda", self.local_rank)
