@@ -319,15 +319,35 @@ def run_engine(args, wl, group):
                   "pitch_lpc": (sm["pitch"]["autocorr"] + sm["pitch"]["levinson"]) * frames_p,
                   "pitch_psola": (sm["pitch"]["residual_fir"] + sm["pitch"]["psola"]) * frames_p,
                   "pitch_iir": (sm["pitch"]["iir"] + sm["pitch"]["ola"]) * frames_p}.get(kname, 0.0)
+        # the same stage counted as the FP64 multiply-adds its algorithm needs (these kernels run on the FP64 pipe)
+        wl_, ov_, os_, op_ = sz["wlenV"], prm.lpcVoice, prm.lpcSynth, prm.lpcPitch
+        kdfma = {"voc_synth": (ov_ + os_ + 1) * wl_ * frames_v,
+                 "voc_autocorr": (sum(wl_ - m for m in range(ov_ + 1)) + sum(wl_ - m for m in range(os_ + 1))) * frames_v,
+                 "pitch_psola": (sz["tauMax"] + sz["frameLenP"] + 3 * sz["chunk"]) * (op_ + 1) * frames_p,
+                 "pitch_iir": op_ * sz["frameLenP"] * frames_p}.get(kname)
         ach = 2.0 * kslots / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
         peak = 2.0 * p32 / 1e12
         io_bytes = 12.0 * samples_rank  # voice + synth ch0 in, one channel out (float32)
+        # DRAM bytes of that kernel from the committed ncu --set full capture (per sample there), scaled to one launch here
+        traffic, traffic_note = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01x.json")) as f:
+                tj = json.load(f)
+            if kname in tj["stages"] and wl["fs"] == 48000.0 and not wl["params"]:
+                traffic = tj["stages"][kname]["dram_bytes_per_sample"] * samples_rank / kcnt
+                traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of %s in %s, per sample x samples of one launch" % (
+                    tj["stages"][kname]["kernel"], tj["source"])
+        except Exception:
+            pass
         roofline = {"bound": "fp32", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                    "traffic": None, "kernel_ms_per_launch": kms / kcnt, "kernel_launches_timed": kcnt,
+                    "traffic": traffic, "traffic_note": traffic_note, "kernel_ms_per_launch": kms / kcnt, "kernel_launches_timed": kcnt,
                     "kernel_share_of_step": kms / tot_ms if tot_ms else None,
                     "peak_source": "vp_measure_peaks FP32 FMA issue-rate microbenchmark on this GPU in this run (2 flop per lane-op); "
                                    "MEASURED_PEAKS.json (%s) has no FP32 CUDA-core figure" % peaks_src,
                     "note": "algorithmic FP32 lane-ops of the minimal direct form (SURVEY App. C.5), 1 lane-op counted as 2 flop on both sides",
+                    "fp64": (None if kdfma is None else {"achieved_tdfma_per_s": kdfma / (kms * 1e-3) / 1e12, "peak_tdfma_per_s": peaks_fp["fp64_fma_per_s"] / 1e12,
+                                                         "frac": kdfma / (kms * 1e-3) / peaks_fp["fp64_fma_per_s"],
+                                                         "note": "this kernel is FP64-pipe bound: algorithmic DFMAs / event time vs the measured DFMA issue rate"}),
                     "chain": {"slots_per_sample": chain_slots, "achieved_tflops": 2.0 * chain_slots * samples_rank / dev_s / 1e12,
                               "frac": chain_slots * samples_rank / dev_s / p32 if p32 else None},
                     "hbm": {"achieved_gbs": io_bytes / dev_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src,
