@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch
 
 // P > 0: LPC order known at compile time (coefficients and the residual window live in registers); P == 0: any order.
 template <int P>
-__global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables tb, const float* __restrict__ voice,
+__global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                             vp_pitch_frame* __restrict__ frames,
                                                             const double* __restrict__ aP, float* __restrict__ outE,
                                                             int xLen, int eLen) {
@@ -1050,37 +1050,11 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
 
     vp_stage<8>(xf, v, p - X0, xLen, g, tid, PF_THREADS);
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
-    if (tid == 0) sAn[VP_MAX_MARKS] = 0;
+    __shared__ int sELo, sEHi;
+    if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; }
     const double* ap = aP + fidx * (size_t)(ord + 1);
     __syncthreads();
-    // ---- residual e[j] = sum_k a[k] x[j - tauMax - k] over frame-relative [-tauMax, L + 3c) (PitchProcess.cpp:280-302)
-    if (P > 0) {
-        constexpr int PP = (P > 0) ? P : 1;
-        double ar[PP + 1];
-#pragma unroll
-        for (int k = 0; k <= PP; ++k) ar[k] = ap[k];
-        for (int j0 = tid * PF_RJ; j0 < eLen; j0 += PF_THREADS * PF_RJ) {
-            double w[PF_RJ + PP];
-#pragma unroll
-            for (int q = 0; q < PF_RJ + PP; ++q) w[q] = (j0 + q < xLen) ? (double)xf[j0 + q] : 0.0;  // x at e-index j0 + q - PP
-#pragma unroll
-            for (int jj = 0; jj < PF_RJ; ++jj) {
-                double acc = 0.0;
-#pragma unroll
-                for (int k = 0; k <= PP; ++k) acc = fma(ar[k], w[jj + PP - k], acc);
-                if (j0 + jj < eLen) e[j0 + jj] = acc;
-            }
-        }
-    } else {
-        for (int j = tid; j < eLen; j += PF_THREADS) {
-            double acc = 0.0;
-            for (int k = 0; k <= ord; ++k) acc = fma(ap[k], (double)xf[j + ord - k], acc);
-            e[j] = acc;
-        }
-    }
-    __syncthreads();
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
-    for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;  // own indices only (i mod PF_THREADS == tid): no barrier needed
     if (T > 0 && T < tauMax) {
         const double* __restrict__ hg = tb.hann + tb.hannOff[T];
         for (int i = tid; i < 2 * T + 1; i += PF_THREADS) hs[i] = __ldg(hg + i);
@@ -1135,12 +1109,43 @@ __global__ void __launch_bounds__(PF_THREADS) k_pitch_psola(VPGeom g, VPTables t
                 gEv[tid] = L + nc;                            // residual filtered so far
                 gX0[tid] = x0;
                 gX1[tid] = xEnd;
+                atomicMin(&sELo, max(clAn - T + tauMax - 1, 0));          // grain samples j = 0 .. 2T (and j - 1)
+                atomicMax(&sEHi, min(clAn + T + tauMax + 1, eLen));
                 fl |= 1 | (tid == 0 ? 2 : 0) | (tid == nSt - 1 ? 4 : 0);
             }
         }
         gFl[tid] = fl;
     }
     __syncthreads();
+    // ---- residual e[j] = sum_k a[k] x[j - tauMax - k] (PitchProcess.cpp:280-302). The reference filters frame-relative
+    // [-samplesToKeep, L + 3c); only the part the grains read is computed: [eLo, eHi) from the grain table.
+    const int eLo = sELo, eHi = sEHi;
+    if (P > 0) {
+        constexpr int PP = (P > 0) ? P : 1;
+        double ar[PP + 1];
+#pragma unroll
+        for (int k = 0; k <= PP; ++k) ar[k] = ap[k];
+        for (int j0 = eLo + tid * PF_RJ; j0 < eHi; j0 += PF_THREADS * PF_RJ) {
+            double w[PF_RJ + PP];
+#pragma unroll
+            for (int q = 0; q < PF_RJ + PP; ++q) w[q] = (j0 + q < xLen) ? (double)xf[j0 + q] : 0.0;  // x at e-index j0 + q - PP
+#pragma unroll
+            for (int jj = 0; jj < PF_RJ; ++jj) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k <= PP; ++k) acc = fma(ar[k], w[jj + PP - k], acc);
+                if (j0 + jj < eHi) e[j0 + jj] = acc;
+            }
+        }
+    } else {
+        for (int j = eLo + tid; j < eHi; j += PF_THREADS) {
+            double acc = 0.0;
+            for (int k = 0; k <= ord; ++k) acc = fma(ap[k], (double)xf[j + ord - k], acc);
+            e[j] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;  // own indices only (i mod PF_THREADS == tid): no barrier needed
     bool ub = !okT;
     if (okT) {
         for (int m = 0; m < nSt; ++m) {
