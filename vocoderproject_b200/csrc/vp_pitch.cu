@@ -1306,9 +1306,10 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
             if (i < steps) {
                 const long long u = pf + i;
                 if (u >= 0 && u < g.n) {  // positions before 0 went out with an earlier call, beyond n go out with a later one
-                    float* o = outP + (size_t)sf * g.wstride + u;
+                    float* o = outP + (size_t)sf * g.pstride + u;
                     const float val = tout[warp][fr][lane];
-                    if (i < c || i >= 3 * c) atomicAdd(o, val);
+                    if (i < c || i >= 3 * c) atomicAdd(o, val);   // cross-fade chunks: two frames contribute
+                    else if (g.pAccum) *o += val;                  // private chunk, on top of the vocoder's output
                     else *o = val;
                 }
             }

@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     const long long emit1 = lastSeg ? g.n : (long long)kE * hop + g.offV;
     const int rho0 = (seg == 0) ? -VP_VC : kS - 3;  // a position is covered by 4 frames; 4 carry rows when offV > 0
     const VPRow y = vp_row(synth, g.histS, s, g);
-    float* o = outV + (size_t)s * g.wstride;
+    float* o = outV + (size_t)s * g.vstride;
     const double gv = (double)g.gainVocF;
     double a[P + 1], as[PS + 1], st[P + 1], t[PS + 1];
 #pragma unroll
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
     }
     __syncwarp();
     if (live) {
-        float* o = outV + (size_t)s * g.wstride;
+        float* o = outV + (size_t)s * g.vstride;
         const int ov = wlen - hop;
         for (int i = lane; i < span; i += 32) {
             const long long u = uBase + i;
