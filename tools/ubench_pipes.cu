@@ -120,6 +120,28 @@ __global__ void k_ffma2(float* sink, int iters) {
     if (r == 123456789.0f) sink[0] = r;
 }
 
+// sliding-window correlation pattern of the engine's autocorrelation / YIN loops: acc[j] += x_u * W[(u + j) % R]
+// (ROT = 1: every accumulator meets every window register) versus the same FMAs with a fixed pairing (ROT = 0)
+template <typename T, int R, int ROT>
+__global__ void k_window(T* sink, int iters) {
+    T acc[R], W[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { acc[j] = (T)0; W[j] = (T)1e-3 * (T)(j + 1 + (threadIdx.x & 3)); }
+    T x = (T)0.999 + (T)1e-6 * (T)threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = fma(x, W[ROT ? (u + j) % R : j], acc[j]);
+            x = -x;
+        }
+    }
+    T r = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) r += acc[j] + W[j];
+    if (r == (T)123456789) sink[0] = r;
+}
+
 template <typename F>
 static double timeit(F launch) {
     cudaEvent_t a, b;
@@ -173,6 +195,19 @@ int main() {
         printf(" | FFMA ch16 %6.2f", n * 16 / t / 1e12);
         t = timeit([&] { k_ffma2<8><<<sms, threads>>>((float*)sink, iters); });
         printf("  FFMA2 ch8x2 %6.2f T FMA/s\n", n * 16 / t / 1e12);
+    }
+    {
+        const int threads = 256, blocks = sms * 4, it2 = 2000;
+        const double n = (double)blocks * threads * it2;
+        double t;
+        t = timeit([&] { k_window<float, 15, 0><<<blocks, threads>>>((float*)sink, it2); });
+        printf("window R=15 FP32 fixed pairing    %6.2f T FMA/s\n", n * 225 / t / 1e12);
+        t = timeit([&] { k_window<float, 15, 1><<<blocks, threads>>>((float*)sink, it2); });
+        printf("window R=15 FP32 rotating pairing %6.2f T FMA/s\n", n * 225 / t / 1e12);
+        t = timeit([&] { k_window<double, 14, 0><<<blocks, threads>>>((double*)sink, it2); });
+        printf("window R=14 FP64 fixed pairing    %6.2f T FMA/s\n", n * 196 / t / 1e12);
+        t = timeit([&] { k_window<double, 14, 1><<<blocks, threads>>>((double*)sink, it2); });
+        printf("window R=14 FP64 rotating pairing %6.2f T FMA/s\n", n * 196 / t / 1e12);
     }
     return 0;
 }
