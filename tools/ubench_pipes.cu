@@ -142,6 +142,43 @@ __global__ void k_window(T* sink, int iters) {
     if (r == (T)123456789) sink[0] = r;
 }
 
+// the YIN correlation inner loop with its shared-memory traffic: a = xa[n] (broadcast), window refilled from xw[n + R]
+// (lane stride R). VEC = 1: the a values come as one 64-bit broadcast load per two steps.
+template <int R, int VEC>
+__global__ void __launch_bounds__(256, 4) k_yinloop(float* sink, int c, int reps) {
+    __shared__ float xs[8 * 288 + 512];
+    for (int j = threadIdx.x; j < 8 * 288 + 512; j += blockDim.x) xs[j] = 1e-3f * (float)((j * 7 + blockIdx.x) % 113);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xa = xs + warp * 288;
+    const float* xw = xa + lane * R;
+    float tot = 0.f;
+    for (int rep = 0; rep < reps; ++rep) {
+        float acc[R], W[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r] = 0.f; W[r] = xw[r]; }
+        for (int n = 0; n + R <= c; n += R) {
+            if (VEC && (R % 2 == 1)) {
+                // odd R: steps pair up across two bodies; keep it simple: scalar loads for the odd tail
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                float a;
+                if (VEC && (u % 2 == 0) && u + 1 < R) {
+                    const float2 a2 = *reinterpret_cast<const float2*>(xa + ((n + u) & ~1));
+                    a = ((n + u) & 1) ? a2.y : a2.x;
+                } else a = xa[n + u];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = fmaf(a, W[(u + r) % R], acc[r]);
+                W[u % R] = xw[n + u + R];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) tot += acc[r];
+    }
+    if (tot == 123456789.f) sink[0] = tot;
+}
+
 template <typename F>
 static double timeit(F launch) {
     cudaEvent_t a, b;
@@ -204,6 +241,12 @@ int main() {
         printf("window R=15 FP32 fixed pairing    %6.2f T FMA/s\n", n * 225 / t / 1e12);
         t = timeit([&] { k_window<float, 15, 1><<<blocks, threads>>>((float*)sink, it2); });
         printf("window R=15 FP32 rotating pairing %6.2f T FMA/s\n", n * 225 / t / 1e12);
+        {
+            const int c = 270, reps = 400;
+            const double nf = (double)blocks * threads * reps * (c / 15) * 225.0;
+            t = timeit([&] { k_yinloop<15, 0><<<blocks, threads>>>((float*)sink, c, reps); });
+            printf("YIN loop R=15 with LDS (a broadcast + window refill) %6.2f T FMA/s\n", nf / t / 1e12);
+        }
         t = timeit([&] { k_window<double, 14, 0><<<blocks, threads>>>((double*)sink, it2); });
         printf("window R=14 FP64 fixed pairing    %6.2f T FMA/s\n", n * 196 / t / 1e12);
         t = timeit([&] { k_window<double, 14, 1><<<blocks, threads>>>((double*)sink, it2); });

@@ -22,7 +22,6 @@ struct VPGeom {
     long long wstride; // row stride of the engine's own per-sample intermediates (outV, outP)
     long long vstride; // row stride of the array the vocoder synthesis writes (wstride, or the caller's stride in direct mode)
     long long pstride; // same for the pitch path
-    int pAccum;        // 1 = the pitch path ADDS onto what the vocoder wrote (direct mode: no separate planes, no mix kernel)
     int nFramesV;      // vocoder frames with start < n   (VocoderProcess.cpp:176)
     int nFramesP;      // pitch frames with start < n     (PitchProcess.cpp:169)
     int ordV, ordS, ordP;

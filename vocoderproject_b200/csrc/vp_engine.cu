@@ -29,8 +29,6 @@ struct vp_engine {
     std::vector<cudaEvent_t> evSide;  // (start, end) pairs of the side-stream kernel when stage timing is on
     size_t evSideUsed = 0;
     bool overlapMarks = true;
-    bool directOut = false;  // VP_DIRECT=1: vocoder writes outL, pitch path adds onto it, no k_mix (measured slower: the
-                             // read-modify-write of the pitch OLA misses in L2; kept for experiments)
     std::string err;
     vp_params prm;
     vp_sizes sz;
@@ -291,7 +289,6 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
     }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&e->evTimer[i]);
     { const char* ov = getenv("VP_OVERLAP"); e->overlapMarks = !(ov && ov[0] == '0'); }
-    { const char* dv = getenv("VP_DIRECT"); e->directOut = dv && dv[0] == '1'; }
     const char* pt = getenv("VP_STAGE_TIMING");
     e->stageTiming = pt && pt[0] == '1';
     *out = e;
@@ -525,7 +522,6 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     g->nBlocks = nBlocks; g->n = (long long)nBlocks * e->B; g->stride = (long long)stride;
     g->wstride = (long long)e->maxBlocks * e->B;
     g->vstride = g->pstride = g->wstride;
-    g->pAccum = 0;
     {   // call-local frame grid: the timeline continues where the previous call ended
         const long long u0 = e->blocksDone * (long long)e->B;
         g->offV = (int)((z.hopV - (u0 % z.hopV)) % z.hopV);
@@ -559,17 +555,8 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     g.histV = e->cHist[hc][0] + sb * e->H;
     g.histS = e->cHist[hc][1] + sb * e->H;
     g.histR = e->cHist[hc][2] + sb * e->H;
-    // Direct mode (the plug-in's default configuration): the vocoder synthesis writes every output position of outL and
-    // the pitch path adds onto it -- no separate planes, no mix kernel. Otherwise (dry voice / dry side-chain mixed in,
-    // non-default LPC orders, a path switched off) the two planes are summed by k_mix.
-    const bool direct = e->directOut && g.vocOn && !g.dryOn && !g.synthOn && !vp_voc_synth_needs_clear(g);
     float* vDst = e->dOutV;
     float* pDst = e->dOutP;
-    if (direct) {
-        g.vstride = g.pstride = g.stride;
-        g.pAccum = 1;
-        vDst = pDst = outL;
-    }
     int* listCount = e->dListCount + (e->passCount % 1024);
     e->passCount++;
     const size_t fP = (size_t)Sp * g.nFramesP;
@@ -592,7 +579,7 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     // [main stream: the vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.
     bool forked = false;
     if (g.pitchOn) {
-        if (!direct) VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), st));
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), st));
         VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
         stage_mark(e, ST_CLEAR);
         if (g.nFramesP > 0) {
@@ -655,13 +642,8 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         e->launches += 4;
         e->yinFrames += fP;
     }
-    if (!direct) {
-        vp_launch_mix(st, g, Sp, voice, synthL, synthR, e->dOutV, e->dOutP, outL, outR);
-        e->launches++;
-    } else if (outR) {  // L == R in this configuration
-        VP_CUDA_OK(cudaMemcpy2DAsync(outR, (size_t)g.stride * sizeof(float), outL, (size_t)g.stride * sizeof(float),
-                                     (size_t)g.n * sizeof(float), Sp, cudaMemcpyDeviceToDevice, st));
-    }
+    vp_launch_mix(st, g, Sp, voice, synthL, synthR, e->dOutV, e->dOutP, outL, outR);
+    e->launches++;
     stage_mark(e, ST_MIX);
     // ---- state for the next call: last rows of (carry ++ new), and the last H input samples
     vp_launch_carry_out(st, e->cGate + sb * e->gateCarry * 4, e->dGatePart, Sp, 32, e->gateCarry, g.nBlocks, rowsG);

@@ -1309,7 +1309,6 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
                     float* o = outP + (size_t)sf * g.pstride + u;
                     const float val = tout[warp][fr][lane];
                     if (i < c || i >= 3 * c) atomicAdd(o, val);   // cross-fade chunks: two frames contribute
-                    else if (g.pAccum) *o += val;                  // private chunk, on top of the vocoder's output
                     else *o = val;
                 }
             }
