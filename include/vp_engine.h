@@ -108,6 +108,12 @@ const char* vp_last_error(const vp_engine* e);
  * (0 = default); it decides how many streams are in flight per pass. */
 int vp_engine_prepare(vp_engine* e, double sampleRate, int samplesPerBlock, int nStreams, int maxBlocks,
                       size_t workspaceBytes);
+/* Replaces the reference's parameter pulls (treeState.getRawParameterValue(id)->load(); VocoderProcess.cpp:193-194,291,
+ * PitchProcess.cpp:70,206,336, PluginProcessor.cpp:212-230). Before prepare: anything in the plug-in's ranges. Between
+ * process calls of a running stream (automation): the four gains and keyPitch take effect exactly as in the reference
+ * (gainVoc per vocoder frame, gainPitch per emitted chunk, gainVoice / gainSynth per block, keyPitch per pitch frame);
+ * lpcVoice / lpcSynth / vocBool / pitchBool changes return VP_E_STATE until vp_engine_reset; lpcPitch is fixed at prepare
+ * (as in the reference, PitchProcess.cpp:70). */
 int vp_engine_set_params(vp_engine* e, const vp_params* p);
 int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out);
 

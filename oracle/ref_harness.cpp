@@ -205,11 +205,16 @@ static void process_block_logged(VocoderAudioProcessor& p, AudioBuffer<float>& b
 
 // Run one stream. voice/synthL/synthR: nBlocks*B floats each (synthR may be
 // NULL -> copy of synthL). outL/outR: nBlocks*B floats. plog/vlog may be NULL
-// when log == 0. Returns 0, or -1 on bad arguments.
-int vpref_run(double fs, int B, int nBlocks, const float* voice, const float* synthL, const float* synthR,
-              const vpref_params* q, int log, float* outL, float* outR, vpref_sizes* sizes,
-              vpref_pitch_frame* plog, int plogCap, int* nP, vpref_voc_frame* vlog, int vlogCap, int* nV) {
+// when log == 0. Parameter automation: before block schedBlock[i] the i-th
+// entry of sched is stored into the parameter tree (what a DAW's automation
+// does between two processBlock calls); q applies from prepareToPlay on.
+// Returns 0, or -1 on bad arguments.
+static int run_impl(double fs, int B, int nBlocks, const float* voice, const float* synthL, const float* synthR,
+                    const vpref_params* q, const vpref_params* sched, const int* schedBlock, int nSched, int log,
+                    float* outL, float* outR, vpref_sizes* sizes, vpref_pitch_frame* plog, int plogCap, int* nP,
+                    vpref_voc_frame* vlog, int vlogCap, int* nV) {
     if (!voice || !synthL || !q || !outL || B <= 0 || nBlocks < 0) return -1;
+    if (nSched > 0 && (!sched || !schedBlock)) return -1;
     if (!synthR) synthR = synthL;
     VocoderAudioProcessor proc;
     set_params(proc, *q);
@@ -221,6 +226,8 @@ int vpref_run(double fs, int B, int nBlocks, const float* voice, const float* sy
     std::vector<vpref_voc_frame> vl;
     int pframe = 0, vframe = 0;
     for (int b = 0; b < nBlocks; ++b) {
+        for (int i = 0; i < nSched; ++i)
+            if (schedBlock[i] == b) set_params(proc, sched[i]);
         std::memcpy(buf.getWritePointer(0), voice + (size_t)b * B, sizeof(float) * B);
         std::memcpy(buf.getWritePointer(1), synthL + (size_t)b * B, sizeof(float) * B);
         std::memcpy(buf.getWritePointer(2), synthR + (size_t)b * B, sizeof(float) * B);
@@ -234,6 +241,21 @@ int vpref_run(double fs, int B, int nBlocks, const float* voice, const float* sy
     if (plog) for (int i = 0; i < (int)pl.size() && i < plogCap; ++i) plog[i] = pl[i];
     if (vlog) for (int i = 0; i < (int)vl.size() && i < vlogCap; ++i) vlog[i] = vl[i];
     return 0;
+}
+
+int vpref_run(double fs, int B, int nBlocks, const float* voice, const float* synthL, const float* synthR,
+              const vpref_params* q, int log, float* outL, float* outR, vpref_sizes* sizes,
+              vpref_pitch_frame* plog, int plogCap, int* nP, vpref_voc_frame* vlog, int vlogCap, int* nV) {
+    return run_impl(fs, B, nBlocks, voice, synthL, synthR, q, nullptr, nullptr, 0, log, outL, outR, sizes, plog, plogCap, nP,
+                    vlog, vlogCap, nV);
+}
+
+int vpref_run_sched(double fs, int B, int nBlocks, const float* voice, const float* synthL, const float* synthR,
+                    const vpref_params* q, const vpref_params* sched, const int* schedBlock, int nSched, int log,
+                    float* outL, float* outR, vpref_sizes* sizes, vpref_pitch_frame* plog, int plogCap, int* nP,
+                    vpref_voc_frame* vlog, int vlogCap, int* nV) {
+    return run_impl(fs, B, nBlocks, voice, synthL, synthR, q, sched, schedBlock, nSched, log, outL, outR, sizes, plog, plogCap,
+                    nP, vlog, vlogCap, nV);
 }
 
 // Notes table as the reference builds it (Notes.cpp:43-70), incl. the popped

@@ -534,7 +534,22 @@ int vpo_process(double fs, int B, int nBlocks, const float* voice, const float* 
                 const vpo_params* params, float* outL, float* outR, vpo_sizes* sizes,
                 vpo_pitch_frame* plog, int plogCap, int* nP, vpo_voc_frame* vlog, int vlogCap, int* nV,
                 int* ubFlags) {
+    return vpo_process_sched(fs, B, nBlocks, voice, synthL, synthR, params, NULL, NULL, 0, outL, outR, sizes, plog, plogCap,
+                             nP, vlog, vlogCap, nV, ubFlags);
+}
+
+/* Same, with parameter automation: before block schedBlock[i] the parameter tree takes sched[i] (every read site of
+ * the reference loads the atomics afresh: VocoderProcess.cpp:193-194,291, PitchProcess.cpp:206,336,
+ * PluginProcessor.cpp:212-230; lpcPitch is only read in prepare, PitchProcess.cpp:70). */
+int vpo_process_sched(double fs, int B, int nBlocks, const float* voice, const float* synthL, const float* synthR,
+                      const vpo_params* params, const vpo_params* sched, const int* schedBlock, int nSched,
+                      float* outL, float* outR, vpo_sizes* sizes,
+                      vpo_pitch_frame* plog, int plogCap, int* nP, vpo_voc_frame* vlog, int vlogCap, int* nV,
+                      int* ubFlags) {
     if (!voice || !synthL || !params || !outL || B <= 0 || nBlocks < 0 || fs <= 0) return -1;
+    if (nSched > 0 && (!sched || !schedBlock)) return -1;
+    for (int i = 0; i < nSched; ++i)
+        if (sched[i].lpcVoice > ORDER_MAX || sched[i].lpcSynth > ORDER_MAX || sched[i].lpcVoice < 1 || sched[i].lpcSynth < 1) return -2;
     if (params->lpcVoice > ORDER_MAX || params->lpcPitch > ORDER_MAX || params->lpcSynth > ORDER_MAX ||
         params->lpcVoice < 1 || params->lpcPitch < 1 || params->lpcSynth < 1) return -2;
     vpo_t* o = (vpo_t*)calloc(1, sizeof(vpo_t));
@@ -588,9 +603,18 @@ int vpo_process(double fs, int B, int nBlocks, const float* voice, const float* 
     }
 
     int startV = 0, startP = 0; /* VocoderProcess::startSample, PitchProcess::startSample */
-    float gVoice = params->gainVoice, gSynth = params->gainSynth;
     for (int b = 0; b < nBlocks; ++b) {
         long base = (long)b * B;
+        for (int i = 0; i < nSched; ++i)
+            if (schedBlock[i] == b) {
+                const int keyOld = o->prm.keyPitch, ordP = o->prm.lpcPitch;
+                o->prm = sched[i];
+                o->prm.lpcPitch = ordP; /* read in prepare only */
+                /* Notes::getClosestFreq rebuilds the table when the key differs (Notes.cpp:83-88) */
+                if (o->prm.keyPitch != keyOld) notes_build(o->freq, &o->nFreq, o->prm.keyPitch, o->fMin, o->fMax);
+            }
+        params = &o->prm;
+        const float gVoice = params->gainVoice, gSynth = params->gainSynth;
         int gateV = -1, gateS = -1; /* lazily evaluated ring RMS gates for this block */
         /* VocoderProcess::process :173-183 */
         if (params->vocBool) {

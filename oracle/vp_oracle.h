@@ -72,6 +72,13 @@ int vpo_process(double fs, int B, int nBlocks, const float* voice, const float* 
                 vpo_pitch_frame* plog, int plogCap, int* nP, vpo_voc_frame* vlog, int vlogCap, int* nV,
                 int* ubFlags);
 
+/* Same with parameter automation: sched[i] replaces the parameters before block schedBlock[i]. */
+int vpo_process_sched(double fs, int B, int nBlocks, const float* voice, const float* synthL, const float* synthR,
+                      const vpo_params* params, const vpo_params* sched, const int* schedBlock, int nSched,
+                      float* outL, float* outR, vpo_sizes* sizes,
+                      vpo_pitch_frame* plog, int plogCap, int* nP, vpo_voc_frame* vlog, int vlogCap, int* nV,
+                      int* ubFlags);
+
 /* Notes.cpp:43-70 table; returns its size, *popped = the popped slot (U6). */
 int vpo_notes(int key, double fMin, double fMax, double* freq, int cap, double* popped);
 

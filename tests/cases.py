@@ -22,6 +22,12 @@ CASES = {
     # non-default LPC orders
     "chain44_orders": dict(fs=44100.0, B=512, seconds=1.5, input=("synth", 0, 6),
                            params=dict(lpcVoice=24, lpcSynth=8, lpcPitch=20)),
+    # parameter automation between blocks (what a DAW does to the plug-in's atomics): gains and key change mid-stream
+    "chain44_automation": dict(fs=44100.0, B=512, seconds=3.0, input=("synth", 0, 7),
+                               params=dict(keyPitch=3, gainVoice=-20.0, gainSynth=-30.0),
+                               schedule=[(40, dict(gainVoc=-6.0, gainPitch=3.0)), (97, dict(keyPitch=12)),
+                                         (150, dict(gainVoice=-60.0, gainSynth=-10.0, keyPitch=7)),
+                                         (201, dict(gainVoc=2.0, gainPitch=-4.0, keyPitch=0))]),
     # leading silence -> gates (vocoder + pitch) then voiced onset; KAT-style inputs delayed by 0.5 s
     "gate_onset": dict(fs=44100.0, B=1024, seconds=2.0, input=("kat_delayed", 22050), params=dict(keyPitch=3)),
 }
@@ -51,6 +57,16 @@ KAT_MARKS = {
     9: (768, [80, 300, 521, 742, 963], [175, 400, 625, 850]),
 }
 KAT_PERIOD, KAT_NOTE, KAT_BETA, KAT_PERIODNEW = 221, 6, 0.9822107863034768, 225
+
+
+def case_schedule(case):
+    """[(block, cumulative parameter dict), ...] of a case ('schedule' entries override what is in force so far)."""
+    cur = dict(case["params"])
+    out = []
+    for b, d in case.get("schedule", []):
+        cur = dict(cur, **d)
+        out.append((b, dict(cur)))
+    return out
 
 
 def case_inputs(vp, case):

@@ -20,17 +20,24 @@ sys.path[:0] = [ROOT, TESTS]
 
 import vocoderproject_b200 as vp  # noqa: E402  (host-side synthetic input generator only)
 import refbind  # noqa: E402
-from cases import CASES, case_inputs  # noqa: E402
+from cases import CASES, case_inputs, case_schedule  # noqa: E402
 from common import crc, oracle_decisions, stats  # noqa: E402
 
 
 def main():
     assert refbind.available("strict"), "build oracle/_ref first: make -C oracle ref"
+    only = set(sys.argv[1:])  # optional: regenerate the named cases only
     index = {}
+    if only:
+        with open(os.path.join(HERE, "index.json")) as f:
+            index = json.load(f)
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         voice, sl, sr = case_inputs(vp, case)
         prm = refbind.default_params(**case["params"])
-        r = refbind.run(case["fs"], case["B"], voice, sl, synthR=sr, params=prm, log=True, kind="strict")
+        sched = [(b, refbind.default_params(**d)) for b, d in case_schedule(case)]
+        r = refbind.run(case["fs"], case["B"], voice, sl, synthR=sr, params=prm, log=True, kind="strict", schedule=sched)
         rows = oracle_decisions(r["pitch"])
         mm = max([len(x["an"]) for x in rows] + [len(x["st"]) for x in rows] + [1])
         an = np.full((len(rows), mm), -1, np.int32)

@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from refbind import Params, PitchFrame, VocFrame, Sizes, default_params, _fptr  # same struct layouts
+from refbind import Params, PitchFrame, VocFrame, Sizes, default_params, sched_arrays, _fptr  # same struct layouts
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -34,6 +34,11 @@ def load():
     lib.vpo_process.argtypes = [C.c_double, C.c_int, C.c_int, fp, fp, fp, C.POINTER(Params), fp, fp,
                                 C.POINTER(Sizes), C.POINTER(PitchFrame), C.c_int, C.POINTER(C.c_int),
                                 C.POINTER(VocFrame), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.vpo_process_sched.restype = C.c_int
+    lib.vpo_process_sched.argtypes = [C.c_double, C.c_int, C.c_int, fp, fp, fp, C.POINTER(Params), C.POINTER(Params),
+                                      C.POINTER(C.c_int), C.c_int, fp, fp,
+                                      C.POINTER(Sizes), C.POINTER(PitchFrame), C.c_int, C.POINTER(C.c_int),
+                                      C.POINTER(VocFrame), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vpo_bench.restype = C.c_double
     lib.vpo_bench.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, fp, fp, fp, C.POINTER(Params), C.c_int, fp]
     lib.vpo_notes.restype = C.c_int
@@ -45,7 +50,8 @@ def load():
     return lib
 
 
-def run(fs, B, voice, synthL, synthR=None, params=None, log=False):
+def run(fs, B, voice, synthL, synthR=None, params=None, log=False, schedule=None):
+    """schedule: [(block, Params), ...] -- parameter automation, applied before that block."""
     lib = load()
     params = params or default_params()
     voice = np.ascontiguousarray(voice, np.float32)
@@ -61,9 +67,10 @@ def run(fs, B, voice, synthL, synthR=None, params=None, log=False):
     plog = (PitchFrame * pcap)() if log else None
     vlog = (VocFrame * vcap)() if log else None
     nP, nV, ub = C.c_int(0), C.c_int(0), C.c_int(0)
-    rc = lib.vpo_process(fs, B, nBlocks, _fptr(voice), _fptr(synthL), _fptr(synthR), C.byref(params),
-                         _fptr(outL), _fptr(outR), C.byref(sizes), plog, pcap, C.byref(nP), vlog, vcap,
-                         C.byref(nV), C.byref(ub))
+    sp, sb, ns = sched_arrays(schedule)
+    rc = lib.vpo_process_sched(fs, B, nBlocks, _fptr(voice), _fptr(synthL), _fptr(synthR), C.byref(params), sp, sb, ns,
+                               _fptr(outL), _fptr(outR), C.byref(sizes), plog, pcap, C.byref(nP), vlog, vcap,
+                               C.byref(nV), C.byref(ub))
     if rc != 0:
         raise RuntimeError("vpo_process failed: %d" % rc)
     res = {"outL": outL, "outR": outR, "ub": ub.value,

@@ -66,6 +66,11 @@ def load(kind="strict"):
     lib.vpref_run.argtypes = [C.c_double, C.c_int, C.c_int, fp, fp, fp, C.POINTER(Params), C.c_int, fp, fp,
                               C.POINTER(Sizes), C.POINTER(PitchFrame), C.c_int, C.POINTER(C.c_int),
                               C.POINTER(VocFrame), C.c_int, C.POINTER(C.c_int)]
+    lib.vpref_run_sched.restype = C.c_int
+    lib.vpref_run_sched.argtypes = [C.c_double, C.c_int, C.c_int, fp, fp, fp, C.POINTER(Params), C.POINTER(Params),
+                                    C.POINTER(C.c_int), C.c_int, C.c_int, fp, fp,
+                                    C.POINTER(Sizes), C.POINTER(PitchFrame), C.c_int, C.POINTER(C.c_int),
+                                    C.POINTER(VocFrame), C.c_int, C.POINTER(C.c_int)]
     lib.vpref_bench.restype = C.c_double
     lib.vpref_bench.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, fp, fp, fp, C.POINTER(Params), C.c_int, fp]
     lib.vpref_notes.restype = C.c_int
@@ -81,9 +86,23 @@ def _fptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def run(fs, B, voice, synthL, synthR=None, params=None, log=False, kind="strict"):
+def sched_arrays(schedule):
+    """[(block, Params), ...] -> (Params array, int array, count) for the *_sched entry points."""
+    if not schedule:
+        return None, None, 0
+    n = len(schedule)
+    ps = (Params * n)()
+    bs = (C.c_int * n)()
+    for i, (b, q) in enumerate(schedule):
+        C.memmove(C.byref(ps[i]), C.byref(q), C.sizeof(Params))
+        bs[i] = int(b)
+    return ps, bs, n
+
+
+def run(fs, B, voice, synthL, synthR=None, params=None, log=False, kind="strict", schedule=None):
     """One stream through the reference's processBlock. Returns dict with
-    outL, outR (float32[nBlocks*B]), sizes, and (log=True) pitch/voc frame logs."""
+    outL, outR (float32[nBlocks*B]), sizes, and (log=True) pitch/voc frame logs.
+    schedule: [(block, Params), ...] -- parameter automation, stored before that block."""
     lib = load(kind)
     params = params or default_params()
     voice = np.ascontiguousarray(voice, np.float32)
@@ -100,9 +119,10 @@ def run(fs, B, voice, synthL, synthR=None, params=None, log=False, kind="strict"
     vlog = (VocFrame * vcap)() if log else None
     nP = C.c_int(0)
     nV = C.c_int(0)
-    rc = lib.vpref_run(fs, B, nBlocks, _fptr(voice), _fptr(synthL), _fptr(synthR), C.byref(params),
-                       1 if log else 0, _fptr(outL), _fptr(outR), C.byref(sizes), plog, pcap, C.byref(nP),
-                       vlog, vcap, C.byref(nV))
+    sp, sb, ns = sched_arrays(schedule)
+    rc = lib.vpref_run_sched(fs, B, nBlocks, _fptr(voice), _fptr(synthL), _fptr(synthR), C.byref(params), sp, sb, ns,
+                             1 if log else 0, _fptr(outL), _fptr(outR), C.byref(sizes), plog, pcap, C.byref(nP),
+                             vlog, vcap, C.byref(nV))
     if rc != 0:
         raise RuntimeError("vpref_run failed: %d" % rc)
     res = {"outL": outL, "outR": outR, "sizes": {k: getattr(sizes, k) for k, _ in Sizes._fields_}}

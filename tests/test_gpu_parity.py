@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 import refbind
-from cases import CASES, KAT, KAT_BETA, KAT_MARKS, KAT_NOTE, KAT_PERIOD, KAT_PERIODNEW, case_inputs
+from cases import CASES, KAT, KAT_BETA, KAT_MARKS, KAT_NOTE, KAT_PERIOD, KAT_PERIODNEW, case_inputs, case_schedule
 from common import MAXABS_MAX, SNR_MIN_DB, compare_decisions, golden_index, golden_load, kat_inputs, maxabs, oracle_decisions, snr_db, stats
 
 pytestmark = pytest.mark.gpu
@@ -42,12 +42,56 @@ def golden_rows(g):
     return rows
 
 
+class _FrameRows:
+    """pitch / vocoder frame records of one stream accumulated over several calls"""
+    def __init__(self, pf, vf):
+        self.pf, self.vf = pf, vf
+
+    def pitch_frames(self, s):
+        return self.pf
+
+    def voc_frames(self, s):
+        return self.vf
+
+    def close(self):
+        pass
+
+
+def run_engine_scheduled(vp, case, voice, sl, sr, extra_cuts=()):
+    """One stream of an automation case: process calls split at the schedule's blocks (+ extra cuts), vp_engine_set_params
+    in between -- the C-ABI equivalent of a DAW writing the plug-in's parameter atomics between processBlock calls."""
+    fs, B = case["fs"], case["B"]
+    nb = len(voice) // B
+    sched = dict(case_schedule(case))
+    cuts = sorted(set([0, nb]) | set(sched) | set(extra_cuts))
+    eng = vp.Engine(fs, B, 1, max(b - a for a, b in zip(cuts, cuts[1:])), params=vp.default_params(**case["params"]))
+    try:
+        outL, outR, pf = [], [], []
+        vf = {"gated": [], "EeVoice": [], "EeSynth": [], "g": []}
+        for a, b in zip(cuts, cuts[1:]):
+            if a in sched:
+                eng.set_params(vp.default_params(**sched[a]))
+            l, r = eng.process(voice[None, a * B:b * B], sl[None, a * B:b * B], sr[None, a * B:b * B])
+            outL.append(l[0]); outR.append(r[0])
+            pf += eng.pitch_frames(0)
+            v = eng.voc_frames(0)
+            for k in vf:
+                vf[k].append(v[k])
+    finally:
+        eng.close()
+    return np.concatenate(outL), np.concatenate(outR), _FrameRows(pf, {k: np.concatenate(v) for k, v in vf.items()})
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_engine_matches_reference_golden(vp, name):
     case = CASES[name]
     g = golden_load(name)
     voice, sl, sr = case_inputs(vp, case)
-    outL, outR, eng = run_engine(vp, case["fs"], case["B"], voice[None], sl[None], sr[None], case["params"])
+    if "schedule" in case:
+        l, r, eng = run_engine_scheduled(vp, case, voice, sl, sr)
+        outL, outR = l[None], r[None]
+    else:
+        outL, outR, eng = run_engine(vp, case["fs"], case["B"], voice[None], sl[None], sr[None], case["params"])
     try:
         assert_audio(g["outL"], outL[0], name + " L")
         assert_audio(g["outR"] if len(g["outR"]) else g["outL"], outR[0], name + " R")
@@ -225,6 +269,28 @@ def test_consecutive_calls_continue_the_streams(vp, fs, B, pieces, params):
         eng.reset()  # and reset really is prepareToPlay
         l, r = eng.process(voice[:, :pieces[0] * B], sl[:, :pieces[0] * B], sr[:, :pieces[0] * B])
         assert np.abs(l - refL[:, :pieces[0] * B]).max() <= (4e-7 if "lpcVoice" in params else 0.0)
+    finally:
+        eng.close()
+
+
+def test_automation_is_independent_of_call_splitting_and_rejects_layout_changes(vp):
+    """Parameter changes between calls: the result depends on WHERE (which block) they happen, not on how the blocks in
+    between are grouped into calls; orders / enables mid-stream are refused until a reset."""
+    case = CASES["chain44_automation"]
+    voice, sl, sr = case_inputs(vp, case)
+    aL, aR, _ = run_engine_scheduled(vp, case, voice, sl, sr)
+    bL, bR, _ = run_engine_scheduled(vp, case, voice, sl, sr, extra_cuts=(1, 39, 41, 98, 149, 151, 200, 257))
+    assert np.array_equal(aL, bL) and np.array_equal(aR, bR)
+    eng = vp.Engine(case["fs"], case["B"], 1, 8, params=vp.default_params(**case["params"]))
+    try:
+        eng.process(voice[None, :4 * 512], sl[None, :4 * 512], sr[None, :4 * 512])
+        for bad in (dict(lpcVoice=30), dict(lpcSynth=7), dict(vocBool=0), dict(pitchBool=0)):
+            with pytest.raises(vp.EngineError) as ei:
+                eng.set_params(vp.default_params(**dict(case["params"], **bad)))
+            assert ei.value.code == vp.VP_E_STATE
+        eng.reset()
+        eng.set_params(vp.default_params(**dict(case["params"], lpcVoice=30)))  # fine after prepareToPlay
+        eng.process(voice[None, :4 * 512], sl[None, :4 * 512], sr[None, :4 * 512])
     finally:
         eng.close()
 

@@ -142,8 +142,8 @@ struct VPTables {
 int vp_gate_carry_rows(const VPGeom& g);
 void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synth, uint8_t* gate,
                     double* part /* [S][partRows][4]: carry rows then this call's blocks */, int partRows);
-void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G,
-                        double* hist /* [S][20] carried energy histories */);
+void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G, double* Gs,
+                        double* hist);
 
 void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                             const float* synth, const uint8_t* gate, double* rV, double* rS);

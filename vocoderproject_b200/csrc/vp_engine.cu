@@ -53,7 +53,7 @@ struct vp_engine {
     double *cGate = nullptr, *cAV = nullptr, *cAS = nullptr, *cEeS = nullptr, *cG = nullptr, *cGainHist = nullptr;
     vp_pitch_frame* cFrames = nullptr; // [S][VP_PC]
     VPMarkState* cMarks = nullptr;     // [S]
-    double *dRV = nullptr, *dRS = nullptr, *dAV = nullptr, *dAS = nullptr, *dEeV = nullptr, *dEeS = nullptr, *dG = nullptr;
+    double *dRV = nullptr, *dRS = nullptr, *dAV = nullptr, *dAS = nullptr, *dEeV = nullptr, *dEeS = nullptr, *dG = nullptr, *dGs = nullptr;
     int *dPeriod = nullptr, *dList = nullptr, *dListCount = nullptr;
     uint32_t* dYFlags = nullptr;
     vp_pitch_frame* dFrames = nullptr;
@@ -242,7 +242,7 @@ static void free_workspace(vp_engine* e) {
     for (void** p : cptrs) if (*p) { cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) if (e->cHist[i][j]) { cudaFree(e->cHist[i][j]); e->cHist[i][j] = nullptr; }
     void** ptrs[] = {(void**)&e->dGate, (void**)&e->dRV, (void**)&e->dRS, (void**)&e->dAV, (void**)&e->dAS, (void**)&e->dEeV,
-                     (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
+                     (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dGs, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
                      (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
                      (void**)&e->dOutP, (void**)&e->dFramesAll, (void**)&e->dGateAll, (void**)&e->dEeVAll, (void**)&e->dEeSAll,
                      (void**)&e->dGAll, (void**)&e->dGatePart, (void**)&e->dYinP, (void**)&e->dYinE, (void**)&e->dRP};
@@ -333,6 +333,15 @@ extern "C" int vp_engine_set_params(vp_engine* e, const vp_params* p) {
     // LPC orders size the workspace; lpcPitch is read in prepare only in the reference too (PitchProcess.cpp:70)
     if (e->prepared && (p->lpcVoice > e->capV || p->lpcSynth > e->capS || p->lpcPitch != e->capP))
         return vp_err(e, VP_E_STATE, "LPC order beyond what vp_engine_prepare sized (lpcPitch is fixed at prepare): set params before prepare");
+    // Mid-stream automation (between two process calls of a running stream) is exact for the gains and the key: every
+    // one of those is read per block / per frame / per chunk in the reference (PluginProcessor.cpp:226-230,
+    // VocoderProcess.cpp:291, PitchProcess.cpp:206,336) and the engine keeps per-frame copies where a frame outlives
+    // the call it started in. The LPC orders and the two enables change the layout of the carried per-stream state
+    // (coefficient rows, frame phase): those need vp_engine_reset (= prepareToPlay) first.
+    if (e->prepared && e->blocksDone > 0 &&
+        (p->lpcVoice != e->prm.lpcVoice || p->lpcSynth != e->prm.lpcSynth || (p->vocBool != 0) != (e->prm.vocBool != 0) ||
+         (p->pitchBool != 0) != (e->prm.pitchBool != 0)))
+        return vp_err(e, VP_E_STATE, "lpcVoice / lpcSynth / vocBool / pitchBool cannot change mid-stream: call vp_engine_reset first");
     if (memcmp(&e->prm, p, sizeof *p) != 0) {  // kernel arguments are baked into the captured graphs
         for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
         e->graphs.clear();
@@ -442,6 +451,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     if ((rc = wsalloc(e, &e->dEeV, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dEeS, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dG, fVc))) return rc;
+    if ((rc = wsalloc(e, &e->dGs, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dPeriod, fP))) return rc;
     if ((rc = wsalloc(e, &e->dYFlags, fP))) return rc;
     e->maxList = (int)std::min<size_t>(fP, (size_t)1 << 22);
@@ -569,7 +579,7 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         vp_launch_carry_in(st, e->dAV, e->cAV + sb * VP_VC * ordV1, Sp, 8 * ordV1, VP_VC, rowsV);
         vp_launch_carry_in(st, e->dAS, e->cAS + sb * VP_VC * ordS1, Sp, 8 * ordS1, VP_VC, rowsV);
         vp_launch_carry_in(st, e->dEeS, e->cEeS + sb * VP_VC, Sp, 8, VP_VC, rowsV);
-        vp_launch_carry_in(st, e->dG, e->cG + sb * VP_VC, Sp, 8, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dGs, e->cG + sb * VP_VC, Sp, 8, VP_VC, rowsV);
     }
     if (g.pitchOn) vp_launch_carry_in(st, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
     vp_launch_gate(st, g, Sp, voice, synthL, e->dGate, e->dGatePart, (int)rowsG);
@@ -620,11 +630,11 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
             vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
             stage_mark(e, ST_VOC_AC);
             vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
-            vp_launch_voc_gain(st, g, Sp, e->dEeV, e->dEeS, e->dG, e->cGainHist + sb * 20);
+            vp_launch_voc_gain(st, g, Sp, e->dEeV, e->dEeS, e->dG, e->dGs, e->cGainHist + sb * 20);
             stage_mark(e, ST_VOC_LEV);
             e->launches += 3;
         }
-        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dAV, e->dAS, e->dEeS, e->dG, vDst);
+        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dAV, e->dAS, e->dEeS, e->dGs, vDst);
         stage_mark(e, ST_VOC_SYN);
         e->launches += 1;
     }
@@ -651,7 +661,7 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         vp_launch_carry_out(st, e->cAV + sb * VP_VC * ordV1, e->dAV, Sp, 8 * ordV1, VP_VC, g.nFramesV, rowsV);
         vp_launch_carry_out(st, e->cAS + sb * VP_VC * ordS1, e->dAS, Sp, 8 * ordS1, VP_VC, g.nFramesV, rowsV);
         vp_launch_carry_out(st, e->cEeS + sb * VP_VC, e->dEeS, Sp, 8, VP_VC, g.nFramesV, rowsV);
-        vp_launch_carry_out(st, e->cG + sb * VP_VC, e->dG, Sp, 8, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cG + sb * VP_VC, e->dGs, Sp, 8, VP_VC, g.nFramesV, rowsV);
     }
     if (g.pitchOn) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
     vp_launch_hist_update(st, e->cHist[hc ^ 1][0] + sb * e->H, g.histV, voice, Sp, e->H, g.n, g.stride);

@@ -541,7 +541,8 @@ __device__ __forceinline__ int vs_skew(int pos, int hop, int sk) { return pos + 
 // One thread per frame scans back over this call's frames and, if the call started fewer than 10 processed frames
 // ago, continues into the stream's carried histories hist[s] = {EeVoice[10], EeSynth[10]} (newest first).
 __global__ void __launch_bounds__(128) k_voc_gain(VPGeom g, const double* __restrict__ EeV, const double* __restrict__ EeS,
-                                                  double* __restrict__ G, const double* __restrict__ hist, long long tot) {
+                                                  double* __restrict__ G, double* __restrict__ Gs,
+                                                  const double* __restrict__ hist, long long tot) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= tot) return;
     const int s = (int)(idx / g.nFramesV), k = (int)(idx - (long long)s * g.nFramesV);
@@ -560,6 +561,9 @@ __global__ void __launch_bounds__(128) k_voc_gain(VPGeom g, const double* __rest
         gain = sqrt(sv / ss);
     }
     G[row0 + k] = gain;
+    // what the synthesis applies: g times the frame's own gainVoc (read once per frame, VocoderProcess.cpp:291-294), so a
+    // frame that is finished by a later call keeps the gain of the block it was started in
+    Gs[row0 + k] = gain * (double)g.gainVocF;
 }
 
 // the carried histories after this call: the 10 newest processed frames of (old history ++ this call's frames)
@@ -579,9 +583,10 @@ __global__ void __launch_bounds__(64) k_voc_gain_carry(VPGeom g, const double* _
     for (int i = 0; i < 10; ++i) { h[i] = hv[i]; h[10 + i] = hs[i]; }
 }
 
-void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G, double* hist) {
+void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G, double* Gs,
+                        double* hist) {
     const long long tot = (long long)S * g.nFramesV;
-    if (tot > 0) k_voc_gain<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, EeV, EeS, G, hist, tot);
+    if (tot > 0) k_voc_gain<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, EeV, EeS, G, Gs, hist, tot);
     k_voc_gain_carry<<<(S + 63) / 64, 64, 0, st>>>(g, EeV, EeS, hist, S);
 }
 
@@ -647,7 +652,6 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     const int rho0 = (seg == 0) ? -VP_VC : kS - 3;  // a position is covered by 4 frames; 4 carry rows when offV > 0
     const VPRow y = vp_row(synth, g.histS, s, g);
     float* o = outV + (size_t)s * g.vstride;
-    const double gv = (double)g.gainVocF;
     double a[P + 1], as[PS + 1], st[P + 1], t[PS + 1];
 #pragma unroll
     for (int j = 0; j <= P; ++j) { a[j] = 0.0; st[j] = 0.0; }
@@ -770,7 +774,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
                     const double ov = e[j] + st[0];
 #pragma unroll
                     for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
-                    c[j] = (float)(gv * ov * wr[i0 + j]);  // window re-read from shared memory: cheaper than 8 live registers
+                    c[j] = (float)(ov * wr[i0 + j]);  // window re-read from shared memory: cheaper than 8 live registers
                 } else c[j] = 0.0f;
             }
             // ---- overlap-add of the 4 phase lanes for the 4 positions of block b-1: transpose-reduce, 3 shuffles;
@@ -846,7 +850,6 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
     const double* sp = aS + fidx * (size_t)(PS + 1);
     double h[VP_ORDER_MAX];
     for (int j = 0; j < P; ++j) h[j] = 0.0;
-    const double gv = (double)g.gainVocF;
     for (int i = 0; i < wlen; ++i) {
         const double w = tb.wV[i];
         double o = 0.0;
@@ -857,7 +860,7 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
             o = gain * e;
             for (int kk = 1; kk <= P && kk <= i; ++kk) o = fma(-ap[kk], h[(i - kk) % P], o);
             h[i % P] = o;
-            obuf[vs_idx(lane, i, hop, sk)] += (float)(gv * o * w);
+            obuf[vs_idx(lane, i, hop, sk)] += (float)(o * w);
         }
         if ((i & 31) == 31) __syncwarp();
     }
