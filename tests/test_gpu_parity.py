@@ -370,8 +370,18 @@ def test_errors_are_codes(vp):
         with pytest.raises(vp.EngineError) as ei:
             eng.set_params(vp.default_params(lpcVoice=101))
         assert ei.value.code == vp.VP_E_RANGE
+        z4 = z[:, :4 * 1024]
+        eng.process(z4, z4, z4)
         with pytest.raises(vp.EngineError) as ei:
-            eng.set_params(vp.default_params(lpcPitch=16))  # read in prepare only (PitchProcess.cpp:70)
+            eng.set_params(vp.default_params(lpcPitch=16))  # read in prepare only (PitchProcess.cpp:70): not mid-stream
         assert ei.value.code == vp.VP_E_STATE
+        # on a reset engine it is accepted, but the workspace has to be sized again before the next block
+        eng.reset()
+        eng.set_params(vp.default_params(lpcPitch=16))
+        with pytest.raises(vp.EngineError) as ei:
+            eng.process(z4, z4, z4)
+        assert ei.value.code == vp.VP_E_STATE
+        eng._check(eng.lib.vp_engine_prepare(eng.h, 44100.0, 1024, 2, 4, 0))
+        eng.process(z4, z4, z4)
     finally:
         eng.close()

@@ -331,8 +331,12 @@ extern "C" int vp_engine_set_params(vp_engine* e, const vp_params* p) {
     if (rc) return vp_err(e, rc, "parameter outside the plug-in's range");
     const bool keyChanged = p->keyPitch != e->prm.keyPitch;
     // LPC orders size the workspace; lpcPitch is read in prepare only in the reference too (PitchProcess.cpp:70)
-    if (e->prepared && (p->lpcVoice > e->capV || p->lpcSynth > e->capS || p->lpcPitch != e->capP))
-        return vp_err(e, VP_E_STATE, "LPC order beyond what vp_engine_prepare sized (lpcPitch is fixed at prepare): set params before prepare");
+    if (e->prepared && (p->lpcVoice > e->capV || p->lpcSynth > e->capS || p->lpcPitch != e->capP)) {
+        if (e->blocksDone > 0)
+            return vp_err(e, VP_E_STATE, "LPC order beyond what vp_engine_prepare sized (lpcPitch is fixed at prepare): "
+                                         "vp_engine_reset, set the parameters, then vp_engine_prepare again");
+        e->prepared = false;  // freshly prepared / reset engine: accepted, the workspace must be sized again (vp_engine_prepare)
+    }
     // Mid-stream automation (between two process calls of a running stream) is exact for the gains and the key: every
     // one of those is read per block / per frame / per chunk in the reference (PluginProcessor.cpp:226-230,
     // VocoderProcess.cpp:291, PitchProcess.cpp:206,336) and the engine keeps per-frame copies where a frame outlives

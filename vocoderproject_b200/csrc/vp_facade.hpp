@@ -111,6 +111,9 @@ public:
         beginBlock();
     }
     void setParams(const vp_params& p) { params = p; engine.check(vp_engine_set_params(engine.h, &params)); }
+    // prepareToPlay on a running instance: back to the freshly prepared state first, so that parameters which re-lay the
+    // carried state (LPC orders, enables) are accepted again
+    void restart() { if (B > 0) engine.check(vp_engine_reset(engine.h)); }
     const vp_params& getParams() const { return params; }
 
     // fillInputBuffers(voiceBuffer, synthBuffer): host rows [S][stride]; synth channel 1 may be null when gainSynth is off
@@ -203,6 +206,7 @@ public:
         const int c256 = (int)std::floor(256.0 * ratioSR);                 // :168
         const int hopPitch = 3 * c256, frameLenPitch = 4 * c256;           // :169-170
         const double silenceDb = -60.0;                                    // :148
+        myBuffer.restart();
         myBuffer.setParams(params);
         pitchProcess.prepare(sampleRate, 100.0, 800.0, frameLenPitch, hopPitch, samplesPerBlock, silenceDb);   // :172
         vocoderProcess.prepare(wlenVoc, hopVoc, "sine", silenceDb);                                             // :173
