@@ -145,6 +145,7 @@ def test_engine_known_answer_table(vp, which):
     (44100.0, 1000, 2, 2.0, 0, dict(keyPitch=9)),             # ragged block
     (44100.0, 4096, 2, 3.0, 0, dict()),                       # block larger than every frame
     (88200.0, 1024, 1, 1.5, 0, dict()),                       # double sample rate: all sizes x2
+    (96000.0, 1024, 1, 1.2, 0, dict(keyPitch=3)),             # 96 kHz: tauMax 960 -> generic YIN decision kernel
 ])
 def test_engine_matches_oracle(vp, oracle, fs, B, S, secs, flavour, params):
     n = int(fs * secs) // B * B

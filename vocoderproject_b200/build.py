@@ -59,6 +59,21 @@ def build_host(force=False):
     return HOST
 
 
+WAVBATCH = os.path.join(LIBDIR, "vp_wavbatch")
+
+
+def build_wavbatch(force=False):
+    """WAV front-end of the batch engine (csrc/vp_wavbatch.cpp: vp_wav.hpp + vp_facade.hpp over the C ABI)."""
+    src = [os.path.join(CSRC, f) for f in ("vp_wavbatch.cpp", "vp_wav.hpp", "vp_facade.hpp")] + [LIB]
+    if not force and os.path.exists(WAVBATCH) and all(os.path.getmtime(f) <= os.path.getmtime(WAVBATCH) for f in src):
+        return WAVBATCH
+    cxx = shutil.which("g++") or "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", WAVBATCH, os.path.join(CSRC, "vp_wavbatch.cpp"), "-L" + LIBDIR,
+                           "-lvp_engine", "-Wl,-rpath,$ORIGIN"], cwd=CSRC)
+    return WAVBATCH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
+    print(build_wavbatch(force="--force" in sys.argv))
