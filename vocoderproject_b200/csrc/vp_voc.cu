@@ -92,17 +92,29 @@ __device__ __forceinline__ void ac_task(const double* __restrict__ xw, int n0, i
     double W[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) { acc[j] = 0.0; W[j] = xw[n0 + m0 + j]; }
-    const int nEnd = n0 + segLen;
-    for (int nb = n0; nb < nEnd; nb += R) {
+    // full rounds of R samples: no bounds predicate, every shared-memory access is base + immediate
+    const double* p = xw + n0;            // a = x[n]
+    const double* pw = p + m0 + R - 1;    // newest window element x[n + m0 + R - 1]
+    const int full = segLen / R;
+    for (int r = 0; r < full; ++r, p += R, pw += R) {
 #pragma unroll
         for (int u = 0; u < R; ++u) {
-            const int n = nb + u;
-            if (u > 0) W[(u + R - 1) % R] = xw[n + m0 + R - 1];
-            const double a = (n < nEnd) ? xw[n] : 0.0;
+            if (u > 0) W[(u + R - 1) % R] = pw[u];
+            const double a = p[u];
 #pragma unroll
             for (int j = 0; j < R; ++j) acc[j] = fma(a, W[(u + j) % R], acc[j]);
         }
-        W[(R - 1) % R] = xw[nb + R + m0 + R - 1];  // element for u = 0 of the next round
+        W[(R - 1) % R] = pw[R];  // element for u = 0 of the next round
+    }
+    const int rem = segLen - full * R;
+    if (rem > 0) {  // last, partial round (the window reads beyond it stay inside the zero padding)
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            if (u > 0) W[(u + R - 1) % R] = pw[u];
+            const double a = (u < rem) ? p[u] : 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = fma(a, W[(u + j) % R], acc[j]);
+        }
     }
 }
 
@@ -256,12 +268,25 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
         }
         __syncwarp();
         // ---- windowed FP64 copies from the ring
-        for (int j = lane; j < wlen; j += 32) {
-            int idx = r0 + j;
-            if (idx >= wlen) idx -= wlen;
-            const double w = wv[j];
-            xw[j] = (double)ringV[idx] * w;
-            sw[j] = (double)ringS[idx] * w;
+        {   // two spans, each linear in the ring (no wrap test per element): j in [0, wlen - r0) and [wlen - r0, wlen)
+            const int split = wlen - r0;
+            const float* rv = ringV + r0;
+            const float* rs = ringS + r0;
+#pragma unroll 3
+            for (int j = lane; j < split; j += 32) {
+                const double w = wv[j];
+                xw[j] = (double)rv[j] * w;
+                sw[j] = (double)rs[j] * w;
+            }
+            rv = ringV - split;
+            rs = ringS - split;
+            const int jb = split + ((lane - split) & 31);  // first j >= split with j = lane (mod 32)
+#pragma unroll 3
+            for (int j = jb; j < wlen; j += 32) {
+                const double w = wv[j];
+                xw[j] = (double)rv[j] * w;
+                sw[j] = (double)rs[j] * w;
+            }
         }
         __syncwarp();
         double acc[AC_R];
