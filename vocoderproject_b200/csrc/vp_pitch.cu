@@ -1028,6 +1028,7 @@ __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch
 
 #define PF_THREADS 128
 #define PF_RJ 11  // residual outputs per thread and pass (odd stride: conflict-free window loads)
+#define PF_XPAD 32  // zero floats after the staged frame / spare doubles after the residual (>= 2 PF_RJ)
 
 // P > 0: LPC order known at compile time (coefficients and the residual window live in registers); P == 0: any order.
 template <int P>
@@ -1044,7 +1045,7 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
     double* e = smd;                    // [eLen] residual, e[j] <-> frame-relative idx j - tauMax
-    double* hs = e + eLen;              // [2 tauMax + 2] Hann table of this frame's period (PitchProcess.cpp:878-882)
+    double* hs = e + eLen + PF_XPAD;    // [2 tauMax + 2] Hann table of this frame's period (PitchProcess.cpp:878-882)
     float* xf = (float*)(hs + 2 * tauMax + 2);  // [xLen] floats; dead after the residual -> reused as oE [L] doubles
     double* oE = (double*)xf;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
@@ -1052,11 +1053,22 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
     const long long p = (long long)f * g.hopP + g.offP;
     const int tid = threadIdx.x;
 
-    vp_stage<8>(xf, v, p - X0, xLen, g, tid, PF_THREADS);
+    {   // frame samples global -> shared without a register round trip (zero-filled outside history / input, and in the
+        // PF_XPAD floats of padding the residual loop may read)
+        const long long t0 = p - X0 - g.lat;
+        for (int j = tid; j < xLen + PF_XPAD; j += PF_THREADS) {
+            const long long t = t0 + j;
+            const bool ok = j < xLen && t >= -(long long)g.H && t < g.n;
+            const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);
+            __pipeline_memcpy_async(xf + j, src, 4, ok ? 0 : 4);
+        }
+        __pipeline_commit();
+    }
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
     __shared__ int sELo, sEHi;
     if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; }
     const double* ap = aP + fidx * (size_t)(ord + 1);
+    __pipeline_wait_prior(0);
     __syncthreads();
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
     if (T > 0 && T < tauMax) {
@@ -1129,17 +1141,25 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
         double ar[PP + 1];
 #pragma unroll
         for (int k = 0; k <= PP; ++k) ar[k] = ap[k];
+        // Scatter form: every input sample is loaded and converted once and feeds the (up to PP + 1) outputs of this
+        // thread it belongs to -- PF_RJ accumulators instead of a PF_RJ + PP window in registers, no bounds predicates
+        // (xf and e are padded). Inputs run newest to oldest so that each output still sums its taps k = 0 .. PP in order.
         for (int j0 = eLo + tid * PF_RJ; j0 < eHi; j0 += PF_THREADS * PF_RJ) {
-            double w[PF_RJ + PP];
+            double acc[PF_RJ];
 #pragma unroll
-            for (int q = 0; q < PF_RJ + PP; ++q) w[q] = (j0 + q < xLen) ? (double)xf[j0 + q] : 0.0;  // x at e-index j0 + q - PP
+            for (int jj = 0; jj < PF_RJ; ++jj) acc[jj] = 0.0;
+            const float* xq = xf + j0;  // xq[q] = x at e-index j0 + q - PP
 #pragma unroll
-            for (int jj = 0; jj < PF_RJ; ++jj) {
-                double acc = 0.0;
+            for (int q = PF_RJ + PP - 1; q >= 0; --q) {
+                const double x = (double)xq[q];
 #pragma unroll
-                for (int k = 0; k <= PP; ++k) acc = fma(ar[k], w[jj + PP - k], acc);
-                if (j0 + jj < eHi) e[j0 + jj] = acc;
+                for (int jj = 0; jj < PF_RJ; ++jj) {
+                    const int k = jj + PP - q;
+                    if (k >= 0 && k <= PP) acc[jj] = fma(ar[k], x, acc[jj]);
+                }
             }
+#pragma unroll
+            for (int jj = 0; jj < PF_RJ; ++jj) e[j0 + jj] = acc[jj];
         }
     } else {
         for (int j = eLo + tid; j < eHi; j += PF_THREADS) {
@@ -1212,7 +1232,7 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     int xLen = g.tauMax + g.ordP + g.L + 3 * g.c;  // frame-relative [-tauMax - ord, L + 3c)
     xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
     xLen = (xLen + 3) & ~3;
-    const size_t smem = (size_t)(eLen + 2 * g.tauMax + 2) * sizeof(double) + (size_t)xLen * sizeof(float);
+    const size_t smem = (size_t)(eLen + PF_XPAD + 2 * g.tauMax + 2) * sizeof(double) + (size_t)(xLen + PF_XPAD) * sizeof(float);
     dim3 grid(g.nFramesP + VP_PC, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
