@@ -1044,37 +1044,46 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
     if (!pf_live(g, rec, f)) return;
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
-    double* e = smd;                    // [eLen] residual, e[j] <-> frame-relative idx j - tauMax
-    double* hs = e + eLen + PF_XPAD;    // [2 tauMax + 2] Hann table of this frame's period (PitchProcess.cpp:878-882)
-    float* xf = (float*)(hs + 2 * tauMax + 2);  // [xLen] floats; dead after the residual -> reused as oE [L] doubles
-    double* oE = (double*)xf;
+    double* e = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smd) + 15) & ~(uintptr_t)15);  // [eLen + pad] residual, e[j] <-> frame-relative idx j - tauMax
+    double* hs = e + ((eLen + PF_XPAD + 1) & ~1);  // [2 tauMax + 2] Hann table of this frame's period (PitchProcess.cpp:878-882)
+    float* xfBase = (float*)(hs + 2 * tauMax + 2);  // 16-byte aligned; [xLen + pad] floats; dead after the residual -> oE [L] doubles
+    double* oE = (double*)xfBase;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
     const VPRow v = vp_row(voice, g.histV, s, g);
     const long long p = (long long)f * g.hopP + g.offP;
     const int tid = threadIdx.x;
 
-    {   // frame samples global -> shared without a register round trip (zero-filled outside history / input, and in the
-        // PF_XPAD floats of padding the residual loop may read)
-        const long long t0 = p - X0 - g.lat;
-        for (int j = tid; j < xLen + PF_XPAD; j += PF_THREADS) {
+    // ---- frame samples global -> shared without a register round trip. Common case (the whole span lies inside this
+    // call's input): 16-byte copies from the 16-byte aligned address at or below the first sample, the frame then starts
+    // m floats into the buffer. Otherwise (history before the call / end of the input): 4-byte copies with zero fill.
+    const long long t0 = p - X0 - g.lat;
+    int m = (int)((reinterpret_cast<uintptr_t>(v.x + t0) >> 2) & 3);
+    if (t0 - m >= 0 && t0 + xLen + 4 <= g.n) {
+        const float4* s4 = reinterpret_cast<const float4*>(v.x + t0 - m);
+        float4* d4 = reinterpret_cast<float4*>(xfBase);
+        const int n4 = (m + xLen + 3) >> 2;
+        for (int j = tid; j < n4; j += PF_THREADS) __pipeline_memcpy_async(d4 + j, s4 + j, 16);
+    } else {
+        m = 0;
+        for (int j = tid; j < xLen; j += PF_THREADS) {
             const long long t = t0 + j;
-            const bool ok = j < xLen && t >= -(long long)g.H && t < g.n;
+            const bool ok = t >= -(long long)g.H && t < g.n;
             const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);
-            __pipeline_memcpy_async(xf + j, src, 4, ok ? 0 : 4);
+            __pipeline_memcpy_async(xfBase + j, src, 4, ok ? 0 : 4);
         }
-        __pipeline_commit();
     }
+    const float* xf = xfBase + m;  // the PF_XPAD floats after xf[xLen - 1] only feed residual samples nobody reads
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
     __shared__ int sELo, sEHi;
     if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; }
     const double* ap = aP + fidx * (size_t)(ord + 1);
-    __pipeline_wait_prior(0);
-    __syncthreads();
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
     if (T > 0 && T < tauMax) {
         const double* __restrict__ hg = tb.hann + tb.hannOff[T];
-        for (int i = tid; i < 2 * T + 1; i += PF_THREADS) hs[i] = __ldg(hg + i);
+        for (int i = tid; i < 2 * T + 1; i += PF_THREADS) __pipeline_memcpy_async(hs + i, hg + i, 8);
     }
+    __pipeline_commit();
+    __syncthreads();  // marks visible; the staging copies are still in flight under the grain table
     // ---- PSOLA (PitchProcess.cpp:665-741, :788-870). Grain table first: thread m prepares synthesis mark m -- the
     // chunk n at which the reference handles it (the first n with stMark - T < (n + 1) c), the look-ahead and residual
     // extent visible at that chunk, the closest complete analysis mark, the output range -- so that the element loop
@@ -1132,6 +1141,7 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
         }
         gFl[tid] = fl;
     }
+    __pipeline_wait_prior(0);
     __syncthreads();
     // ---- residual e[j] = sum_k a[k] x[j - tauMax - k] (PitchProcess.cpp:280-302). The reference filters frame-relative
     // [-samplesToKeep, L + 3c); only the part the grains read is computed: [eLo, eHi) from the grain table.
@@ -1232,7 +1242,7 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     int xLen = g.tauMax + g.ordP + g.L + 3 * g.c;  // frame-relative [-tauMax - ord, L + 3c)
     xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
     xLen = (xLen + 3) & ~3;
-    const size_t smem = (size_t)(eLen + PF_XPAD + 2 * g.tauMax + 2) * sizeof(double) + (size_t)(xLen + PF_XPAD) * sizeof(float);
+    const size_t smem = (size_t)(((eLen + PF_XPAD + 1) & ~1) + 2 * g.tauMax + 2) * sizeof(double) + (size_t)(xLen + PF_XPAD + 4) * sizeof(float) + 16;
     dim3 grid(g.nFramesP + VP_PC, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
