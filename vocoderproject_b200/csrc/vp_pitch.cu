@@ -1089,7 +1089,6 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
     // extent visible at that chunk, the closest complete analysis mark, the output range -- so that the element loop
     // below carries no per-grain scalar work.
     __shared__ int gSt[VP_MAX_MARKS], gCl[VP_MAX_MARKS], gI0[VP_MAX_MARKS], gI1[VP_MAX_MARKS], gEv[VP_MAX_MARKS], gFl[VP_MAX_MARKS];
-    __shared__ double gX0[VP_MAX_MARKS], gX1[VP_MAX_MARKS];
     const double beta = rec->beta;
     const bool okT = T > 0 && T < tauMax;
     if (tid < VP_MAX_MARKS) {
@@ -1129,11 +1128,12 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
                 if (x0 >= 0.0 && x0 == floor(x0)) fl |= 8;  // U5
                 gSt[tid] = stMark;
                 gCl[tid] = clAn;
-                gI0[tid] = max(max((int)floor(x0), 0), nc);  // i < nc: chunk already filtered (App. A.4 #6)
+                // output indices i with x0 <= i <= xEnd (interp(), PitchProcess.cpp:850-852), i >= nc (chunk already
+                // filtered, App. A.4 #6), i < L: as integer bounds -- i >= x0 <=> i >= ceil(x0), and i < ceil(xEnd)
+                // already implies i <= xEnd -- so that the element loop compares integers only
+                gI0[tid] = max(max((int)ceil(x0), 0), nc);
                 gI1[tid] = min((int)ceil(xEnd), L);
                 gEv[tid] = L + nc;                            // residual filtered so far
-                gX0[tid] = x0;
-                gX1[tid] = xEnd;
                 atomicMin(&sELo, max(clAn - T + tauMax - 1, 0));          // grain samples j = 0 .. 2T (and j - 1)
                 atomicMax(&sEHi, min(clAn + T + tauMax + 1, eLen));
                 fl |= 1 | (tid == 0 ? 2 : 0) | (tid == nSt - 1 ? 4 : 0);
@@ -1188,14 +1188,14 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
             if (!(fl & 1)) continue;
             const bool first = (fl & 2) != 0, last = (fl & 4) != 0, inner = !first && !last;
             const int clAn = gCl[m], eValid = gEv[m], startIdx = gI0[m], stopIdx = gI1[m];
-            const double dSt = (double)gSt[m], x0 = gX0[m], xEnd = gX1[m];
+            const double dSt = (double)gSt[m];
             const int eBase = clAn - T + tauMax;  // e index of grain sample j = 0
             const int jLim = min(eLen - eBase, eValid - (clAn - T));  // grain samples j < jLim exist in the residual so far
             // thread <-> output index i is fixed (i mod PF_THREADS) so that successive grains
             // accumulate into oE[i] in mark order without synchronisation
             for (int i = (startIdx / PF_THREADS) * PF_THREADS + tid; i < stopIdx; i += PF_THREADS) {
+                if (i < startIdx) continue;
                 const double di = (double)i;
-                if (i < startIdx || !(di >= x0 && di <= xEnd)) continue;
                 // interp() (PitchProcess.cpp:842-870): lower_bound j over x[j] = stMark + (j - T) / beta, then linear
                 // interpolation between grain samples j-1 and j. In grain coordinates tg = T + (i - stMark) beta the
                 // bound is j = ceil(tg) and the weight (i - x[j-1]) / (x[j] - x[j-1]) = tg - (j - 1). The interpolant

@@ -24,12 +24,25 @@ __global__ void __launch_bounds__(128) k_gate_partial(VPGeom g, const float* __r
     const float* y = synth + (size_t)s * g.stride + (size_t)b * g.B;
     double sv = 0.0, ss = 0.0, tv = 0.0, ts = 0.0;
     const int tail0 = g.B - rem;
-    for (int t = threadIdx.x; t < g.B; t += blockDim.x) {
-        const double a = (double)__ldg(v + t), c = (double)__ldg(y + t);
-        const double a2 = a * a, c2 = c * c;
-        sv += a2;
-        ss += c2;
-        if (t >= tail0) { tv += a2; ts += c2; }
+    // 2 x 8 independent loads in flight per thread before the first use (a block of 1024 samples = one batch)
+    constexpr int GU = 8;
+    for (int t0 = threadIdx.x; t0 < g.B; t0 += blockDim.x * GU) {
+        float av[GU], cv[GU];
+#pragma unroll
+        for (int k = 0; k < GU; ++k) {
+            const int t = t0 + k * (int)blockDim.x;
+            av[k] = (t < g.B) ? __ldg(v + t) : 0.0f;
+            cv[k] = (t < g.B) ? __ldg(y + t) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < GU; ++k) {
+            const int t = t0 + k * (int)blockDim.x;
+            const double a = (double)av[k], c = (double)cv[k];
+            const double a2 = a * a, c2 = c * c;
+            sv += a2;   // zeros beyond the block add nothing: same sums, same order
+            ss += c2;
+            if (t >= tail0) { tv += a2; ts += c2; }
+        }
     }
     sv = vp_warp_sum(sv); ss = vp_warp_sum(ss); tv = vp_warp_sum(tv); ts = vp_warp_sum(ts);
     __shared__ double red[4][4];
