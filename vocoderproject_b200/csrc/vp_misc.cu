@@ -15,28 +15,43 @@ __global__ void __launch_bounds__(256) k_mix(VPGeom g, const float* __restrict__
                                              float* __restrict__ outR) {
     const int s = blockIdx.y;
     const size_t row = (size_t)s * g.stride, wrow = (size_t)s * g.wstride;
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < g.n; u += (long long)gridDim.x * blockDim.x) {
-        float l = 0.0f;
-        if (g.vocOn) l += outV[wrow + u];
-        if (g.pitchOn) l += outP[wrow + u];
-        float r = l;
-        if (g.dryOn) {
-            const float d = g.gainVoiceF * vp_x(vp_row(voice, g.histV, s, g), u, g);
-            l += d; r += d;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    constexpr int MU = 4;  // independent loads in flight per thread and plane
+    for (long long u0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; u0 < g.n; u0 += step * MU) {
+        float a[MU], b[MU];
+#pragma unroll
+        for (int k = 0; k < MU; ++k) {
+            const long long u = u0 + k * step;
+            a[k] = (g.vocOn && u < g.n) ? __ldg(outV + wrow + u) : 0.0f;
+            b[k] = (g.pitchOn && u < g.n) ? __ldg(outP + wrow + u) : 0.0f;
         }
-        if (g.synthOn) {
-            l += g.gainSynthF * vp_x(vp_row(synthL, g.histS, s, g), u, g);
-            r += g.gainSynthF * (synthR ? vp_x(vp_row(synthR, g.histR, s, g), u, g) : vp_x(vp_row(synthL, g.histS, s, g), u, g));
+#pragma unroll
+        for (int k = 0; k < MU; ++k) {
+            const long long u = u0 + k * step;
+            if (u >= g.n) break;
+            float l = 0.0f;
+            if (g.vocOn) l += a[k];
+            if (g.pitchOn) l += b[k];
+            float r = l;
+            if (g.dryOn) {
+                const float d = g.gainVoiceF * vp_x(vp_row(voice, g.histV, s, g), u, g);
+                l += d; r += d;
+            }
+            if (g.synthOn) {
+                l += g.gainSynthF * vp_x(vp_row(synthL, g.histS, s, g), u, g);
+                r += g.gainSynthF * (synthR ? vp_x(vp_row(synthR, g.histR, s, g), u, g) : vp_x(vp_row(synthL, g.histS, s, g), u, g));
+            }
+            outL[row + u] = l;
+            if (outR) outR[row + u] = r;
         }
-        outL[row + u] = l;
-        if (outR) outR[row + u] = r;
     }
 }
 
 void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
                    const float* synthR, const float* outV, const float* outP, float* outL, float* outR) {
-    long long bx = (g.n + 255) / 256;
+    long long bx = (g.n + 4 * 256 - 1) / (4 * 256);
     if (bx > 4096) bx = 4096;
+    if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, S);
     k_mix<<<grid, 256, 0, st>>>(g, voice, synthL, synthR, outV, outP, outL, outR);
 }

@@ -1296,6 +1296,10 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
     }
     // per-lane metadata shared through shuffles for the cooperative slab moves
     const long long myP = (long long)f * g.hopP + g.offP;
+    // frame-relative output range that lands inside this call: positions before 0 went out with an earlier call, beyond
+    // n go out with a later one; and the frame's base offset in the output plane
+    const int myLo = (int)max(0LL, -myP), myHi = (int)min((long long)nSteps, (long long)g.n - myP);
+    const long long myBase = (long long)s * (long long)g.pstride + myP;
     const double gp = (double)g.gainPitchF;
     const int nSlabs = (L + 31) / 32;
     int maxSteps = nSteps;
@@ -1333,18 +1337,14 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
         }
         __syncwarp();
         for (int fr = 0; fr < 32; ++fr) {
-            const int steps = __shfl_sync(0xffffffffu, nSteps, fr);
-            const long long pf = __shfl_sync(0xffffffffu, myP, fr);
-            const int sf = __shfl_sync(0xffffffffu, s, fr);
+            const int lo = __shfl_sync(0xffffffffu, myLo, fr), hi = __shfl_sync(0xffffffffu, myHi, fr);
+            const long long ob = __shfl_sync(0xffffffffu, myBase, fr);
             const int i = i0 + lane;
-            if (i < steps) {
-                const long long u = pf + i;
-                if (u >= 0 && u < g.n) {  // positions before 0 went out with an earlier call, beyond n go out with a later one
-                    float* o = outP + (size_t)sf * g.pstride + u;
-                    const float val = tout[warp][fr][lane];
-                    if (i < c || i >= 3 * c) atomicAdd(o, val);   // cross-fade chunks: two frames contribute
-                    else *o = val;
-                }
+            if (i >= lo && i < hi) {
+                float* o = outP + ob + i;
+                const float val = tout[warp][fr][lane];
+                if (i < c || i >= 3 * c) atomicAdd(o, val);   // cross-fade chunks: two frames contribute
+                else *o = val;
             }
         }
         __syncwarp();
