@@ -513,8 +513,11 @@ __global__ void __launch_bounds__(LV_THREADS) k_voc_levinson_static(VPGeom g, VP
     const int nF = (int)((tot - f0 < LV_THREADS) ? tot - f0 : LV_THREADS);
     const int wlen = g.wlenV;
     // ---- coalesced staging (rows of consecutive frames are contiguous in global memory)
-    for (int i = tid; i < nF * RV; i += LV_THREADS) sR[(i / RV) * RS + (i % RV)] = rV[f0 * RV + i];
-    for (int i = tid; i < nF * RSY; i += LV_THREADS) sR[(i / RSY) * RS + RV + (i % RSY)] = rS[f0 * RSY + i];
+    // asynchronous 8-byte copies: all of a thread's ~90 elements are in flight at once, no register round trip
+    for (int i = tid; i < nF * RV; i += LV_THREADS) __pipeline_memcpy_async(sR + (i / RV) * RS + (i % RV), rV + f0 * RV + i, 8);
+    for (int i = tid; i < nF * RSY; i += LV_THREADS) __pipeline_memcpy_async(sR + (i / RSY) * RS + RV + (i % RSY), rS + f0 * RSY + i, 8);
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncthreads();
     if (tid < nF) {
         const long long idx = f0 + tid;
