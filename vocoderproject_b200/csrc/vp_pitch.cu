@@ -1269,7 +1269,7 @@ template <int P>
 __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables tb, const vp_pitch_frame* __restrict__ frames,
                                                              const double* __restrict__ aP, const float* __restrict__ outE,
                                                              float* __restrict__ outP, long long nFramesTot) {
-    __shared__ float tin[PI_WARPS][32][33];
+    __shared__ float tin[PI_WARPS][2][32][33];
     __shared__ float tout[PI_WARPS][32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long f0 = ((long long)blockIdx.x * PI_WARPS + warp) * 32;
@@ -1305,24 +1305,28 @@ __global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables 
     int maxSteps = nSteps;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xffffffffu, maxSteps, o));
-    for (int sl = 0; sl < nSlabs; ++sl) {
+    // slab sl: row fr of the tile <- outE[frame f0+fr][32 sl .. 32 sl + 32), as asynchronous 4-byte copies (zero fill
+    // beyond the frame's steps) into one of two tiles: the next slab is in flight while this one is filtered
+    auto issue = [&](int sl, int buf) {
         const int i0 = sl * 32;
-        if (i0 >= maxSteps) break;
-        // load: row fr of the tile <- outE[frame f0+fr][i0 .. i0+32)
-        for (int fr0 = 0; fr0 < 32; fr0 += 8) {  // 8 independent loads in flight per lane
-            float val[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int steps = __shfl_sync(0xffffffffu, nSteps, fr0 + q);
-                val[q] = (i0 + lane < steps) ? __ldg(outE + (size_t)(f0 + fr0 + q) * L + i0 + lane) : 0.0f;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) tin[warp][fr0 + q][lane] = val[q];
+#pragma unroll 8
+        for (int fr = 0; fr < 32; ++fr) {
+            const int steps = __shfl_sync(0xffffffffu, nSteps, fr);
+            const bool ok = i0 + lane < steps;
+            __pipeline_memcpy_async(&tin[warp][buf][fr][lane], outE + (ok ? (size_t)(f0 + fr) * L + i0 + lane : 0), 4, ok ? 0 : 4);
         }
+        __pipeline_commit();
+    };
+    if (maxSteps > 0) issue(0, 0);
+    for (int sl = 0; sl < nSlabs; ++sl) {
+        const int i0 = sl * 32, buf = sl & 1;
+        if (i0 >= maxSteps) break;
+        if (sl + 1 < nSlabs && i0 + 32 < maxSteps) { issue(sl + 1, buf ^ 1); __pipeline_wait_prior(1); }
+        else __pipeline_wait_prior(0);
         __syncwarp();
         for (int j = 0; j < 32; ++j) {
             const int i = i0 + j;
-            double acc = (double)tin[warp][lane][j];
+            double acc = (double)tin[warp][buf][lane][j];
             if (P > 0) {
                 // transposed direct form II: y = x + s_1; s_k <- s_{k+1} - a[k] y  (independent DFMAs, no history shift)
                 acc += h[0];
