@@ -923,24 +923,55 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
     double* xd = smd + (size_t)warp * xdLen;  // frame samples as double, zero beyond L (rectangular window, LPC.cpp:44-97)
     const VPRow v = vp_row(voice, g.histV, s, g);
     const long long p = (long long)f * g.hopP + g.offP;
-    vp_stage<8>(xd, v, p, L, g, lane, 32);
-    for (int j = L + lane; j < xdLen; j += 32) xd[j] = 0.0;
+    {   // frame samples: asynchronous 4-byte copies into the warp's float buffer (all in flight at once, zero fill outside
+        // the carried history / this call's input), then one conversion pass to double
+        float* xf = reinterpret_cast<float*>(smd + (size_t)PA_WARPS * xdLen) + (size_t)warp * xdLen;
+        const long long t0 = p - g.lat;
+        if (t0 >= 0 && t0 + L <= g.n) {
+            const float* src = v.x + t0;
+            for (int j = lane; j < L; j += 32) __pipeline_memcpy_async(xf + j, src + j, 4);
+        } else {
+            for (int j = lane; j < L; j += 32) {
+                const long long t = t0 + j;
+                const bool ok = t >= -(long long)g.H && t < g.n;
+                const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);
+                __pipeline_memcpy_async(xf + j, src, 4, ok ? 0 : 4);
+            }
+        }
+        __pipeline_commit();
+        for (int j = L + lane; j < xdLen; j += 32) xd[j] = 0.0;
+        __pipeline_wait_prior(0);
+        __syncwarp();
+#pragma unroll 4
+        for (int j = lane; j < L; j += 32) xd[j] = (double)xf[j];
+    }
     __syncwarp();
     const int seg = lane & (PA_SEGS - 1), half = lane >> 4;
-    const int n0 = seg * segLen, nEnd = n0 + segLen;
+    const int n0 = seg * segLen;
+    const int full = segLen / PA_R, rem = segLen - full * PA_R;
     double* r = rP + (size_t)fidx * (size_t)(ord + 1);
     for (int m0 = half * PA_R; m0 <= ord; m0 += 2 * PA_R) {
         double acc[PA_R], W[PA_R];
 #pragma unroll
         for (int j = 0; j < PA_R; ++j) { acc[j] = 0.0; W[j] = xd[n0 + m0 + j]; }
-        for (int nb = n0; nb < nEnd; nb += PA_R) {
+        const double* pa = xd + n0;              // a = x[n]
+        const double* pw = pa + m0 + PA_R;       // window element entering at step u: x[n + m0 + R]
+        for (int rr = 0; rr < full; ++rr, pa += PA_R, pw += PA_R) {  // full rounds: no bounds predicate
 #pragma unroll
             for (int u = 0; u < PA_R; ++u) {
-                const int n = nb + u;
-                const double a = (n < nEnd) ? xd[n] : 0.0;
+                const double a = pa[u];
 #pragma unroll
                 for (int j = 0; j < PA_R; ++j) acc[j] = fma(a, W[(u + j) % PA_R], acc[j]);
-                W[u % PA_R] = xd[n + m0 + PA_R];
+                W[u % PA_R] = pw[u];
+            }
+        }
+        if (rem > 0) {
+#pragma unroll
+            for (int u = 0; u < PA_R; ++u) {
+                const double a = (u < rem) ? pa[u] : 0.0;
+#pragma unroll
+                for (int j = 0; j < PA_R; ++j) acc[j] = fma(a, W[(u + j) % PA_R], acc[j]);
+                W[u % PA_R] = pw[u];
             }
         }
 #pragma unroll
@@ -1229,7 +1260,7 @@ void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* v
     if ((segLen & 1) == 0) ++segLen;  // odd -> the 16 segments of a half-warp hit 16 distinct 64-bit banks
     const int groups = (g.ordP + 1 + 2 * PA_R - 1) / (2 * PA_R);
     const int xdLen = (PA_SEGS * segLen + 2 * PA_R * groups + 2 * PA_R + 3) & ~1;
-    const size_t smem = (size_t)PA_WARPS * xdLen * sizeof(double);
+    const size_t smem = (size_t)PA_WARPS * xdLen * (sizeof(double) + sizeof(float));  // xd [warps][xdLen] doubles, then the float landing zones
     cudaFuncSetAttribute(k_pitch_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     k_pitch_autocorr<<<(unsigned)((tot + PA_WARPS - 1) / PA_WARPS), 32 * PA_WARPS, smem, st>>>(g, voice, frames, rP, segLen, xdLen, tot);
     if (g.ordP == 15) k_pitch_levinson<15><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot);
