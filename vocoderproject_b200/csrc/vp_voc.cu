@@ -258,27 +258,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
         if (k >= g.nFramesV) break;
         const long long u0 = (long long)k * hop + g.offV;
         const int r0 = (int)(((long long)k * hop) % wlen);
-        // ---- prefetch the hop new samples of frame k+1 (positions u0 + wlen .. u0 + wlen + hop)
-        float nv[AV_NPRE], ns[AV_NPRE];
         const bool more = (fb + 1 < AV_BATCH) && (k + 1 < g.nFramesV);
-        {
-            const long long t0 = u0 + wlen - g.lat;  // input index of the first new sample
-            if (more && t0 >= 0 && t0 + hop <= g.n) {  // common case: entirely inside this call's input
-#pragma unroll
-                for (int q = 0; q < AV_NPRE; ++q) {
-                    const int j = lane + q * 32;
-                    nv[q] = (j < hop) ? __ldg(v.x + t0 + j) : 0.0f;
-                    ns[q] = (j < hop) ? __ldg(y.x + t0 + j) : 0.0f;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < AV_NPRE; ++q) {
-                    const int j = lane + q * 32;
-                    nv[q] = (more && j < hop) ? vp_x(v, u0 + wlen + j, g) : 0.0f;
-                    ns[q] = (more && j < hop) ? vp_x(y, u0 + wlen + j, g) : 0.0f;
-                }
-            }
-        }
         __syncwarp();
         // ---- windowed FP64 copies from the ring
         {   // two spans, each linear in the ring (no wrap test per element): j in [0, wlen - r0) and [wlen - r0, wlen)
@@ -302,6 +282,27 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
             }
         }
         __syncwarp();
+        // ---- the ring's oldest hop entries are dead now: the hop NEW samples of frame k+1 (positions u0 + wlen ..
+        // u0 + wlen + hop) land there as asynchronous copies while this frame is being correlated
+        if (more) {
+            const long long t0 = u0 + wlen - g.lat;  // input index of the first new sample
+            if (t0 >= 0 && t0 + hop <= g.n) {        // common case: entirely inside this call's input
+                for (int j = lane; j < hop; j += 32) {
+                    int idx = r0 + j;
+                    if (idx >= wlen) idx -= wlen;
+                    __pipeline_memcpy_async(ringV + idx, v.x + t0 + j, 4);
+                    __pipeline_memcpy_async(ringS + idx, y.x + t0 + j, 4);
+                }
+            } else {
+                for (int j = lane; j < hop; j += 32) {
+                    int idx = r0 + j;
+                    if (idx >= wlen) idx -= wlen;
+                    ringV[idx] = vp_x(v, u0 + wlen + j, g);
+                    ringS[idx] = vp_x(y, u0 + wlen + j, g);
+                }
+            }
+        }
+        __pipeline_commit();
         double acc[AC_R];
         ac_task<AC_R>(sig, seg * segLen, segLen, m0, acc);
 #pragma unroll
@@ -325,14 +326,8 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
         // the frame's last `order` windowed samples, appended to its row (coalesced)
         for (int t = lane; t < g.ordV; t += 32) rowV[g.ordV + 1 + t] = (wlen - g.ordV + t >= 0) ? xw[wlen - g.ordV + t] : 0.0;
         for (int t = lane; t < g.ordS; t += 32) rowS[g.ordS + 1 + t] = (wlen - g.ordS + t >= 0) ? sw[wlen - g.ordS + t] : 0.0;
-        // ---- retire the oldest hop ring entries: they become the new samples of frame k+1
-        if (more) {
-#pragma unroll
-            for (int q = 0; q < AV_NPRE; ++q) {
-                const int j = lane + q * 32;
-                if (j < hop) { int idx = r0 + j; if (idx >= wlen) idx -= wlen; ringV[idx] = nv[q]; ringS[idx] = ns[q]; }
-            }
-        }
+        __pipeline_wait_prior(0);  // frame k+1's samples are in the ring
+        __syncwarp();
     }
 }
 
