@@ -471,7 +471,34 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     const int kA = lane * PER;
     const long long tq = q - g.lat;                                     // input index of x[q]
     const bool inside = tq >= 0 && tq + L + tauMax <= g.n;              // common case: no history, no end of input
-    const float* P0 = P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad + kA;
+    // A lane owns PER consecutive lags, so direct global reads touch ~15 cache lines per load instruction and the kernel
+    // was bound by L1 wavefronts. The frame's inputs -- 4 chunk rows of P, the tauMax samples entering and leaving the
+    // window -- are copied global -> shared asynchronously with lanes on consecutive addresses instead (16-byte
+    // copies for the aligned P rows), and each lane then reads its own lags from shared memory (stride PER floats, PER
+    // odd: conflict-free).
+    extern __shared__ float ydsm[];
+    float* sb = ydsm + (size_t)warp * 6 * lagPad;  // rows 0..3: P chunks 3f..3f+3; row 4: x[q + L + k]; row 5: x[q + k]
+    {
+        const float4* src = reinterpret_cast<const float4*>(P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad);
+        float4* dst = reinterpret_cast<float4*>(sb);
+        for (int j = lane; j < lagPad; j += 32) __pipeline_memcpy_async(dst + j, src + j, 16);  // 4 rows x lagPad / 4
+        float* sh = sb + 4 * lagPad;
+        float* sl = sb + 5 * lagPad;
+        if (inside) {
+            const float* ph = v.x + tq + L;
+            const float* pl = v.x + tq;
+            for (int k = lane; k < tauMax; k += 32) {
+                __pipeline_memcpy_async(sh + k, ph + k, 4);
+                __pipeline_memcpy_async(sl + k, pl + k, 4);
+            }
+        } else {
+            for (int k = lane; k < tauMax; k += 32) { sh[k] = vp_x(v, q + L + k, g); sl[k] = vp_x(v, q + k, g); }
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncwarp();
+    }
+    const float* P0 = sb + kA;
     double dn[PER], en[PER];
     double locDelta = 0.0;
 #pragma unroll
@@ -479,14 +506,12 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         const int k = kA + j;
         double dl = 0.0;
         if (k < tauMax) {
-            double h, l;
-            if (inside) { h = (double)__ldg(v.x + tq + L + k); l = (double)__ldg(v.x + tq + k); }
-            else { h = (double)vp_x(v, q + L + k, g); l = (double)vp_x(v, q + k, g); }
+            const double h = (double)sb[4 * lagPad + k], l = (double)sb[5 * lagPad + k];
             dl = h * h - l * l;
         }
         en[j] = dl;  // delta for now
         locDelta += dl;
-        dn[j] = ((double)P0[j] + (double)P0[(size_t)lagPad + j]) + ((double)P0[(size_t)2 * lagPad + j] + (double)P0[(size_t)3 * lagPad + j]);
+        dn[j] = ((double)P0[j] + (double)P0[lagPad + j]) + ((double)P0[2 * lagPad + j] + (double)P0[3 * lagPad + j]);
     }
     double inc = locDelta;
 #pragma unroll
@@ -615,7 +640,9 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
     const long long tot = (long long)S * g.nFramesP;
     if (g.tauMax <= 32 * 15) {
-        k_yin_decide_reg<15><<<(unsigned)((tot + 7) / 8), 256, 0, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
+        const size_t smemReg = (size_t)8 * 6 * lagPad * sizeof(float);
+        cudaFuncSetAttribute(k_yin_decide_reg<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        k_yin_decide_reg<15><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
                                                                         recheckList, recheckCount, maxList);
         return;
     }
