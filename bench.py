@@ -331,7 +331,8 @@ def run_engine(args, wl, group):
         # DRAM bytes of that kernel from the committed ncu --set full capture (per sample there), scaled to one launch here
         traffic, traffic_note = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01x.json")) as f:
+            import glob
+            with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))[-1]) as f:  # newest capture
                 tj = json.load(f)
             if kname in tj["stages"] and wl["fs"] == 48000.0 and not wl["params"]:
                 traffic = tj["stages"][kname]["dram_bytes_per_sample"] * samples_rank / kcnt
