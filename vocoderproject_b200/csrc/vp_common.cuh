@@ -159,9 +159,13 @@ void vp_launch_yin(cudaStream_t st, const VPGeom& g, int S, const float* voice, 
 // correlation-form YIN (default): chunk partials P [S][3 nFramesP + 1][lagPad] floats, then the per-frame decision
 int vp_yin_corr_lagpad(const VPGeom& g);
 int vp_yin_corr_chunks(const VPGeom& g);
-void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech);
+int vp_yin_corr_tiles(const VPGeom& g);
+void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech, int lagBegin,
+                        int lagEnd, const int* tileList, const int* tileCount);
+int vp_yin_phase_split(const VPGeom& g);
 void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P, const double* Ech,
-                          int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList);
+                          int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList, int kLimit, int phase,
+                          uint8_t* pending, int* tileFlag, int* tileList, int* tileCount);
 void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                            uint32_t* yflags, const int* recheckList, const int* recheckCount, int maxList);
 void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,

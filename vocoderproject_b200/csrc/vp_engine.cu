@@ -60,6 +60,10 @@ struct vp_engine {
     double *dAP = nullptr, *dRP = nullptr;
     float* dOutE = nullptr;
     float* dYinP = nullptr;   // correlation-form YIN chunk partials
+    int* dYinTiles = nullptr;     // two-phase YIN: [1 count | tile flags | tile list]
+    uint8_t* dYinPending = nullptr;  // frames whose decision needs the upper lags
+    size_t yinTilesPerStreamCap = 0;
+    bool yinTwoPhase = true;  // VP_YIN_PHASES=1: one pass over all lags
     double* dYinE = nullptr;  // chunk energies
     int yinDirect = 0;        // VP_YIN_MODE=direct: FP32 direct-form (a-b)^2 kernel instead
     float *dOutV = nullptr, *dOutP = nullptr;
@@ -245,7 +249,7 @@ static void free_workspace(vp_engine* e) {
                      (void**)&e->dEeS, (void**)&e->dG, (void**)&e->dGs, (void**)&e->dPeriod, (void**)&e->dList, (void**)&e->dListCount,
                      (void**)&e->dYFlags, (void**)&e->dFrames, (void**)&e->dAP, (void**)&e->dOutE, (void**)&e->dOutV,
                      (void**)&e->dOutP, (void**)&e->dFramesAll, (void**)&e->dGateAll, (void**)&e->dEeVAll, (void**)&e->dEeSAll,
-                     (void**)&e->dGAll, (void**)&e->dGatePart, (void**)&e->dYinP, (void**)&e->dYinE, (void**)&e->dRP};
+                     (void**)&e->dGAll, (void**)&e->dGatePart, (void**)&e->dYinP, (void**)&e->dYinE, (void**)&e->dRP, (void**)&e->dYinTiles, (void**)&e->dYinPending};
     for (void** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) if (e->hIn[i][j]) { cudaFree(e->hIn[i][j]); e->hIn[i][j] = nullptr; }
@@ -289,6 +293,7 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
     }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&e->evTimer[i]);
     { const char* ov = getenv("VP_OVERLAP"); e->overlapMarks = !(ov && ov[0] == '0'); }
+    { const char* yp = getenv("VP_YIN_PHASES"); e->yinTwoPhase = !(yp && yp[0] == '1'); }
     const char* pt = getenv("VP_STAGE_TIMING");
     e->stageTiming = pt && pt[0] == '1';
     *out = e;
@@ -468,6 +473,9 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     if ((rc = wsalloc(e, &e->dOutE, fPc * (size_t)z.frameLenP))) return rc;
     if ((rc = wsalloc(e, &e->dYinP, (size_t)Sc * yinP))) return rc;
     if ((rc = wsalloc(e, &e->dYinE, e->yinDirect ? 1 : (size_t)Sc * vp_yin_corr_chunks(gy)))) return rc;
+    e->yinTilesPerStreamCap = e->yinDirect ? 0 : (size_t)vp_yin_corr_tiles(gy);
+    if ((rc = wsalloc(e, &e->dYinTiles, 4 + 2 * (size_t)Sc * e->yinTilesPerStreamCap))) return rc;
+    if ((rc = wsalloc(e, &e->dYinPending, (size_t)Sc * (size_t)std::max(nP, 1)))) return rc;
     if ((rc = wsalloc(e, &e->dOutV, (size_t)Sc * n))) return rc;
     if ((rc = wsalloc(e, &e->dOutP, (size_t)Sc * n))) return rc;
     // decisions for all streams (small): frames, gates, energies
@@ -601,11 +609,35 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
                 vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
                 stage_mark(e, ST_YIN);
             } else {
-                vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE);
-                stage_mark(e, ST_YIN);
-                vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-                stage_mark(e, ST_YIN_DECIDE);
-                e->launches++;
+                // (batch calls only: a streaming block has at most one pitch frame per stream and pays per launch)
+                const int k1 = (e->yinTwoPhase && g.nFramesP >= 16) ? vp_yin_phase_split(g) : 0;
+                if (k1 > 0) {
+                    // two lag phases: the decision of most voiced frames ends below k1, and the lags above it are then
+                    // never correlated for their chunks (exact: see k_yin_decide_reg)
+                    const size_t nT = (size_t)Sp * (size_t)vp_yin_corr_tiles(g);
+                    int* tCount = e->dYinTiles;
+                    int* tFlag = e->dYinTiles + 4;
+                    int* tList = tFlag + (size_t)e->Sc * e->yinTilesPerStreamCap;
+                    VP_CUDA_OK(cudaMemsetAsync(e->dYinTiles, 0, (4 + nT) * sizeof(int), st));
+                    vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, 0, k1, nullptr, nullptr);
+                    stage_mark(e, ST_YIN);
+                    vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
+                                         e->maxList, k1, 1, e->dYinPending, tFlag, tList, tCount);
+                    stage_mark(e, ST_YIN_DECIDE);
+                    vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, k1, 0, tList, tCount);
+                    stage_mark(e, ST_YIN);
+                    vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
+                                         e->maxList, 0, 2, e->dYinPending, tFlag, tList, tCount);
+                    stage_mark(e, ST_YIN_DECIDE);
+                    e->launches += 3;
+                } else {
+                    vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, 0, 0, nullptr, nullptr);
+                    stage_mark(e, ST_YIN);
+                    vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
+                                         e->maxList, 0, 0, nullptr, nullptr, nullptr, nullptr);
+                    stage_mark(e, ST_YIN_DECIDE);
+                    e->launches++;
+                }
             }
             vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
             stage_mark(e, ST_YIN64);

@@ -242,46 +242,64 @@ void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float*
 // being correlated -- the staging latency never reaches the FFMA loop.
 __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const float* __restrict__ voice, float* __restrict__ P,
                                                              double* __restrict__ Ech, int nChunks, int lagPad,
-                                                             int tilesPerStream, long long nTiles, int spanPad) {
-    extern __shared__ float xsAll[];  // 2 x [spanPad], spanPad >= YC_CH * c + lagPad + 16
+                                                             int tilesPerStream, long long nTiles, int spanPad, int lagBegin,
+                                                             int lagEnd, const int* __restrict__ tileList,
+                                                             const int* __restrict__ tileCount) {
+    extern __shared__ float xsAll[];  // 2 x [spanPad]; spanPad = 2 sub-spans of subPad floats
     const int c = g.c, tauMax = g.tauMax;
-    const int span = YC_CH * c + lagPad + 16;
+    // A tile = 2 groups of YC_CH consecutive chunks. Warp w works on chunk w of BOTH groups at once: its lower half-warp on
+    // group 0, its upper half-warp on group 1, 16 lanes x YC_R lags = YC_LAGS / 2 lags per pass. A pass costs what half of a
+    // 32-lane pass over one chunk would, so the lag range can be cut in two phases at no loss. Each group is staged as its
+    // own sub-span (its chunks + the lag tail); group 1's starts 16 banks after group 0's so that the two half-warps' window
+    // loads (lane stride YC_R floats, odd) never meet in a bank.
+    const int sub = YC_CH * c + lagPad + 16;
+    const int subPad = spanPad >> 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // with a tile list (second lag phase) the persistent loop runs over the listed tiles only
+    const long long nWork = tileList ? (long long)*tileCount : nTiles;
+    auto tileOf = [&](long long i) -> long long { return tileList ? (long long)tileList[i] : i; };
     auto issue = [&](long long tile, float* dst) {
         const int s = (int)(tile / tilesPerStream);
-        const int m0 = (int)(tile - (long long)s * tilesPerStream) * YC_CH;
+        const int m0 = (int)(tile - (long long)s * tilesPerStream) * (2 * YC_CH);
         const VPRow v = vp_row(voice, g.histV, s, g);
-        const long long t0 = (long long)m0 * c + g.offP - tauMax - g.lat;  // (call-local) input index of dst[0]
-        for (int j = threadIdx.x; j < span; j += blockDim.x) {
-            const long long t = t0 + j;
-            const bool ok = t >= -(long long)g.H && t < g.n;
-            const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);  // this call's samples / carried history
-            __pipeline_memcpy_async(dst + j, src, 4, ok ? 0 : 4);
+        for (int grp = 0; grp < 2; ++grp) {
+            const long long t0 = (long long)(m0 + grp * YC_CH) * c + g.offP - tauMax - g.lat;  // (call-local) input index of the sub-span's first sample
+            float* d = dst + grp * subPad;
+            for (int j = threadIdx.x; j < sub; j += blockDim.x) {
+                const long long t = t0 + j;
+                const bool ok = t >= -(long long)g.H && t < g.n;
+                const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);  // this call's samples / carried history
+                __pipeline_memcpy_async(d + j, src, 4, ok ? 0 : 4);
+            }
         }
         __pipeline_commit();
     };
-    long long tile = blockIdx.x;
-    if (tile >= nTiles) return;
+    long long wi = blockIdx.x;
+    if (wi >= nWork) return;
     int cur = 0;
-    issue(tile, xsAll);
-    for (; tile < nTiles; tile += gridDim.x) {
-        const long long next = tile + gridDim.x;
+    issue(tileOf(wi), xsAll);
+    const int half = lane >> 4, lg = lane & 15;
+    for (; wi < nWork; wi += gridDim.x) {
+        const long long tile = tileOf(wi);
+        const long long next = wi + gridDim.x;
         float* xs = xsAll + (size_t)cur * spanPad;
-        if (next < nTiles) { issue(next, xsAll + (size_t)(cur ^ 1) * spanPad); __pipeline_wait_prior(1); }
+        if (next < nWork) { issue(tileOf(next), xsAll + (size_t)(cur ^ 1) * spanPad); __pipeline_wait_prior(1); }
         else __pipeline_wait_prior(0);
         __syncthreads();
         const int s = (int)(tile / tilesPerStream);
-        const int m = (int)(tile - (long long)s * tilesPerStream) * YC_CH + warp;
-        if (m < nChunks) {
-            const float* xa = xs + warp * c;
-            float* out = P + ((size_t)s * nChunks + m) * (size_t)lagPad;
-            {   // chunk energy sum_j x[j]^2 in FP64 (exact products): A and B(k) of the decision kernel build on it
+        const int m = (int)(tile - (long long)s * tilesPerStream) * (2 * YC_CH) + half * YC_CH + warp;  // this half-warp's chunk
+        const bool live = m < nChunks;
+        {
+            const float* xa = xs + half * subPad + warp * c;
+            float* out = P + ((size_t)s * nChunks + (live ? m : 0)) * (size_t)lagPad;
+            if (lagBegin == 0) {  // chunk energy sum_j x[j]^2 in FP64 (exact products): A and B(k) of the decision kernel build on it
                 double e2 = 0.0;
-                for (int n = lane; n < c; n += 32) { const double x = (double)xa[n]; e2 = fma(x, x, e2); }
-                e2 = vp_warp_sum(e2);
-                if (lane == 0) Ech[(size_t)s * nChunks + m] = e2;
+                for (int n = lg; n < c; n += 16) { const double x = (double)xa[n]; e2 = fma(x, x, e2); }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+                if (lg == 0 && live) Ech[(size_t)s * nChunks + m] = e2;
             }
-            for (int k0 = lane * YC_R; k0 < lagPad; k0 += YC_LAGS) {
+            for (int k0 = lagBegin + lg * YC_R; k0 < lagEnd; k0 += YC_LAGS / 2) {
                 const float* xw = xa + k0;
                 float acc[YC_R], acc2[YC_R], W[YC_R];
 #pragma unroll
@@ -308,8 +326,10 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
                     for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
                     W[u % YC_R] = xw[n + u + YC_R];
                 }
+                if (live) {
 #pragma unroll
-                for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc2[r] + acc[r];
+                    for (int r = 0; r < YC_R; ++r) out[k0 + r] = acc2[r] + acc[r];
+                }
             }
         }
         __syncthreads();  // everyone is done with this buffer before the tile after next lands in it
@@ -452,7 +472,10 @@ template <int PER>
 __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* __restrict__ voice, const uint8_t* __restrict__ gate,
                                                         const float* __restrict__ P, const double* __restrict__ Ech, int nChunks,
                                                         int lagPad, int S, int* __restrict__ period, uint32_t* __restrict__ yflags,
-                                                        int* __restrict__ list, int* __restrict__ listCount, int maxList) {
+                                                        int* __restrict__ list, int* __restrict__ listCount, int maxList,
+                                                        int kLimit, int phase, uint8_t* __restrict__ pending,
+                                                        int* __restrict__ tileFlag, int* __restrict__ tileList,
+                                                        int* __restrict__ tileCount, int tilesPerStream) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long fidx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (fidx >= (long long)S * g.nFramesP) return;
@@ -460,10 +483,18 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
     const long long p = (long long)f * g.hopP + g.offP;
     const int b = (int)(p / g.B);
-    if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {
-        if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; }
+    // Two lag phases (phase 1: lags below kLimit only, phase 2: all lags, for the frames phase 1 could not finish; phase 0:
+    // one pass over all lags). The decision reads d'(tau) only up to the end of the descent after the first dip below the
+    // threshold, and d' at a lag depends on smaller lags only: whenever that point lies below kLimit the result of phase 1
+    // is the result of the full computation, and the upper lags of the frame's chunks are never correlated.
+    if (phase == 2) {
+        if (!pending[fidx]) return;
+    } else if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {
+        if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; if (phase == 1) pending[fidx] = 0; }
         return;
     }
+    const int kEnd = (phase == 1) ? min(kLimit, tauMax) : tauMax;  // lags [0, kEnd) are available
+    const bool partial = kEnd < tauMax;
     const VPRow v = vp_row(voice, g.histV, s, g);
     const long long q = p - tauMax;
     const double* Ec = Ech + (size_t)s * nChunks + (size_t)3 * f;
@@ -481,18 +512,26 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     {
         const float4* src = reinterpret_cast<const float4*>(P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad);
         float4* dst = reinterpret_cast<float4*>(sb);
-        for (int j = lane; j < lagPad; j += 32) __pipeline_memcpy_async(dst + j, src + j, 16);  // 4 rows x lagPad / 4
+        if (!partial) {
+            for (int j = lane; j < lagPad; j += 32) __pipeline_memcpy_async(dst + j, src + j, 16);  // 4 rows x lagPad / 4
+        } else {
+            const int q4 = (kEnd + 3) >> 2, r4 = lagPad >> 2;  // 16-byte pieces per row that hold lags < kEnd
+            for (int j = lane; j < 4 * q4; j += 32) {
+                const int row = j / q4, col = j - row * q4;
+                __pipeline_memcpy_async(dst + row * r4 + col, src + row * r4 + col, 16);
+            }
+        }
         float* sh = sb + 4 * lagPad;
         float* sl = sb + 5 * lagPad;
         if (inside) {
             const float* ph = v.x + tq + L;
             const float* pl = v.x + tq;
-            for (int k = lane; k < tauMax; k += 32) {
+            for (int k = lane; k < kEnd; k += 32) {
                 __pipeline_memcpy_async(sh + k, ph + k, 4);
                 __pipeline_memcpy_async(sl + k, pl + k, 4);
             }
         } else {
-            for (int k = lane; k < tauMax; k += 32) { sh[k] = vp_x(v, q + L + k, g); sl[k] = vp_x(v, q + k, g); }
+            for (int k = lane; k < kEnd; k += 32) { sh[k] = vp_x(v, q + L + k, g); sl[k] = vp_x(v, q + k, g); }
         }
         __pipeline_commit();
         __pipeline_wait_prior(0);
@@ -505,7 +544,7 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     for (int j = 0; j < PER; ++j) {
         const int k = kA + j;
         double dl = 0.0;
-        if (k < tauMax) {
+        if (k < kEnd) {
             const double h = (double)sb[4 * lagPad + k], l = (double)sb[5 * lagPad + k];
             dl = h * h - l * l;
         }
@@ -525,7 +564,7 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         const double Bk = A + run;
         run += en[j];
         double d = (A + Bk) - 2.0 * dn[j], e = beta * (A + Bk);
-        if (k == 0 || k >= tauMax) { d = 0.0; e = 0.0; }
+        if (k == 0 || k >= kEnd) { d = 0.0; e = 0.0; }
         dn[j] = d;
         en[j] = e;
         locD += d;
@@ -553,7 +592,7 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         const double kr = (double)k * __drcp_rn(runD);
         double x = d * kr, ex;
         if (runD > 2.0 * runE) ex = (e * kr + fabs(x) * (runE * __drcp_rn(runD))) * 1.01;
-        else { ex = 1e300; if (runE > 0.0 && k >= g.tauMin && k < tauMax) shaky = true; }
+        else { ex = 1e300; if (runE > 0.0 && k >= g.tauMin && k < kEnd) shaky = true; }
         if (k == 0) { x = 1.0; ex = 0.0; }
         dn[j] = x;
         en[j] = ex;
@@ -565,7 +604,7 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
 #pragma unroll
     for (int j = PER - 1; j >= 0; --j) {
         const int k = kA + j;
-        if (k >= g.tauMin && k < tauMax && dn[j] < tol) first = k;
+        if (k >= g.tauMin && k < kEnd && dn[j] < tol) first = k;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
@@ -573,12 +612,13 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     unsigned fl = 0;
     bool unsafe = false;
     const bool have = (first != 0x7fffffff) && total > 0.0;
+    bool complete = !partial;  // phase 1: the decision is final only if it ends below kEnd
     if (energy > 0.0) {
-        const int kLast = have ? first : tauMax - 1;
+        const int kLast = have ? first : kEnd - 1;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             const int k = kA + j;
-            if (k >= g.tauMin && k <= kLast && k < tauMax && !(fabs(dn[j] - tol) > en[j])) unsafe = true;
+            if (k >= g.tauMin && k <= kLast && k < kEnd && !(fabs(dn[j] - tol) > en[j])) unsafe = true;
         }
         if (shaky) unsafe = true;
     }
@@ -589,21 +629,36 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         for (int j = PER - 1; j >= 0; --j) {
             const int k = kA + j;
             const double nx = (j == PER - 1) ? dnNext : dn[(j + 1) % PER];
-            if (k >= first && k < tauMax && (k + 1 >= tauMax || !(nx < dn[j]))) stop = k;
+            // (phase 1: d'(k + 1) must be one of the available lags)
+            if (k >= first && k < kEnd && (partial ? (k + 1 < kEnd && !(nx < dn[j])) : (k + 1 >= tauMax || !(nx < dn[j])))) stop = k;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) stop = min(stop, __shfl_xor_sync(0xffffffffu, stop, o));
         per_ = stop;
+        if (partial) complete = (stop != 0x7fffffff) && energy > 0.0;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             const int k = kA + j;
             const double nx = (j == PER - 1) ? dnNext : dn[(j + 1) % PER];
             const double ne = (j == PER - 1) ? enNext : en[(j + 1) % PER];
-            if (k >= first && k <= stop && k + 1 < tauMax && !(fabs(nx - dn[j]) > en[j] + ne)) unsafe = true;
+            if (k >= first && k <= stop && k + 1 < kEnd && !(fabs(nx - dn[j]) > en[j] + ne)) unsafe = true;
         }
+    }
+    if (!complete) {  // uniform across the warp: hand the frame to phase 2 and ask for the upper lags of its chunks' tiles
+        if (lane == 0) {
+            pending[fidx] = 1;
+            const int tl = 2 * YC_CH;
+            const int t0 = (3 * f) / tl, t1 = (3 * f + 3) / tl;
+            for (int t = t0; t <= t1; ++t) {
+                const int ti = s * tilesPerStream + t;
+                if (atomicExch(tileFlag + ti, 1) == 0) tileList[atomicAdd(tileCount, 1)] = ti;
+            }
+        }
+        return;
     }
     unsafe = __any_sync(0xffffffffu, unsafe);
     if (lane == 0) {
+        if (phase == 1) pending[fidx] = 0;
         if (unsafe) fl |= YF_RECHECK;
         period[fidx] = per_;
         yflags[fidx] = fl;
@@ -616,13 +671,19 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
 
 int vp_yin_corr_lagpad(const VPGeom& g) { return (g.tauMax + YC_LAGS - 1) / YC_LAGS * YC_LAGS; }
 int vp_yin_corr_chunks(const VPGeom& g) { return 3 * g.nFramesP + 1; }
+int vp_yin_corr_tiles(const VPGeom& g) { return (vp_yin_corr_chunks(g) + 2 * YC_CH - 1) / (2 * YC_CH); }  // per stream; tile = 2 x YC_CH chunks
 
-void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech) {
+// lags [lagBegin, lagEnd) (multiples of YC_LAGS / 2) of every tile, or -- tileList != nullptr -- of the *tileCount listed tiles
+void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* voice, float* P, double* Ech, int lagBegin,
+                        int lagEnd, const int* tileList, const int* tileCount) {
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
-    const int spanPad = (YC_CH * g.c + lagPad + 16 + 3) & ~3;
+    // sub-span of one chunk group, rounded to 32 floats, + 16: group 1 starts half the banks after group 0
+    const int subPad = ((YC_CH * g.c + lagPad + 16 + 31) & ~31) + 16;
+    const int spanPad = 2 * subPad;
     const size_t smem = (size_t)2 * spanPad * sizeof(float);
-    const int tilesPerStream = (nChunks + YC_CH - 1) / YC_CH;
+    const int tilesPerStream = vp_yin_corr_tiles(g);
     const long long nTiles = (long long)tilesPerStream * S;
+    if (lagEnd <= 0 || lagEnd > lagPad) lagEnd = lagPad;
     cudaFuncSetAttribute(k_yin_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int perSM = 4;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_yin_corr, 32 * YC_CH, smem);
@@ -632,18 +693,38 @@ void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* vo
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)nSM * perSM;
     if (grid > nTiles) grid = nTiles;
-    k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad);
+    k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad, lagBegin,
+                                                         lagEnd, tileList, tileCount);
 }
 
+// First lag phase of the two-phase YIN (0 = not applicable: one pass over all lags). Applicable when the register-resident
+// decision kernel is (tauMax <= 32 x 15, one YC_LAGS pass) and the split leaves lags on both sides.
+int vp_yin_phase_split(const VPGeom& g) {
+    const int k1 = YC_LAGS / 2;
+    return (vp_yin_corr_lagpad(g) == YC_LAGS && g.tauMax > k1 + 8 && g.tauMin + 8 < k1) ? k1 : 0;
+}
+
+// phase 0: all lags, every frame. phase 1: lags < kLimit, frames whose decision needs more are marked pending and their
+// tiles listed. phase 2: all lags, pending frames only. aux = {pending bytes, tileFlag, tileList, tileCount}.
 void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,
-                          const double* Ech, int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList) {
+                          const double* Ech, int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList,
+                          int kLimit, int phase, uint8_t* pending, int* tileFlag, int* tileList, int* tileCount) {
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
     const long long tot = (long long)S * g.nFramesP;
     if (g.tauMax <= 32 * 15) {
         const size_t smemReg = (size_t)8 * 6 * lagPad * sizeof(float);
         cudaFuncSetAttribute(k_yin_decide_reg<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (phase == 1 && kLimit <= 32 * 9) {
+            // phase 1 reads lags < kLimit only: 9 lags per lane (odd: conflict-free) instead of 15 -> 0.6 x the instructions
+            cudaFuncSetAttribute(k_yin_decide_reg<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            k_yin_decide_reg<9><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
+                                                                           recheckList, recheckCount, maxList, kLimit, phase, pending,
+                                                                           tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
+            return;
+        }
         k_yin_decide_reg<15><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
-                                                                        recheckList, recheckCount, maxList);
+                                                                        recheckList, recheckCount, maxList, kLimit, phase, pending,
+                                                                        tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
         return;
     }
     const int tauPad = (g.tauMax + 3) & ~3;
