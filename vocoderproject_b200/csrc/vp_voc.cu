@@ -745,9 +745,20 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
         // from the same straight-line code, so their latencies hide under the FP64 pipe. Samples are fetched two
         // blocks ahead. The pipeline drains at the end of a row (a new frame may start at the next one).
         const int nblk = (hop + 3) >> 2;
+        // side-chain loads of this row (offsets reach at most hop + 7 past its start): when all of them fall inside this
+        // call's input they are plain loads off one row pointer, no per-block range test or 64-bit address arithmetic
+        const long long rowIn = tBase - g.lat;
+        const bool rowFast = rowIn >= 0 && rowIn + hop + 8 <= g.n;
+        const float* rowPtr = y.x + rowIn;
+        auto load4 = [&](int off, float* x) {
+            if (rowFast) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = __ldg(rowPtr + off + j);
+            } else vt_load4(y, tBase + off, g, x);
+        };
         if (!primed) {
-            vt_load4(y, tBase, g, xA);
-            vt_load4(y, (4 < hop) ? tBase + 4 : tBase + hop, g, xB);
+            load4(0, xA);
+            load4((4 < hop) ? 4 : hop, xB);
             primed = true;
         }
         double eN[4];
@@ -766,7 +777,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
 #pragma unroll
             for (int j = 0; j < 4; ++j) xA[j] = xB[j];
             // samples of block 2 of this row, or of the first block(s) of the next row
-            vt_load4(y, (8 < hop) ? tBase + 8 : ((4 < hop) ? tBase + hop : tBase + hop + 4), g, xB);
+            load4((8 < hop) ? 8 : ((4 < hop) ? hop : hop + 4), xB);
         }
         float cP[4] = {0.f, 0.f, 0.f, 0.f};
         long long tP = 0;
@@ -796,11 +807,11 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
                 for (int j = 0; j < 4; ++j) xA[j] = xB[j];
                 // start of the block three ahead in the global block sequence (rows are contiguous in position)
                 const int i3 = i0 + 12;
-                long long tn;
-                if (i3 < hop) tn = tBase + i3;
-                else if (i0 + 8 < hop) tn = tBase + hop;          // block b+2 is the row's last: b+3 = next row, block 0
-                else tn = tBase + hop + 4;                        // block b+1 is the row's last: b+3 = next row, block 1
-                vt_load4(y, tn, g, xB);
+                int on;
+                if (i3 < hop) on = i3;
+                else if (i0 + 8 < hop) on = hop;          // block b+2 is the row's last: b+3 = next row, block 0
+                else on = hop + 4;                        // block b+1 is the row's last: b+3 = next row, block 1
+                load4(on, xB);
             }
             // ---- all-pole recursion of block b
             float c[4];
