@@ -780,8 +780,18 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
             load4((8 < hop) ? 8 : ((4 < hop) ? hop : hop + 4), xB);
         }
         float cP[4] = {0.f, 0.f, 0.f, 0.f};
-        long long tP = 0;
-        int nbP = 0;
+        int iP = 0, nbP = 0;  // offset in the row and size of the block whose overlap-add is pending
+        // the whole row lies inside this segment's emission range: stores go off one row pointer, no range test
+        const bool rowEmit = emitRow && tBase >= emit0 && tBase + hop <= emit1;
+        float* orow = o + tBase;
+        auto emit = [&](float tot) {
+            if (rowEmit) {
+                if (phi < nbP) orow[iP + phi] = tot;
+            } else {
+                const long long tp = tBase + iP + phi;
+                if (emitRow && phi < nbP && tp >= emit0 && tp < emit1) o[tp] = tot;
+            }
+        };
         // FULL: block b and block b+1 are both complete blocks of this row -> no guards, one basic block
         auto blockStep = [&](auto fullTag, int b) {
             constexpr bool FULL = decltype(fullTag)::value;
@@ -834,12 +844,11 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
                 const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
                 const float snd = od ? r0 : r1, kp = od ? r1 : r0;
                 const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
-                const long long tp = tP + phi;
-                if (emitRow && phi < nbP && tp >= emit0 && tp < emit1) o[tp] = tot;
+                emit(tot);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) cP[j] = c[j];
-            tP = tBase + i0;
+            iP = i0;
             nbP = nb;
         };
         const int nFullPairs = (hop >> 2) - 1;  // blocks b with b and b+1 both full: b < hop/4 - 1
@@ -854,8 +863,7 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
             const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
             const float snd = od ? r0 : r1, kp = od ? r1 : r0;
             const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
-            const long long tp = tP + phi;
-            if (emitRow && phi < nbP && tp >= emit0 && tp < emit1) o[tp] = tot;
+            emit(tot);
         }
         ++wrow;
     }
