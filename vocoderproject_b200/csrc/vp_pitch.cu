@@ -259,17 +259,22 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
     const long long nWork = tileList ? (long long)*tileCount : nTiles;
     auto tileOf = [&](long long i) -> long long { return tileList ? (long long)tileList[i] : i; };
     auto issue = [&](long long tile, float* dst) {
-        const int s = (int)(tile / tilesPerStream);
-        const int m0 = (int)(tile - (long long)s * tilesPerStream) * (2 * YC_CH);
+        const int s = (int)((unsigned)tile / (unsigned)tilesPerStream);  // tile < 2^31 (checked by the launcher)
+        const int m0 = (int)((unsigned)tile - (unsigned)s * (unsigned)tilesPerStream) * (2 * YC_CH);
         const VPRow v = vp_row(voice, g.histV, s, g);
         for (int grp = 0; grp < 2; ++grp) {
             const long long t0 = (long long)(m0 + grp * YC_CH) * c + g.offP - tauMax - g.lat;  // (call-local) input index of the sub-span's first sample
             float* d = dst + grp * subPad;
-            for (int j = threadIdx.x; j < sub; j += blockDim.x) {
-                const long long t = t0 + j;
-                const bool ok = t >= -(long long)g.H && t < g.n;
-                const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);  // this call's samples / carried history
-                __pipeline_memcpy_async(d + j, src, 4, ok ? 0 : 4);
+            if (t0 >= 0 && t0 + sub <= g.n) {  // common case: the sub-span lies inside this call's input
+                const float* src = v.x + t0;
+                for (int j = threadIdx.x; j < sub; j += blockDim.x) __pipeline_memcpy_async(d + j, src + j, 4);
+            } else {
+                for (int j = threadIdx.x; j < sub; j += blockDim.x) {
+                    const long long t = t0 + j;
+                    const bool ok = t >= -(long long)g.H && t < g.n;
+                    const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);  // this call's samples / carried history
+                    __pipeline_memcpy_async(d + j, src, 4, ok ? 0 : 4);
+                }
             }
         }
         __pipeline_commit();
@@ -286,8 +291,8 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
         if (next < nWork) { issue(tileOf(next), xsAll + (size_t)(cur ^ 1) * spanPad); __pipeline_wait_prior(1); }
         else __pipeline_wait_prior(0);
         __syncthreads();
-        const int s = (int)(tile / tilesPerStream);
-        const int m = (int)(tile - (long long)s * tilesPerStream) * (2 * YC_CH) + half * YC_CH + warp;  // this half-warp's chunk
+        const int s = (int)((unsigned)tile / (unsigned)tilesPerStream);
+        const int m = (int)((unsigned)tile - (unsigned)s * (unsigned)tilesPerStream) * (2 * YC_CH) + half * YC_CH + warp;  // this half-warp's chunk
         const bool live = m < nChunks;
         {
             const float* xa = xs + half * subPad + warp * c;
@@ -693,6 +698,7 @@ void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* vo
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)nSM * perSM;
     if (grid > nTiles) grid = nTiles;
+    if (nTiles >= (1LL << 31)) return;  // cannot happen: the workspace bounds streams x frames per pass far below this
     k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad, lagBegin,
                                                          lagEnd, tileList, tileCount);
 }
