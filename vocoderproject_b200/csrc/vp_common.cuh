@@ -165,7 +165,7 @@ void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* vo
 int vp_yin_phase_split(const VPGeom& g);
 void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P, const double* Ech,
                           int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList, int kLimit, int phase,
-                          uint8_t* pending, int* tileFlag, int* tileList, int* tileCount);
+                          int* pendList, int* pendCount, int* tileFlag, int* tileList, int* tileCount);
 void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, int* period,
                            uint32_t* yflags, const int* recheckList, const int* recheckCount, int maxList);
 void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,

@@ -61,7 +61,7 @@ struct vp_engine {
     float* dOutE = nullptr;
     float* dYinP = nullptr;   // correlation-form YIN chunk partials
     int* dYinTiles = nullptr;     // two-phase YIN: [1 count | tile flags | tile list]
-    uint8_t* dYinPending = nullptr;  // frames whose decision needs the upper lags
+    int* dYinPending = nullptr;  // list of the frames whose decision needs the upper lags
     size_t yinTilesPerStreamCap = 0;
     bool yinTwoPhase = true;  // VP_YIN_PHASES=1: one pass over all lags
     double* dYinE = nullptr;  // chunk energies
@@ -622,19 +622,19 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
                     vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, 0, k1, nullptr, nullptr);
                     stage_mark(e, ST_YIN);
                     vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
-                                         e->maxList, k1, 1, e->dYinPending, tFlag, tList, tCount);
+                                         e->maxList, k1, 1, e->dYinPending, tCount + 1, tFlag, tList, tCount);
                     stage_mark(e, ST_YIN_DECIDE);
                     vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, k1, 0, tList, tCount);
                     stage_mark(e, ST_YIN);
                     vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
-                                         e->maxList, 0, 2, e->dYinPending, tFlag, tList, tCount);
+                                         e->maxList, 0, 2, e->dYinPending, tCount + 1, tFlag, tList, tCount);
                     stage_mark(e, ST_YIN_DECIDE);
                     e->launches += 3;
                 } else {
                     vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, 0, 0, nullptr, nullptr);
                     stage_mark(e, ST_YIN);
                     vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
-                                         e->maxList, 0, 0, nullptr, nullptr, nullptr, nullptr);
+                                         e->maxList, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
                     stage_mark(e, ST_YIN_DECIDE);
                     e->launches++;
                 }

@@ -478,12 +478,15 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
                                                         const float* __restrict__ P, const double* __restrict__ Ech, int nChunks,
                                                         int lagPad, int S, int* __restrict__ period, uint32_t* __restrict__ yflags,
                                                         int* __restrict__ list, int* __restrict__ listCount, int maxList,
-                                                        int kLimit, int phase, uint8_t* __restrict__ pending,
+                                                        int kLimit, int phase, int* __restrict__ pendList, int* __restrict__ pendCount,
                                                         int* __restrict__ tileFlag, int* __restrict__ tileList,
                                                         int* __restrict__ tileCount, int tilesPerStream) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long fidx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (fidx >= (long long)S * g.nFramesP) return;
+    const int wpb = blockDim.x >> 5;
+    // phase 2 runs over the list of frames phase 1 left pending (persistent warps); phases 0 / 1 over every frame
+    const long long nItems = (phase == 2) ? (long long)*pendCount : (long long)S * g.nFramesP;
+    for (long long wi = (long long)blockIdx.x * wpb + warp; wi < nItems; wi += (long long)gridDim.x * wpb) {
+    const long long fidx = (phase == 2) ? (long long)pendList[wi] : wi;
     const int tauMax = g.tauMax, L = g.L;
     const int s = (int)(fidx / g.nFramesP), f = (int)(fidx - (long long)s * g.nFramesP);
     const long long p = (long long)f * g.hopP + g.offP;
@@ -492,11 +495,9 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     // one pass over all lags). The decision reads d'(tau) only up to the end of the descent after the first dip below the
     // threshold, and d' at a lag depends on smaller lags only: whenever that point lies below kLimit the result of phase 1
     // is the result of the full computation, and the upper lags of the frame's chunks are never correlated.
-    if (phase == 2) {
-        if (!pending[fidx]) return;
-    } else if (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE) {
-        if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; if (phase == 1) pending[fidx] = 0; }
-        return;
+    if (phase != 2 && (gate[(size_t)s * g.nBlocks + b] & VP_GATE_VOICE)) {
+        if (lane == 0) { period[fidx] = 0; yflags[fidx] = 0; }
+        continue;
     }
     const int kEnd = (phase == 1) ? min(kLimit, tauMax) : tauMax;  // lags [0, kEnd) are available
     const bool partial = kEnd < tauMax;
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     }
     if (!complete) {  // uniform across the warp: hand the frame to phase 2 and ask for the upper lags of its chunks' tiles
         if (lane == 0) {
-            pending[fidx] = 1;
+            pendList[atomicAdd(pendCount, 1)] = (int)fidx;
             const int tl = 2 * YC_CH;
             const int t0 = (3 * f) / tl, t1 = (3 * f + 3) / tl;
             for (int t = t0; t <= t1; ++t) {
@@ -659,11 +660,10 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
                 if (atomicExch(tileFlag + ti, 1) == 0) tileList[atomicAdd(tileCount, 1)] = ti;
             }
         }
-        return;
+        continue;
     }
     unsafe = __any_sync(0xffffffffu, unsafe);
     if (lane == 0) {
-        if (phase == 1) pending[fidx] = 0;
         if (unsafe) fl |= YF_RECHECK;
         period[fidx] = per_;
         yflags[fidx] = fl;
@@ -671,6 +671,8 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
             const int slot = atomicAdd(listCount, 1);
             if (slot < maxList) list[slot] = (int)fidx;
         }
+    }
+    __syncwarp();  // the warp's shared rows are free for its next frame
     }
 }
 
@@ -714,7 +716,7 @@ int vp_yin_phase_split(const VPGeom& g) {
 // tiles listed. phase 2: all lags, pending frames only. aux = {pending bytes, tileFlag, tileList, tileCount}.
 void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* voice, const uint8_t* gate, const float* P,
                           const double* Ech, int* period, uint32_t* yflags, int* recheckList, int* recheckCount, int maxList,
-                          int kLimit, int phase, uint8_t* pending, int* tileFlag, int* tileList, int* tileCount) {
+                          int kLimit, int phase, int* pendList, int* pendCount, int* tileFlag, int* tileList, int* tileCount) {
     const int lagPad = vp_yin_corr_lagpad(g), nChunks = vp_yin_corr_chunks(g);
     const long long tot = (long long)S * g.nFramesP;
     if (g.tauMax <= 32 * 15) {
@@ -724,13 +726,20 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
             // phase 1 reads lags < kLimit only: 9 lags per lane (odd: conflict-free) instead of 15 -> 0.6 x the instructions
             cudaFuncSetAttribute(k_yin_decide_reg<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             k_yin_decide_reg<9><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
-                                                                           recheckList, recheckCount, maxList, kLimit, phase, pending,
+                                                                           recheckList, recheckCount, maxList, kLimit, phase, pendList, pendCount,
                                                                            tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
             return;
         }
-        k_yin_decide_reg<15><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
-                                                                        recheckList, recheckCount, maxList, kLimit, phase, pending,
-                                                                        tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
+        long long grid = (tot + 7) / 8;
+        if (phase == 2) {  // persistent warps over the pending list (its length is only known on the device)
+            int dev = 0, nSM = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+            grid = std::min<long long>(grid, (long long)nSM * 8);
+        }
+        k_yin_decide_reg<15><<<(unsigned)grid, 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
+                                                             recheckList, recheckCount, maxList, kLimit, phase, pendList, pendCount,
+                                                             tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
         return;
     }
     const int tauPad = (g.tauMax + 3) & ~3;
