@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
             const int split = wlen - r0;
             const float* rv = ringV + r0;
             const float* rs = ringS + r0;
-#pragma unroll 3
+#pragma unroll 6
             for (int j = lane; j < split; j += 32) {
                 const double w = wv[j];
                 xw[j] = (double)rv[j] * w;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
             rv = ringV - split;
             rs = ringS - split;
             const int jb = split + ((lane - split) & 31);  // first j >= split with j = lane (mod 32)
-#pragma unroll 3
+#pragma unroll 6
             for (int j = jb; j < wlen; j += 32) {
                 const double w = wv[j];
                 xw[j] = (double)rv[j] * w;
