@@ -809,8 +809,21 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     const size_t rowB = (size_t)n * sizeof(float);
     int slice = 0;
     if (!e->timingOpen) { e->evUsed = 0; e->evSideUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
-    for (int s0 = 0; s0 < e->S; s0 += e->Sh, ++slice) {
-        const int Sp = std::min(e->Sh, e->S - s0);
+    // Slice schedule: full slices of Sh streams, tapered at both ends (Sh/4, Sh/2, Sh ... Sh, Sh/2, Sh/4) -- the pipeline
+    // (H2D of slice i+1 | kernels of slice i | D2H of slice i-1) is bound by the host link, so what is not overlapped is the
+    // first upload and the last compute + download, and both shrink with the slice they belong to.
+    std::vector<int> sizes;
+    {
+        const int Sh = e->Sh, q = std::max(1, Sh / 4), h = std::max(1, Sh / 2);
+        int rem = e->S;
+        const bool taper = e->S >= 3 * Sh && Sh >= 8;
+        if (taper) { sizes.push_back(q); sizes.push_back(h); rem -= 2 * (q + h); }
+        while (rem > 0) { const int k = std::min(Sh, rem); sizes.push_back(k); rem -= k; }
+        if (taper) { sizes.push_back(h); sizes.push_back(q); }
+    }
+    int s0 = 0;
+    for (size_t si = 0; si < sizes.size(); s0 += sizes[si], ++si, ++slice) {
+        const int Sp = sizes[si];
         const int bi = slice % 3;
         // the buffers of this rotation slot must have been drained (D2H of slice-3 done)
         if (slice >= 3) VP_CUDA_OK(cudaStreamWaitEvent(e->stIn, e->evOut[bi], 0));
