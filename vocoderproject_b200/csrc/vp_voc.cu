@@ -201,12 +201,11 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 // ---------------------------------------------------------------------------
 #define AV_WARPS 7   // 7 x 14.4 KB + window: two CTAs per SM = 14 warps
 #define AV_BATCH 32  // consecutive frames per warp: the initial ring fill is paid once per batch
-#define AV_NPRE 8    // prefetch registers per lane and signal: hop <= 32 * AV_NPRE
 
 // A warp keeps the raw samples of its current frame in a ring of wlen = 4 hop floats per signal (position u lives at
-// u mod wlen). While frame k is being correlated, the hop NEW samples of frame k+1 are already in flight into
-// registers; after the correlation they overwrite the oldest hop ring entries. Global latency is hidden behind the
-// FP64 work and every input sample is loaded exactly once per batch.
+// u mod wlen). Once frame k's windowed copies are built, the ring's oldest hop entries are dead: the hop NEW samples of
+// frame k+1 land there as asynchronous copies (cp.async) while frame k is being correlated. Global latency is hidden
+// behind the FP64 work and every input sample is loaded exactly once per batch.
 __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                                  const float* __restrict__ synth, double* __restrict__ rV,
                                                                  double* __restrict__ rS, int segLen, int FS, int ringLen,
@@ -340,7 +339,7 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
-    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 && g.hopV <= 32 * AV_NPRE) {
+    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 ) {
         FS = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
         const int ringLen = (g.wlenV + 3) & ~3;  // floats per signal; two signals = ringLen doubles
         const size_t smem = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS + ringLen)) * sizeof(double);
