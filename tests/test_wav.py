@@ -72,6 +72,35 @@ def test_wavbatch_builds_and_reports_errors(vp, tool, tmp_path):
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
 
 
+def test_wav_reader_writer_against_python_decoders(tmp_path):
+    """vp_wav.hpp alone (no GPU): PCM16 / PCM24 / float32, mono and stereo, decode to exactly what Python's decoders give;
+    the float32 rewrite is lossless, the PCM16 rewrite is the rounded signal."""
+    exe = str(tmp_path / "wav_roundtrip")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "vocoderproject_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "adapter", "wav_roundtrip.cpp"), "-o", exe])
+    rng = np.random.default_rng(7)
+    for wr, nch in ((write_pcm16, 1), (write_pcm16, 2), (write_pcm24, 2), (write_f32, 1), (write_f32, 2)):
+        x = [(0.8 * rng.standard_normal(3001)).clip(-0.99, 0.99).astype(np.float32) for _ in range(nch)]
+        src = str(tmp_path / "in.wav")
+        dec = wr(src, 22050, x)
+        f32, p16 = str(tmp_path / "f.wav"), str(tmp_path / "p.wav")
+        out = subprocess.run([exe, src, f32, p16], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        j = json.loads(out.stdout)
+        assert (j["sample_rate"], j["channels"], j["frames"]) == (22050, nch, 3001)
+        fs, y = read_f32(f32)
+        y = y.reshape(3001, nch)
+        for c in range(nch):
+            assert np.array_equal(y[:, c], dec[c])  # decoded exactly like Python's decoder, float32 rewrite lossless
+        with wave.open(p16, "rb") as w:
+            q = np.frombuffer(w.readframes(3001), "<i2").reshape(3001, nch)
+        for c in range(nch):
+            assert np.array_equal(q[:, c], np.clip(np.rint(dec[c] * 32768.0), -32768, 32767).astype(np.int16))
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"RIFFxxxxWAVEjunk")
+    assert subprocess.run([exe, str(bad), f32, p16], capture_output=True).returncode == 1
+
+
 @pytest.mark.gpu
 def test_wav_batch_equals_engine_on_decoded_arrays(vp, tool, tmp_path):
     fs, B, K = 44100.0, 1024, 8
