@@ -361,6 +361,55 @@ def test_many_streams_spot_parity(vp, oracle):
         eng.close()
 
 
+def test_two_phase_yin_equals_single_pass(vp, monkeypatch):
+    """The two-lag-phase YIN (phase 1 decides on lags < 240, phase 2 only for the frames that need more) is exact: same
+    periods, same marks, bit-identical audio as one pass over all lags (VP_YIN_PHASES=1), on low and high voices."""
+    fs, B, S = 48000.0, 1024, 48
+    n = int(fs * 2.5) // B * B
+    voice, sl, sr = vp.synth_host(fs, S, n, flavour=0, first_stream=900)
+    res = []
+    for mode in ("1", "2"):
+        monkeypatch.setenv("VP_YIN_PHASES", mode)
+        outL, outR, eng = run_engine(vp, fs, B, voice, sl, None, dict(keyPitch=3))
+        try:
+            fr = [[(f.period, f.note, list(f.anMarks[:f.nAn]), list(f.stMarks[:f.nSt])) for f in eng.pitch_frames(s)] for s in range(S)]
+            res.append((outL, fr))
+        finally:
+            eng.close()
+    assert res[0][1] == res[1][1]
+    assert np.array_equal(res[0][0], res[1][0])
+    periods = [p[0] for s in res[0][1] for p in s if p[0] > 0]
+    assert min(periods) < 200 and max(periods) > 280  # both phases decided frames
+
+
+def test_voiced_silent_voiced_transitions(vp, oracle):
+    """Gates closing and re-opening mid-stream (voiced 1.2 s, silence 0.8 s, voiced again): the pitch path's restart after a
+    gated stretch (anMarks cleared, prevPitch = 0, PitchProcess.cpp:208-214) and the vocoder's frozen energy histories
+    (VocoderProcess.cpp:199-204) -- audio and every decision against the oracle, which reports no UB on this input."""
+    fs, B = 44100.0, 1024
+    v, s_ = kat_inputs(int(fs), 4)
+    n = int(fs * 3.2) // B * B
+    voice = np.zeros(n, np.float32)
+    a, b = int(fs * 1.2), int(fs * 2.0)
+    voice[:a] = v[:a]
+    voice[b:] = v[:n - b]
+    synth = s_[:n].copy()
+    r = oracle.run(fs, B, voice, synth, params=refbind.default_params(keyPitch=3), log=True)
+    assert r["ub"] == 0
+    outL, outR, eng = run_engine(vp, fs, B, voice[None], synth[None], synth[None], dict(keyPitch=3))
+    try:
+        assert_audio(r["outL"], outL[0], "voiced-silent-voiced")
+        rows = oracle_decisions(r["pitch"])
+        assert sum(x["gated"] for x in rows) > 20 and rows[-1]["period"] > 0
+        n_, bad, flagged, first = compare_decisions(vp, rows, eng.pitch_frames(0))
+        assert bad == 0, first
+        assert flagged <= 3
+        vf = eng.voc_frames(0)
+        assert list(vf["gated"]) == [x.gated for x in r["voc"]]
+    finally:
+        eng.close()
+
+
 def test_errors_are_codes(vp):
     eng = vp.Engine(44100.0, 1024, 2, 4)
     try:

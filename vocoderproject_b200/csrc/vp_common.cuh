@@ -122,6 +122,21 @@ __device__ __forceinline__ double vp_warp_sum(double v) {
     return v;
 }
 
+// Every kernel launch goes through VP_LAUNCH: a launch that the runtime refuses (configuration, shared memory, ...) is
+// recorded -- first one wins -- and turns the engine call that issued it into VP_E_CUDA (vp_take_launch_error).
+extern cudaError_t g_vpLaunchError;
+inline void vp_note_launch() {
+    const cudaError_t err = cudaPeekAtLastError();
+    if (err != cudaSuccess && g_vpLaunchError == cudaSuccess) g_vpLaunchError = err;
+}
+inline cudaError_t vp_take_launch_error() {
+    const cudaError_t err = g_vpLaunchError;
+    g_vpLaunchError = cudaSuccess;
+    if (err != cudaSuccess) cudaGetLastError();  // clear the runtime's copy as well
+    return err;
+}
+#define VP_LAUNCH(...) do { __VA_ARGS__; vp_note_launch(); } while (0)
+
 #define VP_CUDA_OK(call)                                                        \
     do {                                                                        \
         cudaError_t _e = (call);                                                \

@@ -20,6 +20,8 @@ static const char* kStageNames[VP_NSTAGES] = {"gate", "voc_autocorr", "voc_levin
                                               "marks", "pitch_psola", "pitch_iir", "mix", "clear", "other",
                                               "yin_decide", "pitch_lpc", "", ""};
 
+cudaError_t g_vpLaunchError = cudaSuccess;
+
 struct vp_engine {
     int device = 0;
     bool prepared = false;
@@ -717,6 +719,7 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         }
         stage_mark(e, ST_OTHER);
     }
+    VP_CUDA_OK(vp_take_launch_error());
     VP_CUDA_OK(cudaGetLastError());
     return VP_OK;
 }

@@ -53,7 +53,7 @@ void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, 
     if (bx > 4096) bx = 4096;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, S);
-    k_mix<<<grid, 256, 0, st>>>(g, voice, synthL, synthR, outV, outP, outL, outR);
+    VP_LAUNCH(k_mix<<<grid, 256, 0, st>>>(g, voice, synthL, synthR, outV, outP, outL, outR));
 }
 
 // ---------------------------------------------------------------------------
@@ -83,15 +83,15 @@ __global__ void __launch_bounds__(256) k_carry_out(uint32_t* __restrict__ carry,
 void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int rowBytes, int C, long long wsRowsPerStream) {
     const long long tot = (long long)S * C * (rowBytes / 4);
     if (tot <= 0) return;
-    k_carry_in<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)ws, (const uint32_t*)carry, S,
-                                                                                       rowBytes / 4, C, wsRowsPerStream);
+    VP_LAUNCH(k_carry_in<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)ws, (const uint32_t*)carry, S,
+                                                                                       rowBytes / 4, C, wsRowsPerStream));
 }
 void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int rowBytes, int C, long long nNew,
                          long long wsRowsPerStream) {
     const long long tot = (long long)S * C * (rowBytes / 4);
     if (tot <= 0) return;
-    k_carry_out<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)carry, (const uint32_t*)ws, S,
-                                                                                        rowBytes / 4, C, nNew, wsRowsPerStream);
+    VP_LAUNCH(k_carry_out<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)carry, (const uint32_t*)ws, S,
+                                                                                        rowBytes / 4, C, nNew, wsRowsPerStream));
 }
 
 // history update: the H input samples that precede the NEXT call = the last H of (old history ++ this call's input)
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_hist_update(float* __restrict__ hNew, c
 void vp_launch_hist_update(cudaStream_t st, float* hNew, const float* hOld, const float* x, int S, int H, long long n,
                            long long stride) {
     const long long tot = (long long)S * H;
-    k_hist_update<<<(unsigned)std::min<long long>((tot + 255) / 256, 8192), 256, 0, st>>>(hNew, hOld, x, S, H, n, stride);
+    VP_LAUNCH(k_hist_update<<<(unsigned)std::min<long long>((tot + 255) / 256, 8192), 256, 0, st>>>(hNew, hOld, x, S, H, n, stride));
 }
 
 // ---------------------------------------------------------------------------
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(32) k_synth(const vp_synth_stream* __restrict_
 
 void vp_launch_synth(cudaStream_t st, const void* streams, int nStreams, long long nSamples, long long stride,
                      float* voice, float* synthL, float* synthR) {
-    k_synth<<<(nStreams + 31) / 32, 32, 0, st>>>((const vp_synth_stream*)streams, nStreams, nSamples, stride, voice,
-                                                 synthL, synthR);
+    VP_LAUNCH(k_synth<<<(nStreams + 31) / 32, 32, 0, st>>>((const vp_synth_stream*)streams, nStreams, nSamples, stride, voice,
+                                                 synthL, synthR));
 }
 
 // ---------------------------------------------------------------------------
@@ -196,15 +196,15 @@ __global__ void __launch_bounds__(256) k_peak2(T* sink, int iters) {
 }
 
 void vp_launch_peak2_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads) {
-    k_peak2<float><<<blocks, threads, 0, st>>>(sink, iters);
+    VP_LAUNCH(k_peak2<float><<<blocks, threads, 0, st>>>(sink, iters));
 }
 void vp_launch_peak2_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads) {
-    k_peak2<double><<<blocks, threads, 0, st>>>(sink, iters);
+    VP_LAUNCH(k_peak2<double><<<blocks, threads, 0, st>>>(sink, iters));
 }
 
 void vp_launch_peak_fp32(cudaStream_t st, float* sink, int iters, int blocks, int threads) {
-    k_peak<float><<<blocks, threads, 0, st>>>(sink, iters);
+    VP_LAUNCH(k_peak<float><<<blocks, threads, 0, st>>>(sink, iters));
 }
 void vp_launch_peak_fp64(cudaStream_t st, double* sink, int iters, int blocks, int threads) {
-    k_peak<double><<<blocks, threads, 0, st>>>(sink, iters);
+    VP_LAUNCH(k_peak<double><<<blocks, threads, 0, st>>>(sink, iters));
 }

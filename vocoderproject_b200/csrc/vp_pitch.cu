@@ -197,8 +197,8 @@ static void yin_dispatch(cudaStream_t st, const VPGeom& g, int S, const float* v
 #define YIN_CASE(RR)                                                                                               \
     case RR:                                                                                                       \
         cudaFuncSetAttribute(k_yin<RR, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);               \
-        k_yin<RR, T><<<grid, threads, smem, st>>>(g, voice, gate, period, yflags, list, listCount, maxList, c.LT, \
-                                                  c.IG, xsLen, fromList);                                          \
+        VP_LAUNCH(k_yin<RR, T><<<grid, threads, smem, st>>>(g, voice, gate, period, yflags, list, listCount, maxList, c.LT, \
+                                                  c.IG, xsLen, fromList));                                          \
         break;
     switch (c.R) {
         YIN_CASE(5) YIN_CASE(7) YIN_CASE(9) YIN_CASE(11) YIN_CASE(13) YIN_CASE(15)
@@ -701,8 +701,8 @@ void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* vo
     long long grid = (long long)nSM * perSM;
     if (grid > nTiles) grid = nTiles;
     if (nTiles >= (1LL << 31)) return;  // cannot happen: the workspace bounds streams x frames per pass far below this
-    k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad, lagBegin,
-                                                         lagEnd, tileList, tileCount);
+    VP_LAUNCH(k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad, lagBegin,
+                                                         lagEnd, tileList, tileCount));
 }
 
 // First lag phase of the two-phase YIN (0 = not applicable: one pass over all lags). Applicable when the register-resident
@@ -725,9 +725,9 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
         if (phase == 1 && kLimit <= 32 * 9) {
             // phase 1 reads lags < kLimit only: 9 lags per lane (odd: conflict-free) instead of 15 -> 0.6 x the instructions
             cudaFuncSetAttribute(k_yin_decide_reg<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            k_yin_decide_reg<9><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
+            VP_LAUNCH(k_yin_decide_reg<9><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
                                                                            recheckList, recheckCount, maxList, kLimit, phase, pendList, pendCount,
-                                                                           tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
+                                                                           tileFlag, tileList, tileCount, vp_yin_corr_tiles(g)));
             return;
         }
         long long grid = (tot + 7) / 8;
@@ -737,16 +737,16 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
             cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
             grid = std::min<long long>(grid, (long long)nSM * 8);
         }
-        k_yin_decide_reg<15><<<(unsigned)grid, 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
+        VP_LAUNCH(k_yin_decide_reg<15><<<(unsigned)grid, 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
                                                              recheckList, recheckCount, maxList, kLimit, phase, pendList, pendCount,
-                                                             tileFlag, tileList, tileCount, vp_yin_corr_tiles(g));
+                                                             tileFlag, tileList, tileCount, vp_yin_corr_tiles(g)));
         return;
     }
     const int tauPad = (g.tauMax + 3) & ~3;
     const size_t smem = (size_t)YD_WARPS * 2 * tauPad * (sizeof(double) + sizeof(float));
     cudaFuncSetAttribute(k_yin_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k_yin_decide<<<(unsigned)((tot + YD_WARPS - 1) / YD_WARPS), 32 * YD_WARPS, smem, st>>>(
-        g, voice, gate, P, Ech, nChunks, lagPad, tauPad, S, period, yflags, recheckList, recheckCount, maxList);
+    VP_LAUNCH(k_yin_decide<<<(unsigned)((tot + YD_WARPS - 1) / YD_WARPS), 32 * YD_WARPS, smem, st>>>(
+        g, voice, gate, P, Ech, nChunks, lagPad, tauPad, S, period, yflags, recheckList, recheckCount, maxList));
 }
 
 // ===========================================================================
@@ -995,8 +995,8 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
                      VPMarkState* carry) {
     const int threads = 128;
     const long long tot = (long long)S * 32;
-    k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * g.L * sizeof(float), st>>>(
-        g, tb, voice, gate, period, yflags, frames, carry, S);
+    VP_LAUNCH(k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * g.L * sizeof(float), st>>>(
+        g, tb, voice, gate, period, yflags, frames, carry, S));
 }
 
 // ===========================================================================
@@ -1385,9 +1385,9 @@ void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* v
     const int xdLen = (PA_SEGS * segLen + 2 * PA_R * groups + 2 * PA_R + 3) & ~1;
     const size_t smem = (size_t)PA_WARPS * xdLen * (sizeof(double) + sizeof(float));  // xd [warps][xdLen] doubles, then the float landing zones
     cudaFuncSetAttribute(k_pitch_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k_pitch_autocorr<<<(unsigned)((tot + PA_WARPS - 1) / PA_WARPS), 32 * PA_WARPS, smem, st>>>(g, voice, frames, rP, segLen, xdLen, tot);
-    if (g.ordP == 15) k_pitch_levinson<15><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot);
-    else k_pitch_levinson<0><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot);
+    VP_LAUNCH(k_pitch_autocorr<<<(unsigned)((tot + PA_WARPS - 1) / PA_WARPS), 32 * PA_WARPS, smem, st>>>(g, voice, frames, rP, segLen, xdLen, tot));
+    if (g.ordP == 15) VP_LAUNCH(k_pitch_levinson<15><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot));
+    else VP_LAUNCH(k_pitch_levinson<0><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot));
 }
 
 void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
@@ -1400,10 +1400,10 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     dim3 grid(g.nFramesP + VP_PC, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_pitch_psola<15><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen);
+        VP_LAUNCH(k_pitch_psola<15><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen));
     } else {
         cudaFuncSetAttribute(k_pitch_psola<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_pitch_psola<0><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen);
+        VP_LAUNCH(k_pitch_psola<0><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen));
     }
 }
 
@@ -1513,6 +1513,6 @@ void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
                          const double* aP, const float* outE, float* outP) {
     const long long tot = (long long)S * (g.nFramesP + VP_PC);
     const unsigned grid = (unsigned)((tot + 32 * PI_WARPS - 1) / (32 * PI_WARPS));
-    if (g.ordP == 15) k_pitch_iir<15><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot);
-    else k_pitch_iir<0><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot);
+    if (g.ordP == 15) VP_LAUNCH(k_pitch_iir<15><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot));
+    else VP_LAUNCH(k_pitch_iir<0><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot));
 }

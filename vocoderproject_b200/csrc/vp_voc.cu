@@ -83,9 +83,9 @@ void vp_launch_gate(cudaStream_t st, const VPGeom& g, int S, const float* voice,
     const int q = g.inSize / g.B, rem = g.inSize - q * g.B;
     const int carry = q + 1;
     dim3 grid(g.nBlocks, S);
-    k_gate_partial<<<grid, 128, 0, st>>>(g, voice, synth, part, rem, carry, partRows);
+    VP_LAUNCH(k_gate_partial<<<grid, 128, 0, st>>>(g, voice, synth, part, rem, carry, partRows));
     const long long tot = (long long)S * g.nBlocks;
-    k_gate_decide<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, part, gate, q, tot, carry, partRows);
+    VP_LAUNCH(k_gate_decide<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, part, gate, q, tot, carry, partRows));
 }
 
 // ---------------------------------------------------------------------------
@@ -339,21 +339,24 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
-    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 ) {
-        FS = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
-        const int ringLen = (g.wlenV + 3) & ~3;  // floats per signal; two signals = ringLen doubles
-        const size_t smem = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS + ringLen)) * sizeof(double);
+    const int FS2 = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
+    const int ringLen = (g.wlenV + 3) & ~3;   // floats per signal; two signals = ringLen doubles
+    const size_t smem2 = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS2 + ringLen)) * sizeof(double);
+    // the streaming form needs its seven warps' windows + rings in shared memory (fits up to 88.2 kHz frames)
+    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 && smem2 <= (size_t)200 * 1024) {
+        FS = FS2;
+        const size_t smem = smem2;
         const int batchesPerStream = (g.nFramesV + AV_BATCH - 1) / AV_BATCH;
         const long long warps = (long long)batchesPerStream * S;
         cudaFuncSetAttribute(k_voc_autocorr2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_voc_autocorr2<<<(unsigned)((warps + AV_WARPS - 1) / AV_WARPS), 32 * AV_WARPS, smem, st>>>(
-            g, tb, voice, synth, rV, rS, segLen, FS, ringLen, batchesPerStream, S);
+        VP_LAUNCH(k_voc_autocorr2<<<(unsigned)((warps + AV_WARPS - 1) / AV_WARPS), 32 * AV_WARPS, smem, st>>>(
+            g, tb, voice, synth, rV, rS, segLen, FS, ringLen, batchesPerStream, S));
         return;
     }
     const size_t smem = (size_t)2 * AC_FRAMES * FS * sizeof(double);
     cudaFuncSetAttribute(k_voc_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid((g.nFramesV + AC_FRAMES - 1) / AC_FRAMES, S);
-    k_voc_autocorr<<<grid, 32 * (Gv + Gs), smem, st>>>(g, tb, voice, synth, rV, rS, segLen, FS, Gv);
+    VP_LAUNCH(k_voc_autocorr<<<grid, 32 * (Gv + Gs), smem, st>>>(g, tb, voice, synth, rV, rS, segLen, FS, Gv));
 }
 
 // ---------------------------------------------------------------------------
@@ -547,11 +550,11 @@ void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb
     {
         const size_t smem = (size_t)LV_THREADS * ((vp_rowlen(40) + vp_rowlen(5)) | 1) * sizeof(double);
         cudaFuncSetAttribute(k_voc_levinson_static<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_voc_levinson_static<40, 5><<<(unsigned)((tot + LV_THREADS - 1) / LV_THREADS), LV_THREADS, smem, st>>>(
-            g, tb, voice, synth, gate, rV, rS, aV, aS, EeV, EeS, tot);
+        VP_LAUNCH(k_voc_levinson_static<40, 5><<<(unsigned)((tot + LV_THREADS - 1) / LV_THREADS), LV_THREADS, smem, st>>>(
+            g, tb, voice, synth, gate, rV, rS, aV, aS, EeV, EeS, tot));
     }
     else
-        k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, gate, rV, rS, aV, aS, EeV, EeS, S);
+        VP_LAUNCH(k_voc_levinson<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, tb, gate, rV, rS, aV, aS, EeV, EeS, S));
 }
 
 // ---------------------------------------------------------------------------
@@ -621,8 +624,8 @@ __global__ void __launch_bounds__(64) k_voc_gain_carry(VPGeom g, const double* _
 void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* EeV, const double* EeS, double* G, double* Gs,
                         double* hist) {
     const long long tot = (long long)S * g.nFramesV;
-    if (tot > 0) k_voc_gain<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, EeV, EeS, G, Gs, hist, tot);
-    k_voc_gain_carry<<<(S + 63) / 64, 64, 0, st>>>(g, EeV, EeS, hist, S);
+    if (tot > 0) VP_LAUNCH(k_voc_gain<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, EeV, EeS, G, Gs, hist, tot));
+    VP_LAUNCH(k_voc_gain_carry<<<(S + 63) / 64, 64, 0, st>>>(g, EeV, EeS, hist, S));
 }
 
 // ---------------------------------------------------------------------------
@@ -949,8 +952,8 @@ void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
         const size_t smem = ((size_t)4 * rowPad + (size_t)VT_WARPS * 32 * cfStride) * sizeof(double);
         const long long warps = (long long)groups * nSeg;
         cudaFuncSetAttribute(k_voc_synth_stream<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
-            g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, rowPad);
+        VP_LAUNCH(k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
+            g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, rowPad));
         return;
     }
     const int tilesPerStream = (g.nFramesV + VP_VC + 31) / 32;
@@ -962,5 +965,5 @@ void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
     const unsigned grid = (unsigned)((tiles + VS_WARPS - 1) / VS_WARPS);
     const size_t smem = (size_t)VS_WARPS * 2 * spanPad * sizeof(float);
     cudaFuncSetAttribute(k_voc_synth_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, aV, aS, EeS, G, outV, tilesPerStream, S, spanPad, sk);
+    VP_LAUNCH(k_voc_synth_generic<<<grid, 32 * VS_WARPS, smem, st>>>(g, tb, synth, aV, aS, EeS, G, outV, tilesPerStream, S, spanPad, sk));
 }
