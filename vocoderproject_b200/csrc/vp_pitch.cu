@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
                                                              double* __restrict__ Ech, int nChunks, int lagPad,
                                                              int tilesPerStream, long long nTiles, int spanPad, int lagBegin,
                                                              int lagEnd, const int* __restrict__ tileList,
-                                                             const int* __restrict__ tileCount) {
+                                                             const int* __restrict__ tileCount, int pairLags) {
     extern __shared__ float xsAll[];  // 2 x [spanPad]; spanPad = 2 sub-spans of subPad floats
     const int c = g.c, tauMax = g.tauMax;
     // A tile = 2 groups of YC_CH consecutive chunks. Warp w works on chunk w of BOTH groups at once: its lower half-warp on
@@ -252,17 +252,20 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
     // 32-lane pass over one chunk would, so the lag range can be cut in two phases at no loss. Each group is staged as its
     // own sub-span (its chunks + the lag tail); group 1's starts 16 banks after group 0's so that the two half-warps' window
     // loads (lane stride YC_R floats, odd) never meet in a bank.
+    // pairLags (one pass over all lags: single-phase calls, streaming blocks): a tile is ONE group of YC_CH chunks and the
+    // two half-warps of a warp split the lag range of the same chunk instead (lags k and k + YC_LAGS / 2 are 16 banks apart).
     const int sub = YC_CH * c + lagPad + 16;
     const int subPad = spanPad >> 1;
+    const int tileChunks = pairLags ? YC_CH : 2 * YC_CH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // with a tile list (second lag phase) the persistent loop runs over the listed tiles only
     const long long nWork = tileList ? (long long)*tileCount : nTiles;
     auto tileOf = [&](long long i) -> long long { return tileList ? (long long)tileList[i] : i; };
     auto issue = [&](long long tile, float* dst) {
         const int s = (int)((unsigned)tile / (unsigned)tilesPerStream);  // tile < 2^31 (checked by the launcher)
-        const int m0 = (int)((unsigned)tile - (unsigned)s * (unsigned)tilesPerStream) * (2 * YC_CH);
+        const int m0 = (int)((unsigned)tile - (unsigned)s * (unsigned)tilesPerStream) * tileChunks;
         const VPRow v = vp_row(voice, g.histV, s, g);
-        for (int grp = 0; grp < 2; ++grp) {
+        for (int grp = 0; grp < (pairLags ? 1 : 2); ++grp) {
             const long long t0 = (long long)(m0 + grp * YC_CH) * c + g.offP - tauMax - g.lat;  // (call-local) input index of the sub-span's first sample
             float* d = dst + grp * subPad;
             if (t0 >= 0 && t0 + sub <= g.n) {  // common case: the sub-span lies inside this call's input
@@ -292,19 +295,20 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
         else __pipeline_wait_prior(0);
         __syncthreads();
         const int s = (int)((unsigned)tile / (unsigned)tilesPerStream);
-        const int m = (int)((unsigned)tile - (unsigned)s * (unsigned)tilesPerStream) * (2 * YC_CH) + half * YC_CH + warp;  // this half-warp's chunk
+        const int m = (int)((unsigned)tile - (unsigned)s * (unsigned)tilesPerStream) * tileChunks + (pairLags ? 0 : half * YC_CH) + warp;  // this half-warp's chunk
         const bool live = m < nChunks;
         {
-            const float* xa = xs + half * subPad + warp * c;
+            const float* xa = xs + (pairLags ? 0 : half * subPad) + warp * c;
             float* out = P + ((size_t)s * nChunks + (live ? m : 0)) * (size_t)lagPad;
             if (lagBegin == 0) {  // chunk energy sum_j x[j]^2 in FP64 (exact products): A and B(k) of the decision kernel build on it
                 double e2 = 0.0;
                 for (int n = lg; n < c; n += 16) { const double x = (double)xa[n]; e2 = fma(x, x, e2); }
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-                if (lg == 0 && live) Ech[(size_t)s * nChunks + m] = e2;
+                if (lg == 0 && live && !(pairLags && half)) Ech[(size_t)s * nChunks + m] = e2;
             }
-            for (int k0 = lagBegin + lg * YC_R; k0 < lagEnd; k0 += YC_LAGS / 2) {
+            const int kStep = pairLags ? YC_LAGS : YC_LAGS / 2;
+            for (int k0 = lagBegin + (pairLags ? half * (YC_LAGS / 2) : 0) + lg * YC_R; k0 < lagEnd; k0 += kStep) {
                 const float* xw = xa + k0;
                 float acc[YC_R], acc2[YC_R], W[YC_R];
 #pragma unroll
@@ -688,9 +692,12 @@ void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* vo
     const int subPad = ((YC_CH * g.c + lagPad + 16 + 31) & ~31) + 16;
     const int spanPad = 2 * subPad;
     const size_t smem = (size_t)2 * spanPad * sizeof(float);
-    const int tilesPerStream = vp_yin_corr_tiles(g);
-    const long long nTiles = (long long)tilesPerStream * S;
     if (lagEnd <= 0 || lagEnd > lagPad) lagEnd = lagPad;
+    // one pass over every lag of every tile: half-warps split the lags of one chunk (tile = YC_CH chunks); lag phases: half-
+    // warps take two chunk groups (tile = 2 YC_CH chunks, what vp_yin_corr_tiles counts)
+    const int pairLags = (lagBegin == 0 && lagEnd == lagPad && !tileList) ? 1 : 0;
+    const int tilesPerStream = pairLags ? (nChunks + YC_CH - 1) / YC_CH : vp_yin_corr_tiles(g);
+    const long long nTiles = (long long)tilesPerStream * S;
     cudaFuncSetAttribute(k_yin_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int perSM = 4;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_yin_corr, 32 * YC_CH, smem);
@@ -702,7 +709,7 @@ void vp_launch_yin_corr(cudaStream_t st, const VPGeom& g, int S, const float* vo
     if (grid > nTiles) grid = nTiles;
     if (nTiles >= (1LL << 31)) return;  // cannot happen: the workspace bounds streams x frames per pass far below this
     VP_LAUNCH(k_yin_corr<<<(unsigned)grid, 32 * YC_CH, smem, st>>>(g, voice, P, Ech, nChunks, lagPad, tilesPerStream, nTiles, spanPad, lagBegin,
-                                                         lagEnd, tileList, tileCount));
+                                                         lagEnd, tileList, tileCount, pairLags));
 }
 
 // First lag phase of the two-phase YIN (0 = not applicable: one pass over all lags). Applicable when the register-resident
