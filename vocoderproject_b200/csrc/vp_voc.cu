@@ -199,14 +199,15 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 // runs lane = (segment of 8) x (lag group of 4: voice lags 0-13, 14-27, 28-41, side-chain lags 0-13) with the same
 // register-window task as above. Only warp-level synchronisation.
 // ---------------------------------------------------------------------------
-#define AV_WARPS 7   // 7 x 14.4 KB + window: two CTAs per SM = 14 warps
-#define AV_BATCH 32  // consecutive frames per warp: the initial ring fill is paid once per batch
+#define AV_WARPS 10  // 10 x 10.3 KB + window: two CTAs per SM = 20 warps (registers capped at 102 by the launch bounds)
+#define AV_BATCH 32  // consecutive frames per warp (cache locality of the 4x overlapping frame reads)
 
-// A warp keeps the raw samples of its current frame in a ring of wlen = 4 hop floats per signal (position u lives at
-// u mod wlen). Once frame k's windowed copies are built, the ring's oldest hop entries are dead: the hop NEW samples of
-// frame k+1 land there as asynchronous copies (cp.async) while frame k is being correlated. Global latency is hidden
-// behind the FP64 work and every input sample is loaded exactly once per batch.
-__global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTables tb, const float* __restrict__ voice,
+// A warp walks AV_BATCH consecutive frames of one stream and builds each frame's windowed FP64 copies straight from global
+// memory (a sample is read by the 4 frames that overlap it, back to back by the same warp: L1 / L2 hits). An earlier
+// version kept the raw samples in a shared-memory ring (every sample loaded once); dropping it cut the warp's shared
+// memory from 14.7 to 10.3 KB, i.e. 20 instead of 14 resident warps per SM, and that is worth more (143 -> 130 ms): with
+// 3-4 warps per scheduler the FP64 pipe idles whenever all of them are in a non-DFMA stretch.
+__global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                                  const float* __restrict__ synth, double* __restrict__ rV,
                                                                  double* __restrict__ rS, int segLen, int FS, int ringLen,
                                                                  int batchesPerStream, int S) {
@@ -222,8 +223,6 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
     const int k0 = (int)(wid - (long long)s * batchesPerStream) * AV_BATCH;
     double* xw = sm + ((wlen + 1) & ~1) + (size_t)warp * (2 * FS + ringLen);  // [FS] voice * window (zero padded)
     double* sw = xw + FS;                                                     // [FS] synth ch0 * window
-    float* ringV = (float*)(sw + FS);                                         // [wlen]
-    float* ringS = ringV + ringLen;                                           // [wlen]   (2 * ringLen floats = ringLen doubles)
     const VPRow v = vp_row(voice, g.histV, s, g), y = vp_row(synth, g.histS, s, g);
     for (int j = wlen + lane; j < FS; j += 32) { xw[j] = 0.0; sw[j] = 0.0; }
     const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;  // grp 0..2: voice lag groups, grp 3: side-chain
@@ -232,76 +231,32 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
     // loads of two groups on disjoint banks (segLen = 2 mod 4 puts the 8 segments on the 8 even / 8 odd banks)
     const int m0 = (grp == 1) ? AC_R - 1 : (grp == 2) ? 2 * AC_R - 1 : 0;
     const int order = (grp < 3) ? g.ordV : g.ordS;
-    // ---- initial fill: frame k0 occupies ring positions (k0 hop + j) mod wlen
-    {
-        const long long u0 = (long long)k0 * hop + g.offV;
-        const int r0 = (int)(((long long)k0 * hop) % wlen);
-        // positions are contiguous modulo the ring: stage linearly, then the index wraps
-        for (int base = lane; base < wlen; base += 32 * 6) {
-            float tv[6], ts[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const int j = base + q * 32;
-                tv[q] = (j < wlen) ? vp_x(v, u0 + j, g) : 0.0f;
-                ts[q] = (j < wlen) ? vp_x(y, u0 + j, g) : 0.0f;
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const int j = base + q * 32;
-                if (j < wlen) { int idx = r0 + j; if (idx >= wlen) idx -= wlen; ringV[idx] = tv[q]; ringS[idx] = ts[q]; }
-            }
-        }
-    }
     for (int fb = 0; fb < AV_BATCH; ++fb) {
         const int k = k0 + fb;
         if (k >= g.nFramesV) break;
         const long long u0 = (long long)k * hop + g.offV;
-        const int r0 = (int)(((long long)k * hop) % wlen);
-        const bool more = (fb + 1 < AV_BATCH) && (k + 1 < g.nFramesV);
         __syncwarp();
-        // ---- windowed FP64 copies from the ring
-        {   // two spans, each linear in the ring (no wrap test per element): j in [0, wlen - r0) and [wlen - r0, wlen)
-            const int split = wlen - r0;
-            const float* rv = ringV + r0;
-            const float* rs = ringS + r0;
+        // ---- windowed FP64 copies straight from global memory (L1 / L2: a sample is read by 4 consecutive frames)
+        {
+            const long long t0 = u0 - g.lat;
+            if (t0 >= 0 && t0 + wlen <= g.n) {
+                const float* pv = v.x + t0;
+                const float* ps = y.x + t0;
 #pragma unroll 6
-            for (int j = lane; j < split; j += 32) {
-                const double w = wv[j];
-                xw[j] = (double)rv[j] * w;
-                sw[j] = (double)rs[j] * w;
-            }
-            rv = ringV - split;
-            rs = ringS - split;
-            const int jb = split + ((lane - split) & 31);  // first j >= split with j = lane (mod 32)
-#pragma unroll 6
-            for (int j = jb; j < wlen; j += 32) {
-                const double w = wv[j];
-                xw[j] = (double)rv[j] * w;
-                sw[j] = (double)rs[j] * w;
-            }
-        }
-        __syncwarp();
-        // ---- the ring's oldest hop entries are dead now: the hop NEW samples of frame k+1 (positions u0 + wlen ..
-        // u0 + wlen + hop) land there as asynchronous copies while this frame is being correlated
-        if (more) {
-            const long long t0 = u0 + wlen - g.lat;  // input index of the first new sample
-            if (t0 >= 0 && t0 + hop <= g.n) {        // common case: entirely inside this call's input
-                for (int j = lane; j < hop; j += 32) {
-                    int idx = r0 + j;
-                    if (idx >= wlen) idx -= wlen;
-                    __pipeline_memcpy_async(ringV + idx, v.x + t0 + j, 4);
-                    __pipeline_memcpy_async(ringS + idx, y.x + t0 + j, 4);
+                for (int j = lane; j < wlen; j += 32) {
+                    const double w = wv[j];
+                    xw[j] = (double)__ldg(pv + j) * w;
+                    sw[j] = (double)__ldg(ps + j) * w;
                 }
             } else {
-                for (int j = lane; j < hop; j += 32) {
-                    int idx = r0 + j;
-                    if (idx >= wlen) idx -= wlen;
-                    ringV[idx] = vp_x(v, u0 + wlen + j, g);
-                    ringS[idx] = vp_x(y, u0 + wlen + j, g);
+                for (int j = lane; j < wlen; j += 32) {
+                    const double w = wv[j];
+                    xw[j] = (double)vp_x(v, u0 + j, g) * w;
+                    sw[j] = (double)vp_x(y, u0 + j, g) * w;
                 }
             }
         }
-        __pipeline_commit();
+        __syncwarp();
         double acc[AC_R];
         ac_task<AC_R>(sig, seg * segLen, segLen, m0, acc);
 #pragma unroll
@@ -325,7 +280,6 @@ __global__ void __launch_bounds__(32 * AV_WARPS) k_voc_autocorr2(VPGeom g, VPTab
         // the frame's last `order` windowed samples, appended to its row (coalesced)
         for (int t = lane; t < g.ordV; t += 32) rowV[g.ordV + 1 + t] = (wlen - g.ordV + t >= 0) ? xw[wlen - g.ordV + t] : 0.0;
         for (int t = lane; t < g.ordS; t += 32) rowS[g.ordS + 1 + t] = (wlen - g.ordS + t >= 0) ? sw[wlen - g.ordS + t] : 0.0;
-        __pipeline_wait_prior(0);  // frame k+1's samples are in the ring
         __syncwarp();
     }
 }
@@ -340,7 +294,7 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
     const int FS2 = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
-    const int ringLen = (g.wlenV + 3) & ~3;   // floats per signal; two signals = ringLen doubles
+    const int ringLen = 0;   // (no raw-sample ring any more: see k_voc_autocorr2)
     const size_t smem2 = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS2 + ringLen)) * sizeof(double);
     // the streaming form needs its seven warps' windows + rings in shared memory (fits up to 88.2 kHz frames)
     if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 && smem2 <= (size_t)200 * 1024) {
