@@ -1427,7 +1427,7 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
 #define PI_WARPS 2
 
 template <int P>
-__global__ void __launch_bounds__(32 * PI_WARPS) k_pitch_iir(VPGeom g, VPTables tb, const vp_pitch_frame* __restrict__ frames,
+__global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTables tb, const vp_pitch_frame* __restrict__ frames,
                                                              const double* __restrict__ aP, const float* __restrict__ outE,
                                                              float* __restrict__ outP, long long nFramesTot) {
     __shared__ float tin[PI_WARPS][2][32][33];
