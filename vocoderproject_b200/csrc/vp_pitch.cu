@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch
 
 // P > 0: LPC order known at compile time (coefficients and the residual window live in registers); P == 0: any order.
 template <int P>
-__global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTables tb, const float* __restrict__ voice,
+__global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                             vp_pitch_frame* __restrict__ frames,
                                                             const double* __restrict__ aP, float* __restrict__ outE,
                                                             int xLen, int eLen) {
@@ -1206,8 +1206,7 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
     double* e = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smd) + 15) & ~(uintptr_t)15);  // [eLen + pad] residual, e[j] <-> frame-relative idx j - tauMax
-    double* hs = e + ((eLen + PF_XPAD + 1) & ~1);  // [2 tauMax + 2] Hann table of this frame's period (PitchProcess.cpp:878-882)
-    float* xfBase = (float*)(hs + 2 * tauMax + 2);  // 16-byte aligned; [xLen + pad] floats; dead after the residual -> oE [L] doubles
+    float* xfBase = (float*)(e + ((eLen + PF_XPAD + 1) & ~1));  // 16-byte aligned; [xLen + pad] floats; dead after the residual -> oE [L] doubles
     double* oE = (double*)xfBase;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
     const VPRow v = vp_row(voice, g.histV, s, g);
@@ -1239,10 +1238,9 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
     if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; }
     const double* ap = aP + fidx * (size_t)(ord + 1);
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
-    if (T > 0 && T < tauMax) {
-        const double* __restrict__ hg = tb.hann + tb.hannOff[T];
-        for (int i = tid; i < 2 * T + 1; i += PF_THREADS) __pipeline_memcpy_async(hs + i, hg + i, 8);
-    }
+    // Hann table of this frame's period (PitchProcess.cpp:878-882): read in place (one table per period, shared by every
+    // frame with that period: cache resident) -- a private shared copy would cost a CTA slot per SM
+    const double* __restrict__ hs = tb.hann + ((T > 0 && T < tauMax) ? tb.hannOff[T] : 0);
     __pipeline_commit();
     __syncthreads();  // marks visible; the staging copies are still in flight under the grain table
     // ---- PSOLA (PitchProcess.cpp:665-741, :788-870). Grain table first: thread m prepares synthesis mark m -- the
@@ -1367,11 +1365,11 @@ __global__ void __launch_bounds__(PF_THREADS, 6) k_pitch_psola(VPGeom g, VPTable
                 j = max(0, min(j, 2 * T));
                 const int ej = eBase + j;
                 double y1 = (ej >= 0 && j < jLim) ? e[ej] : 0.0;
-                if (inner || (first ? (j >= T) : (j < T))) y1 *= hs[j];
+                if (inner || (first ? (j >= T) : (j < T))) y1 *= __ldg(hs + j);
                 double val = y1;
                 if (j > 0) {
                     double y0 = (ej >= 1 && j - 1 < jLim) ? e[ej - 1] : 0.0;
-                    if (inner || (first ? (j - 1 >= T) : (j - 1 < T))) y0 *= hs[j - 1];
+                    if (inner || (first ? (j - 1 >= T) : (j - 1 < T))) y0 *= __ldg(hs + j - 1);
                     val = fma(y1 - y0, tg - (double)(j - 1), y0);
                 }
                 oE[i] += val;
@@ -1403,7 +1401,7 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     int xLen = g.tauMax + g.ordP + g.L + 3 * g.c;  // frame-relative [-tauMax - ord, L + 3c)
     xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
     xLen = (xLen + 3) & ~3;
-    const size_t smem = (size_t)(((eLen + PF_XPAD + 1) & ~1) + 2 * g.tauMax + 2) * sizeof(double) + (size_t)(xLen + PF_XPAD + 4) * sizeof(float) + 16;
+    const size_t smem = (size_t)((eLen + PF_XPAD + 1) & ~1) * sizeof(double) + (size_t)(xLen + PF_XPAD + 4) * sizeof(float) + 16;
     dim3 grid(g.nFramesP + VP_PC, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
