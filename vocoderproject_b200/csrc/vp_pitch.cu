@@ -1053,27 +1053,17 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
     double* xd = smd + (size_t)warp * xdLen;  // frame samples as double, zero beyond L (rectangular window, LPC.cpp:44-97)
     const VPRow v = vp_row(voice, g.histV, s, g);
     const long long p = (long long)f * g.hopP + g.offP;
-    {   // frame samples: asynchronous 4-byte copies into the warp's float buffer (all in flight at once, zero fill outside
-        // the carried history / this call's input), then one conversion pass to double
-        float* xf = reinterpret_cast<float*>(smd + (size_t)PA_WARPS * xdLen) + (size_t)warp * xdLen;
+    {   // frame samples -> double. Common case (frame inside this call's input): plain coalesced loads, 8 in flight per lane.
+        // No float landing zone in shared memory: the 9.5 KB of xd per warp alone decide how many warps an SM holds.
         const long long t0 = p - g.lat;
         if (t0 >= 0 && t0 + L <= g.n) {
             const float* src = v.x + t0;
-            for (int j = lane; j < L; j += 32) __pipeline_memcpy_async(xf + j, src + j, 4);
+#pragma unroll 8
+            for (int j = lane; j < L; j += 32) xd[j] = (double)__ldg(src + j);
         } else {
-            for (int j = lane; j < L; j += 32) {
-                const long long t = t0 + j;
-                const bool ok = t >= -(long long)g.H && t < g.n;
-                const float* src = (t >= 0) ? v.x + (ok ? t : 0) : v.h + (ok ? g.H + t : 0);
-                __pipeline_memcpy_async(xf + j, src, 4, ok ? 0 : 4);
-            }
+            for (int j = lane; j < L; j += 32) xd[j] = (double)vp_x(v, p + j, g);
         }
-        __pipeline_commit();
         for (int j = L + lane; j < xdLen; j += 32) xd[j] = 0.0;
-        __pipeline_wait_prior(0);
-        __syncwarp();
-#pragma unroll 4
-        for (int j = lane; j < L; j += 32) xd[j] = (double)xf[j];
     }
     __syncwarp();
     const int seg = lane & (PA_SEGS - 1), half = lane >> 4;
@@ -1388,7 +1378,7 @@ void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* v
     if ((segLen & 1) == 0) ++segLen;  // odd -> the 16 segments of a half-warp hit 16 distinct 64-bit banks
     const int groups = (g.ordP + 1 + 2 * PA_R - 1) / (2 * PA_R);
     const int xdLen = (PA_SEGS * segLen + 2 * PA_R * groups + 2 * PA_R + 3) & ~1;
-    const size_t smem = (size_t)PA_WARPS * xdLen * (sizeof(double) + sizeof(float));  // xd [warps][xdLen] doubles, then the float landing zones
+    const size_t smem = (size_t)PA_WARPS * xdLen * sizeof(double);
     cudaFuncSetAttribute(k_pitch_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     VP_LAUNCH(k_pitch_autocorr<<<(unsigned)((tot + PA_WARPS - 1) / PA_WARPS), 32 * PA_WARPS, smem, st>>>(g, voice, frames, rP, segLen, xdLen, tot));
     if (g.ordP == 15) VP_LAUNCH(k_pitch_levinson<15><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(g, frames, rP, aP, tot));
