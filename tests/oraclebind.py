@@ -26,7 +26,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB):
+    src = os.path.join(ROOT, "oracle", "vp_oracle.c")
+    if not os.path.exists(LIB) or os.path.getmtime(src) > os.path.getmtime(LIB):
         build()
     lib = C.CDLL(LIB)
     fp = C.POINTER(C.c_float)
