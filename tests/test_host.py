@@ -42,6 +42,34 @@ def test_facade_mirrors_the_reference_interface():
             assert "%s(" % m in body, (cls, m)
 
 
+def test_facade_notes_equals_reference_notes(oracle, tmp_path):
+    """vpb200::Notes (host side of the facade, the reference's Notes interface) against the oracle's table and -- where
+    oracle/_ref is built -- the reference's own Notes::getClosestFreq, for every key, bit for bit."""
+    import refbind
+    exe = str(tmp_path / "notes_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(ROOT, "vocoderproject_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "adapter", "notes_check.cpp"), "-o", exe])
+    pitches = [90.0, 100.0, 109.99, 110.0, 116.54, 123.0, 220.0, 233.08, 246.9, 440.0, 452.9, 783.99, 790.0, 801.8, 900.0]
+    for key in range(13):
+        out = subprocess.run([exe, str(key), "100", "800"] + [repr(p) for p in pitches], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        vals = out.stdout.split()
+        n = int(vals[0])
+        table, popped = oracle.notes_table(key)
+        assert n == len(table)
+        assert [float(v) for v in vals[1:1 + n]] == list(table)
+        assert float(vals[1 + n]) == popped
+        got = [float(v) for v in vals[2 + n:2 + n + len(pitches)]]
+        if refbind.available("strict"):
+            lib = refbind.load("strict")
+            assert got == [lib.vpref_closest_freq(key, 100.0, 800.0, p) for p in pitches]
+        # key change: the table of the new key
+        k2 = (key + 5) % 13
+        t2, _ = oracle.notes_table(k2)
+        assert int(vals[-1]) == len(t2)
+        assert float(vals[-2]) in list(t2)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("K", [1, 4])
 def test_cpp_host_block_by_block_equals_python_batch(vp, host, K):
