@@ -1178,7 +1178,7 @@ __global__ void __launch_bounds__(128) k_pitch_levinson(VPGeom g, const vp_pitch
 }
 
 #define PF_THREADS 128
-#define PF_RJ 11  // residual outputs per thread and pass (odd stride: conflict-free window loads)
+#define PF_RJ 9  // residual outputs per thread and pass (odd stride: conflict-free window loads)
 #define PF_XPAD 32  // zero floats after the staged frame / spare doubles after the residual (>= 2 PF_RJ)
 
 // P > 0: LPC order known at compile time (coefficients and the residual window live in registers); P == 0: any order.
