@@ -65,21 +65,47 @@ def oracle_decisions(plog):
     return rows
 
 
+class Decisions(tuple):
+    """(n, bad, flagged, first, checked, excused) of compare_decisions; fields by name as well."""
+    __slots__ = ()
+    _names = ("n", "bad", "flagged", "first", "checked", "excused")
+
+    def __new__(cls, *vals):
+        return tuple.__new__(cls, vals)
+
+    def __getattr__(self, k):
+        try:
+            return self[self._names.index(k)]
+        except ValueError:
+            raise AttributeError(k)
+
+
+RESYNC_FRAMES = 2     # agreeing frames after a flagged one before the comparison is trusted again
+PROBATION_FRAMES = 8  # frames after such a re-synchronisation in which a difference re-opens the excused stretch
+
+
 def compare_decisions(vp, ref_rows, eng_frames):
-    """Bit-exact comparison of the integer decisions (period, snapped note, marks).
-    Returns (n_frames, n_mismatch, n_flagged, first_mismatch_text). Frames the engine flags as
-    within epsilon of a decision boundary (or UB in the reference) are excluded, and so is everything
-    after the first such frame of a stream: the mark chain carries state from frame to frame."""
+    """Bit-exact comparison of the integer decisions (period, snapped note, marks) of one stream.
+
+    Returns Decisions(n, bad, flagged, first, checked, excused):
+      n        frames present on both sides,
+      flagged  frames the engine flags as within epsilon of a decision boundary, or as undefined behaviour in the
+               reference (not compared: the reference's own answer is not authoritative there),
+      checked  frames compared AND counted: every caller asserts checked >= CHECKED_FLOOR * n, so a test cannot pass
+               with most of a stream unchecked,
+      bad      compared frames that differ,
+      excused  frames after a flagged one that differ before the two mark chains agree again (the chain carries state
+               from frame to frame; once RESYNC_FRAMES consecutive frames agree in every field the comparison resumes),
+      first    text of the first mismatch."""
     n = min(len(ref_rows), len(eng_frames))
-    bad = flagged = 0
+    bad = flagged = checked = excused = 0
     first = None
-    tainted = False
+    taint = probation = 0
     for i in range(n):
         a, b = ref_rows[i], eng_frames[i]
         if b.flags & (vp.PF_NEAR_YIN | vp.PF_NEAR_GATE | vp.PF_UB):
             flagged += 1
-            tainted = True
-        if tainted:
+            taint = RESYNC_FRAMES
             continue
         gated = 1 if (b.flags & vp.PF_GATED) else 0
         ok = a["gated"] == gated
@@ -88,13 +114,40 @@ def compare_decisions(vp, ref_rows, eng_frames):
                   a["note"] == b.note and a["stale"] == b.anStale)
             if ok and a["an"]:
                 ok = a["periodNew"] == b.periodNew and a["beta"] == b.beta
+        if taint > 0:
+            if ok:
+                taint -= 1
+                checked += 1
+                if taint == 0:
+                    probation = PROBATION_FRAMES
+            else:
+                excused += 1
+                taint = RESYNC_FRAMES
+            continue
+        if not ok and probation > 0:
+            excused += 1
+            taint = RESYNC_FRAMES
+            probation = 0
+            continue
+        probation = max(0, probation - 1)
+        checked += 1
         if not ok:
             bad += 1
             if first is None:
                 first = "frame %d ref %r | eng flags=%d period=%d pnew=%d note=%d an=%r st=%r stale=%d beta=%r" % (
                     i, a, b.flags, b.period, b.periodNew, b.note, list(b.anMarks[:b.nAn]), list(b.stMarks[:b.nSt]),
                     b.anStale, b.beta)
-    return n, bad, flagged, first
+    return Decisions(n, bad, flagged, first, checked, excused)
+
+
+CHECKED_FLOOR = 0.98
+
+
+def assert_decisions(dec, what=""):
+    """0 mismatches and at least CHECKED_FLOOR of the frames actually compared."""
+    assert dec.bad == 0, "%s: %s" % (what, dec.first)
+    assert dec.checked >= CHECKED_FLOOR * dec.n, "%s: only %d of %d frames compared (%d flagged, %d excused)" % (
+        what, dec.checked, dec.n, dec.flagged, dec.excused)
 
 
 def golden_index():

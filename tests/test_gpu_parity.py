@@ -14,7 +14,7 @@ import pytest
 
 import refbind
 from cases import CASES, KAT, KAT_BETA, KAT_MARKS, KAT_NOTE, KAT_PERIOD, KAT_PERIODNEW, case_inputs, case_schedule
-from common import MAXABS_MAX, SNR_MIN_DB, compare_decisions, golden_index, golden_load, kat_inputs, maxabs, oracle_decisions, snr_db, stats
+from common import MAXABS_MAX, SNR_MIN_DB, assert_decisions, compare_decisions, golden_index, golden_load, kat_inputs, maxabs, oracle_decisions, snr_db, stats
 
 pytestmark = pytest.mark.gpu
 
@@ -96,10 +96,10 @@ def test_engine_matches_reference_golden(vp, name):
         assert_audio(g["outL"], outL[0], name + " L")
         assert_audio(g["outR"] if len(g["outR"]) else g["outL"], outR[0], name + " R")
         if case["params"].get("pitchBool", 1):
-            n, bad, flagged, first = compare_decisions(vp, golden_rows(g), eng.pitch_frames(0))
-            assert n == golden_index()[name]["pitch_frames"]
-            assert bad == 0, first
-            assert flagged <= max(1, n // 50)
+            dec = compare_decisions(vp, golden_rows(g), eng.pitch_frames(0))
+            assert dec.n == golden_index()[name]["pitch_frames"]
+            assert_decisions(dec, name)
+            assert dec.flagged <= max(1, dec.n // 50)
         if case["params"].get("vocBool", 1):
             vf = eng.voc_frames(0)
             assert list(vf["gated"]) == list(g["vocGated"])
@@ -159,9 +159,9 @@ def test_engine_matches_oracle(vp, oracle, fs, B, S, secs, flavour, params):
             assert_audio(r["outL"], outL[s], "stream %d L" % s)
             assert_audio(r["outR"], outR[s], "stream %d R" % s)
             if params.get("pitchBool", 1):
-                n_, b_, f_, first = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s))
-                assert b_ == 0, "stream %d: %s" % (s, first)
-                tot += n_; bad += b_; flg += f_
+                dec = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s))
+                assert_decisions(dec, "stream %d" % s)
+                tot += dec.n; bad += dec.bad; flg += dec.flagged
         assert flg <= max(1, tot // 100)
     finally:
         eng.close()
@@ -350,9 +350,9 @@ def test_many_streams_spot_parity(vp, oracle):
         for s in (0, 1, 255, 256, 511, 777, 1023):
             r = oracle.run(fs, B, voice[s], sl[s], params=refbind.default_params(), log=True)
             assert_audio(r["outL"], outL[s], "stream %d" % s)
-            n_, b_, f_, first = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s))
-            assert b_ == 0, "stream %d: %s" % (s, first)
-            tot += n_; flg += f_
+            dec = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s))
+            assert_decisions(dec, "stream %d" % s)
+            tot += dec.n; flg += dec.flagged
         assert flg <= 2
         st = eng.stats()
         assert st["kernel_launches"] >= 10 and st["yin_frames"] == S * len(eng.pitch_frames(0))
@@ -401,9 +401,9 @@ def test_voiced_silent_voiced_transitions(vp, oracle):
         assert_audio(r["outL"], outL[0], "voiced-silent-voiced")
         rows = oracle_decisions(r["pitch"])
         assert sum(x["gated"] for x in rows) > 20 and rows[-1]["period"] > 0
-        n_, bad, flagged, first = compare_decisions(vp, rows, eng.pitch_frames(0))
-        assert bad == 0, first
-        assert flagged <= 3
+        dec = compare_decisions(vp, rows, eng.pitch_frames(0))
+        assert_decisions(dec, "voiced-silent-voiced")
+        assert dec.flagged <= 3
         vf = eng.voc_frames(0)
         assert list(vf["gated"]) == [x.gated for x in r["voc"]]
     finally:
