@@ -116,6 +116,9 @@ int vp_engine_prepare(vp_engine* e, double sampleRate, int samplesPerBlock, int 
  * (as in the reference, PitchProcess.cpp:70). */
 int vp_engine_set_params(vp_engine* e, const vp_params* p);
 int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out);
+/* Layout the engine chose in vp_engine_prepare: streams processed per pass (nStreams / streamsPerPass passes per call),
+ * carried input history per stream (samples) and the device workspace in use. Any pointer may be NULL. */
+int vp_engine_get_info(const vp_engine* e, int* streamsPerPass, int* historySamples, size_t* workspaceBytes);
 
 /* Back to the state right after vp_engine_prepare (= prepareToPlay): rings cleared, histories and pitch marks
  * forgotten, block counter 0. Consecutive vp_engine_process_* calls otherwise CONTINUE the streams: calling with
@@ -127,10 +130,18 @@ int vp_engine_reset(vp_engine* e);
 /* Device-resident batch. Layouts (row stride = strideSamples floats):
  *   voice  [nStreams][stride]   synthL, synthR [nStreams][stride]
  *   outL, outR [nStreams][stride]
- * synthR may be NULL when gainSynth <= -59 dB (the vocoder analyses channel 0
- * only, VocoderProcess.cpp:211,218). outR may be NULL (then only L is written;
- * L == R whenever gainSynth <= -59 dB). Asynchronous on the engine's stream;
- * vp_engine_sync waits. */
+ * synthR may be NULL: the right side-chain channel then equals the left one (the
+ * vocoder analyses channel 0 only, VocoderProcess.cpp:211,218; channel 1 is only
+ * heard through the dry side-chain mix, gainSynth > -59 dB). When it is given its
+ * ring is carried on every call whatever gainSynth is, as in the reference
+ * (MyBuffer.cpp:69-92), so gainSynth can be automated on mid-stream. outR may be
+ * NULL (then only L is written; L == R whenever gainSynth <= -59 dB).
+ * The outputs must NOT overlap the inputs (no in-place use: the mix reads the
+ * delayed inputs while the outputs are being written) -- VP_E_ARG otherwise.
+ * Asynchronous on the engine's stream; vp_engine_sync waits.
+ * If a process call fails after its first pass has been issued (VP_E_CUDA /
+ * VP_E_NOMEM), part of the streams' carried state has advanced: every later
+ * process call returns VP_E_STATE until vp_engine_reset or vp_engine_prepare. */
 int vp_engine_process_device(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
                              const float* synthR, float* outL, float* outR, size_t strideSamples);
 

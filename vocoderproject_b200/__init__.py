@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
     "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset", "vp_engine_stream_buffers", "vp_engine_stream_block",
-    "vp_engine_stream_stats",
+    "vp_engine_stream_stats", "vp_engine_get_info",
 ]
 
 
@@ -83,6 +83,7 @@ def load_library(path=None):
         "vp_engine_prepare": (i, [vp, dbl, i, i, i, sz]),
         "vp_engine_set_params": (i, [vp, C.POINTER(Params)]),
         "vp_engine_get_sizes": (i, [vp, C.POINTER(Sizes)]),
+        "vp_engine_get_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]),
         "vp_engine_process_device": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_process_host": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_sync": (i, [vp]),
@@ -222,6 +223,12 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def info(self):
+        """Layout chosen at prepare: streams per pass, carried history length, workspace bytes."""
+        a, b, c = C.c_int(0), C.c_int(0), C.c_size_t(0)
+        self._check(self.lib.vp_engine_get_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"streams_per_pass": a.value, "history_samples": b.value, "workspace_bytes": c.value}
 
     def reset(self):
         """prepareToPlay again: forget every stream's history; the next process call starts at block 0."""

@@ -124,7 +124,7 @@ __device__ __forceinline__ double vp_warp_sum(double v) {
 
 // Every kernel launch goes through VP_LAUNCH: a launch that the runtime refuses (configuration, shared memory, ...) is
 // recorded -- first one wins -- and turns the engine call that issued it into VP_E_CUDA (vp_take_launch_error).
-extern cudaError_t g_vpLaunchError;
+extern thread_local cudaError_t g_vpLaunchError;
 inline void vp_note_launch() {
     const cudaError_t err = cudaPeekAtLastError();
     if (err != cudaSuccess && g_vpLaunchError == cudaSuccess) g_vpLaunchError = err;

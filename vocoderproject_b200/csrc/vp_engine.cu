@@ -20,11 +20,12 @@ static const char* kStageNames[VP_NSTAGES] = {"gate", "voc_autocorr", "voc_levin
                                               "marks", "pitch_psola", "pitch_iir", "mix", "clear", "other",
                                               "yin_decide", "pitch_lpc", "", ""};
 
-cudaError_t g_vpLaunchError = cudaSuccess;
+thread_local cudaError_t g_vpLaunchError = cudaSuccess;  // per host thread: engines driven from different threads do not see each other's launch failures
 
 struct vp_engine {
     int device = 0;
     bool prepared = false;
+    bool failed = false;  // a process call failed half way: the carried state is undefined until vp_engine_reset / vp_engine_prepare
     cudaStream_t st = nullptr, stIn = nullptr, stOut = nullptr;
     cudaStream_t st2 = nullptr;   // the sequential pitch-mark chain runs here, under the vocoder kernels of the same pass
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -395,6 +396,7 @@ static int reset_state(vp_engine* e) {
     VP_CUDA_OK(cudaStreamSynchronize(e->st));
     e->blocksDone = 0;
     e->histCur = 0;
+    e->failed = false;
     return VP_OK;
 }
 
@@ -413,6 +415,9 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     vp_sizes z;
     if (vp_sizes_for(fs, B, e->prm.keyPitch, &z) != VP_OK) return vp_err(e, VP_E_ARG, "unsupported sample rate / block size");
     if (z.anCap > VP_MAX_MARKS - 1 || z.tauMin < 2) return vp_err(e, VP_E_ARG, "sample rate outside the supported range");
+    // what the kernels can serve: the FP64 YIN re-decision tiles lags as 128 x 15 (tauMax <= 1920), the pitch kernels stage a
+    // frame (+ look-back) in shared memory: 192 kHz is the top of the range (8 kHz the bottom, vp_sizes_for)
+    if (z.tauMax > 1920) return vp_err(e, VP_E_ARG, "sample rate above 192 kHz is not supported");
     VP_CUDA_OK(cudaSetDevice(e->device));
     VP_CUDA_OK(cudaDeviceSynchronize());
     free_workspace(e);
@@ -433,7 +438,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     const size_t yinP = e->yinDirect ? 0 : (size_t)vp_yin_corr_chunks(gy) * (size_t)vp_yin_corr_lagpad(gy);
     // bytes of intermediates per stream
     const size_t perStream = (size_t)maxBlocks * 33 + (size_t)nV * 8 * (size_t)(3 * (e->prm.lpcVoice + 1) + 3 * (e->prm.lpcSynth + 1) + 3) +
-                             (size_t)nP * (8 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
+                             (size_t)nP * (12 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
                              (size_t)n * 8 + yinP * 4 + (size_t)(3 * nP + 1) * 8;
     if (workspaceBytes == 0) {
         // default: up to 64 GiB, never more than 40 % of what is free now (the caller's I/O arrays come on top)
@@ -447,6 +452,8 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     if (Sc > S) Sc = S;
     if (Sc > 32) Sc &= ~31LL;
     if (Sc > 65535) Sc = 65535 & ~31;
+    // frame, chunk and tile indices of a pass are 32-bit in the kernels (re-check / pending / tile lists)
+    while (Sc > 1 && (long long)Sc * (long long)std::max((long long)nV + VP_VC, (long long)3 * nP + 1 + VP_PC) >= (1LL << 30)) Sc = (Sc / 2 > 32) ? ((Sc / 2) & ~31LL) : Sc / 2;
     e->Sc = (int)Sc;
     e->workspace = perStream * (size_t)Sc;
     const size_t fV = (size_t)Sc * nV, fP = (size_t)Sc * nP;
@@ -465,7 +472,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     if ((rc = wsalloc(e, &e->dGs, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dPeriod, fP))) return rc;
     if ((rc = wsalloc(e, &e->dYFlags, fP))) return rc;
-    e->maxList = (int)std::min<size_t>(fP, (size_t)1 << 22);
+    e->maxList = (int)std::max<size_t>(fP, 1);  // every frame of a pass can be listed (once): the list cannot overflow
     if ((rc = wsalloc(e, &e->dList, (size_t)e->maxList))) return rc;
     if ((rc = wsalloc(e, &e->dListCount, 1024))) return rc;
     VP_CUDA_OK(cudaMemset(e->dListCount, 0, 1024 * sizeof(int)));
@@ -704,7 +711,9 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     if (g.pitchOn) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
     vp_launch_hist_update(st, e->cHist[hc ^ 1][0] + sb * e->H, g.histV, voice, Sp, e->H, g.n, g.stride);
     vp_launch_hist_update(st, e->cHist[hc ^ 1][1] + sb * e->H, g.histS, synthL, Sp, e->H, g.n, g.stride);
-    if (g.synthOn && synthR) vp_launch_hist_update(st, e->cHist[hc ^ 1][2] + sb * e->H, g.histR, synthR, Sp, e->H, g.n, g.stride);
+    // channel 1 of the side-chain ring is filled on every block whatever gainSynth is (MyBuffer.cpp:69-92): the history
+    // follows the caller's right channel when there is one, else channel 0 (R == L), so that gainSynth can be automated on
+    vp_launch_hist_update(st, e->cHist[hc ^ 1][2] + sb * e->H, g.histR, synthR ? synthR : synthL, Sp, e->H, g.n, g.stride);
     if (e->keepDecisions && streamBase >= 0) {
         if (g.pitchOn && g.nFramesP > 0)
             VP_CUDA_OK(cudaMemcpy2DAsync(e->dFramesAll + sb * g.nFramesP, (size_t)g.nFramesP * sizeof(vp_pitch_frame),
@@ -734,17 +743,33 @@ static int check_process_args(vp_engine* e, int nBlocks, const float* voice, con
                               float* outL, size_t stride) {
     if (!e) return VP_E_ARG;
     if (!e->prepared) return vp_err(e, VP_E_STATE, "vp_engine_prepare has not been called");
+    if (e->failed) return vp_err(e, VP_E_STATE, "an earlier process call failed half way: the carried stream state is undefined, call vp_engine_reset");
     if (nBlocks <= 0 || nBlocks > e->maxBlocks) return vp_err(e, VP_E_ARG, "nBlocks outside (0, maxBlocks]");
     if (!voice || !synthL || !outL) return vp_err(e, VP_E_ARG, "voice, synthL and outL must be non-null");
     if (stride < (size_t)nBlocks * e->B) return vp_err(e, VP_E_ARG, "strideSamples < nBlocks * samplesPerBlock");
-    if (e->prm.gainSynth > -59.0f && !synthR) return vp_err(e, VP_E_ARG, "synthR is required when gainSynth > -59 dB");
+    (void)synthR;  // optional: without it the right side-chain channel equals the left one
     return VP_OK;
+}
+
+// [a, a + na) and [b, b + nb) floats overlap?
+static bool ranges_overlap(const float* a, size_t na, const float* b, size_t nb) {
+    if (!a || !b) return false;
+    const uintptr_t a0 = (uintptr_t)a, a1 = a0 + na * sizeof(float), b0 = (uintptr_t)b, b1 = b0 + nb * sizeof(float);
+    return a0 < b1 && b0 < a1;
 }
 
 extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
                                         const float* synthR, float* outL, float* outR, size_t stride) {
     int rc = check_process_args(e, nBlocks, voice, synthL, synthR, outL, stride);
     if (rc) return rc;
+    {   // the mix kernel reads the delayed inputs while other threads already write the outputs: no in-place use
+        const size_t span = (size_t)(e->S - 1) * stride + (size_t)nBlocks * e->B;
+        const float* ins[3] = {voice, synthL, synthR};
+        float* outs[2] = {outL, outR};
+        for (const float* in : ins) for (float* out : outs)
+            if (ranges_overlap(in, span, out, span)) return vp_err(e, VP_E_ARG, "output arrays must not overlap the input arrays");
+        if (ranges_overlap(outL, span, outR, span)) return vp_err(e, VP_E_ARG, "outL and outR must not overlap");
+    }
     VP_CUDA_OK(cudaSetDevice(e->device));
     VPGeom g;
     make_geom(e, nBlocks, stride, &g);
@@ -757,7 +782,7 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
         const size_t off = (size_t)s0 * stride;
         rc = run_pass(e, g, Sp, s0, voice + off, synthL + off, synthR ? synthR + off : nullptr, outL + off,
                       outR ? outR + off : nullptr);
-        if (rc) return rc;
+        if (rc) { e->failed = true; return rc; }  // some streams' carried state has advanced, others' has not
     }
     finish_call(e, nBlocks);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
@@ -771,6 +796,24 @@ extern "C" int vp_engine_sync(vp_engine* e) {
     VP_CUDA_OK(cudaStreamSynchronize(e->st2));
     VP_CUDA_OK(cudaStreamSynchronize(e->stIn));
     VP_CUDA_OK(cudaStreamSynchronize(e->stOut));
+    // guard: the FP64 re-decision list holds every frame of a pass, so it cannot overflow; should a count ever exceed it
+    // (a frame listed twice), frames would have kept their unverified FP32 decision -- that is an error, not a truncation
+    if (e->prepared && e->dListCount && e->passCount > 0 && e->prm.pitchBool) {
+        int h[1024];
+        const int np = e->passCount < 1024 ? e->passCount : 1024;
+        VP_CUDA_OK(cudaMemcpy(h, e->dListCount, sizeof(int) * (size_t)np, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < np; ++i)
+            if (h[i] > e->maxList) { e->failed = true; return vp_err(e, VP_E_STATE, "YIN re-decision list overflow: results of this call are not verified"); }
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_engine_get_info(const vp_engine* e, int* streamsPerPass, int* historySamples, size_t* workspaceBytes) {
+    if (!e) return VP_E_ARG;
+    if (!e->prepared) return VP_E_STATE;
+    if (streamsPerPass) *streamsPerPass = e->Sc;
+    if (historySamples) *historySamples = e->H;
+    if (workspaceBytes) *workspaceBytes = e->workspace;
     return VP_OK;
 }
 
@@ -797,12 +840,16 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
         }
         e->Sh = (int)Sh;
     }
-    if (synthOn && !e->hIn[0][2]) {  // the right side-chain / right output only travel when the dry side-chain is mixed in
+    // the right side-chain travels whenever the caller has one (its ring is filled whatever gainSynth is); the right
+    // output only when the dry side-chain is mixed in (otherwise L == R)
+    const bool haveR = synthR != nullptr;
+    if (haveR && !e->hIn[0][2]) {
         const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
-        for (int i = 0; i < 3; ++i) {
-            if ((rc = wsalloc(e, &e->hIn[i][2], cnt))) return rc;
-            if ((rc = wsalloc(e, &e->hOut[i][1], cnt))) return rc;
-        }
+        for (int i = 0; i < 3; ++i) if ((rc = wsalloc(e, &e->hIn[i][2], cnt))) return rc;
+    }
+    if (synthOn && outR && !e->hOut[0][1]) {
+        const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
+        for (int i = 0; i < 3; ++i) if ((rc = wsalloc(e, &e->hOut[i][1], cnt))) return rc;
     }
     VPGeom g;
     make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense
@@ -833,18 +880,18 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
         const size_t hoff = (size_t)s0 * stride;
         VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][0], rowB, voice + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
         VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][1], rowB, synthL + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
-        if (synthOn)
+        if (haveR)
             VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][2], rowB, synthR + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
         VP_CUDA_OK(cudaEventRecord(e->evIn[bi], e->stIn));
         VP_CUDA_OK(cudaStreamWaitEvent(e->st, e->evIn[bi], 0));
-        rc = run_pass(e, g, Sp, s0, e->hIn[bi][0], e->hIn[bi][1], synthOn ? e->hIn[bi][2] : nullptr, e->hOut[bi][0],
+        rc = run_pass(e, g, Sp, s0, e->hIn[bi][0], e->hIn[bi][1], haveR ? e->hIn[bi][2] : nullptr, e->hOut[bi][0],
                       (synthOn && outR) ? e->hOut[bi][1] : nullptr);
-        if (rc) return rc;
+        if (rc) { e->failed = true; return rc; }
         VP_CUDA_OK(cudaEventRecord(e->evComp[bi], e->st));
         VP_CUDA_OK(cudaStreamWaitEvent(e->stOut, e->evComp[bi], 0));
         VP_CUDA_OK(cudaMemcpy2DAsync(outL + hoff, stride * 4, e->hOut[bi][0], rowB, rowB, Sp, cudaMemcpyDeviceToHost, e->stOut));
         if (outR)  // L == R unless the dry synth is mixed in (MyBuffer.cpp:380-448)
-            VP_CUDA_OK(cudaMemcpy2DAsync(outR + hoff, stride * 4, synthOn ? e->hOut[bi][1] : e->hOut[bi][0], rowB, rowB, Sp,
+            VP_CUDA_OK(cudaMemcpy2DAsync(outR + hoff, stride * 4, (synthOn && e->hOut[bi][1]) ? e->hOut[bi][1] : e->hOut[bi][0], rowB, rowB, Sp,
                                          cudaMemcpyDeviceToHost, e->stOut));
         VP_CUDA_OK(cudaEventRecord(e->evOut[bi], e->stOut));
     }

@@ -1002,6 +1002,7 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
                      VPMarkState* carry) {
     const int threads = 128;
     const long long tot = (long long)S * 32;
+    cudaFuncSetAttribute(k_marks, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  // 4 frames of L floats: > 48 KB above 132 kHz
     VP_LAUNCH(k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * g.L * sizeof(float), st>>>(
         g, tb, voice, gate, period, yflags, frames, carry, S));
 }

@@ -3,6 +3,8 @@
 // Reference behaviour: Source/VocoderProcess.cpp:190-297, Source/LPC.cpp:44-148,
 // Source/MyBuffer.cpp:258-261,:299-302.
 #include <cuda_pipeline.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -825,6 +827,259 @@ __global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VP
     }
 }
 
+// ---------------------------------------------------------------------------
+// Row-staged form of the streaming synthesis (default). Same lock-step scheme and the same arithmetic as
+// k_voc_synth_stream (FIR32 = false: bit-identical output), rebuilt around what the pipe microbenchmark
+// (tools/ubench_mix.cu, profiles/ubench_mix_r02a.txt) measured on the B200: next to DFMAs NO other instruction issues for
+// free -- an FFMA, an integer op or a load each cost their own issue cycle, an F2F about 2.7 -- so the step is trimmed to
+// its 40 + 6 DFMAs plus the fewest possible other instructions:
+//   * the side-chain samples of a hop-row (8 streams x hop floats per warp) are copied global -> shared by cp.async one
+//     row ahead (each lane copies a quarter of its stream's row: 0.25 copy instructions per sample instead of one load
+//     with 64-bit address arithmetic and range tests), and a block of 4 positions reads them with ONE 128-bit load;
+//   * window rows are padded so that a block reads its 4 weights with 128-bit loads at immediate offsets;
+//   * frame parameters land in one zone per STREAM (only one of a stream's four phases starts a frame per row), copied by
+//     the stream's four lanes together;
+//   * segments are sized so that the grid is a whole number of waves of resident CTAs (the round-1 launch left a third,
+//     nearly empty wave).
+// FIR32 = true moves the order-PS whitening FIR and both window multiplies to the idle FP32 pipe (the all-pole recursion,
+// its state and its input sum stay FP64); SURVEY.md App. C.4 measured that split at >= 117 dB on the clean voice.
+// ---------------------------------------------------------------------------
+#define VR_WARPS 2
+
+__host__ __device__ inline int vr_pad4odd(int n) {  // smallest multiple of 4 with an odd quotient, >= n rounded up to 4
+    int q = (n + 3) >> 2;
+    if ((q & 1) == 0) ++q;
+    return 4 * q;
+}
+
+template <int P, int PS, bool FIR32>
+__global__ void __launch_bounds__(32 * VR_WARPS) k_voc_synth_rows(VPGeom g, VPTables tb, const float* __restrict__ synth,
+                                                                  const double* __restrict__ aV, const double* __restrict__ aS,
+                                                                  const double* __restrict__ EeS, const double* __restrict__ G,
+                                                                  float* __restrict__ outV, int S, int nSeg, int segFrames,
+                                                                  int wPad, int xPad) {
+    using WT = typename std::conditional<FIR32, float, double>::type;  // window / FIR arithmetic type
+    extern __shared__ __align__(16) unsigned char vr_smem[];
+    constexpr int CF_AS = P + 1, CF_G = P + PS + 2, CF_ES = CF_G + 1, CF_N = CF_ES + 1;
+    constexpr int CF_STRIDE = CF_N | 1;  // odd stride: the 64-bit reads of a warp's 8 zones hit distinct banks
+    const int hop = g.hopV;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xsAll = reinterpret_cast<float*>(vr_smem);                         // [VR_WARPS][2][8][xPad] side-chain rows
+    WT* wv = reinterpret_cast<WT*>(xsAll + (size_t)VR_WARPS * 2 * 8 * xPad);  // [4][wPad] window rows
+    double* cfAll = reinterpret_cast<double*>(wv + (size_t)4 * wPad);         // [VR_WARPS][8][CF_STRIDE] frame parameters
+    for (int i = threadIdx.x; i < 4 * wPad; i += blockDim.x) {
+        const int r = i / wPad, c = i - r * wPad;
+        wv[i] = (c < hop) ? (WT)tb.wV[r * hop + c] : (WT)0;
+    }
+    __syncthreads();
+    const long long wid = (long long)blockIdx.x * VR_WARPS + warp;
+    const int groups = (S + 7) / 8;
+    if (wid >= (long long)groups * nSeg) return;
+    const int grp = (int)(wid / nSeg), seg = (int)(wid - (long long)grp * nSeg);
+    const int phi = lane & 3, j8 = lane >> 2;
+    int s = grp * 8 + j8;
+    const bool sOk = s < S;
+    if (!sOk) s = S - 1;  // idle group: runs along on a valid stream, stores are masked
+    // rows / segments exactly as in k_voc_synth_stream
+    const int kS = seg * segFrames;
+    const int nRowsAll = (int)((g.n - g.offV + hop - 1) / hop);
+    if (seg > 0 && kS >= nRowsAll) return;
+    const bool lastSeg = (seg == nSeg - 1) || (kS + segFrames >= nRowsAll);
+    const int kE = lastSeg ? nRowsAll : kS + segFrames;
+    const long long emit0 = (seg == 0) ? 0 : (long long)kS * hop + g.offV;
+    const long long emit1 = lastSeg ? g.n : (long long)kE * hop + g.offV;
+    const int rho0 = (seg == 0) ? -VP_VC : kS - 3;
+    const VPRow y = vp_row(synth, g.histS, s, g);
+    float* o = outV + (size_t)s * g.vstride;
+    double* cf = cfAll + ((size_t)warp * 8 + j8) * CF_STRIDE;
+    float* xs0 = xsAll + ((size_t)(warp * 2) * 8 + j8) * xPad;  // this stream's row, buffer 0; buffer 1 is 8 xPad further
+    const int xbuf = 8 * xPad;
+    double a[P + 1], st[P + 1];
+    WT as[PS + 1], t[PS + 1];
+#pragma unroll
+    for (int j = 0; j <= P; ++j) { a[j] = 0.0; st[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j <= PS; ++j) { as[j] = (WT)0; t[j] = (WT)0; }
+    int wrow = 0;
+    auto frameOk = [&](int k) { return k + g.kV0 >= 0 && k < g.nFramesV; };
+    // ---- asynchronous copies for row r: the stream's hop side-chain samples (this lane: positions phi, phi + 4, ...) and,
+    // by the stream's four lanes together, the parameters of the frame that starts at row r
+    auto stage = [&](int r, int buf) {
+        float* dst = xs0 + buf * xbuf;
+        const long long tIn = (long long)r * hop + g.offV - g.lat;  // input index of the row's first position
+        if (tIn >= 0 && tIn + hop <= g.n) {
+            const float* src = y.x + tIn;
+#pragma unroll 4
+            for (int i = phi; i < hop; i += 4) __pipeline_memcpy_async(dst + i, src + i, 4);
+        } else {  // history before the call / beyond its input: plain stores (the __syncwarp after the wait orders them)
+            const long long u0 = (long long)r * hop + g.offV;
+            for (int i = phi; i < hop; i += 4) dst[i] = vp_x(y, u0 + i, g);
+        }
+        if (frameOk(r)) {
+            const size_t row = vp_vrow(g, s, r);
+            const double* ap = aV + row * (P + 1);
+            const double* sp = aS + row * (PS + 1);
+#pragma unroll
+            for (int q0 = 0; q0 < CF_N; q0 += 4) {
+                const int q = q0 + phi;
+                if (q < CF_N) {
+                    const double* src = (q <= P) ? ap + q : (q < CF_G) ? sp + (q - CF_AS) : (q == CF_G) ? G + row : EeS + row;
+                    __pipeline_memcpy_async(cf + q, src, 8);
+                }
+            }
+        }
+        __pipeline_commit();
+    };
+    stage(rho0, 0);
+    int cur = 0;
+    for (int rho = rho0; rho < kE; ++rho, cur ^= 1) {
+        __pipeline_wait_prior(0);
+        __syncwarp();
+        // ---- frame start for the phase that begins at this row
+        if (((rho + 4 * VP_VC) & 3) == phi) {
+#pragma unroll
+            for (int j = 0; j <= P; ++j) st[j] = 0.0;
+#pragma unroll
+            for (int j = 0; j <= PS; ++j) t[j] = (WT)0;
+            const bool active = frameOk(rho) && cf[CF_ES] >= 0.0;  // a gated frame carries EeSynth < 0
+            if (active) {
+                const double gain = cf[CF_G];
+#pragma unroll
+                for (int j = 1; j <= P; ++j) a[j] = cf[j];
+#pragma unroll
+                for (int j = 0; j <= PS; ++j) as[j] = (WT)(gain * cf[CF_AS + j]);  // gain folded into the FIR taps
+            } else {
+#pragma unroll
+                for (int j = 1; j <= P; ++j) a[j] = 0.0;
+#pragma unroll
+                for (int j = 0; j <= PS; ++j) as[j] = (WT)0;
+            }
+            wrow = 0;
+        }
+        __syncwarp();  // the zone has been read before the next frame's parameters are copied into it
+        if (rho + 1 < kE) stage(rho + 1, cur ^ 1);
+        const float* xr = xs0 + cur * xbuf;
+        const WT* wr = wv + wrow * wPad;
+        const long long tBase = (long long)rho * hop + g.offV;
+        const bool rowEmit = sOk && tBase >= emit0 && tBase + hop <= emit1;  // whole row inside the emission range
+        const int nblk = (hop + 3) >> 2;
+        const int nFull = hop >> 2;  // full blocks of 4 positions; block nFull (if any) is the row's partial last block
+        // The row body exists twice: EALL = every position of the row is emitted (steady state: stores are plain
+        // pointer + immediate, no range test) and the general form (segment halo rows, first / last rows of a call).
+        auto rowBody = [&](auto emitTag) {
+            constexpr bool EALL = decltype(emitTag)::value;
+            float* op = o + tBase + phi;  // this lane's position in block 0
+            WT eA[4], eB[4];
+            float cA[4], cB[4];
+            // whitening FIR (transposed form) of the block at row offset i1 with nb1 valid positions -> e
+            auto fir = [&](auto fullTag, WT* e, int i1, int nb1) {
+                constexpr bool FULL = decltype(fullTag)::value;
+                const float4 x4 = *reinterpret_cast<const float4*>(xr + i1);
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                WT w4[4];
+                if (FIR32) {
+                    const float4 q = *reinterpret_cast<const float4*>(wr + i1);
+                    w4[0] = (WT)q.x; w4[1] = (WT)q.y; w4[2] = (WT)q.z; w4[3] = (WT)q.w;
+                } else {
+                    const double2 q0 = *reinterpret_cast<const double2*>(wr + i1), q1 = *reinterpret_cast<const double2*>(wr + i1 + 2);
+                    w4[0] = (WT)q0.x; w4[1] = (WT)q0.y; w4[2] = (WT)q1.x; w4[3] = (WT)q1.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    e[j] = (WT)0;
+                    if (FULL || j < nb1) {
+                        const WT x = (WT)xv[j] * w4[j];
+                        e[j] = fma(as[0], x, t[0]);
+#pragma unroll
+                        for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
+                    }
+                }
+            };
+            // all-pole recursion of the block at row offset i0 (transposed direct form II: P independent DFMAs per sample)
+            auto iir = [&](auto fullTag, const WT* e, float* c, int i0, int nb) {
+                constexpr bool FULL = decltype(fullTag)::value;
+                WT w4[4];
+                if (FIR32) {
+                    const float4 q = *reinterpret_cast<const float4*>(wr + i0);
+                    w4[0] = (WT)q.x; w4[1] = (WT)q.y; w4[2] = (WT)q.z; w4[3] = (WT)q.w;
+                } else {
+                    const double2 q0 = *reinterpret_cast<const double2*>(wr + i0), q1 = *reinterpret_cast<const double2*>(wr + i0 + 2);
+                    w4[0] = (WT)q0.x; w4[1] = (WT)q0.y; w4[2] = (WT)q1.x; w4[3] = (WT)q1.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (FULL || j < nb) {
+                        const double ov = (double)e[j] + st[0];
+#pragma unroll
+                        for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
+                        if (FIR32) c[j] = (float)ov * (float)w4[j];
+                        else c[j] = (float)(ov * (double)w4[j]);
+                    } else c[j] = 0.0f;
+                }
+            };
+            // overlap-add of the 4 phase lanes for the 4 positions of the block at row offset iP (nbP valid positions):
+            // transpose-reduce, 3 shuffles; lane phi ends with the sum over the group for position iP + phi
+            auto ola = [&](const float* c, int iP, int nbP) {
+                const bool hi = (phi & 2) != 0, od = (phi & 1) != 0;
+                const float s0 = hi ? c[0] : c[2], s1 = hi ? c[1] : c[3];
+                const float k0 = hi ? c[2] : c[0], k1 = hi ? c[3] : c[1];
+                const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+                const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+                const float snd = od ? r0 : r1, kp = od ? r1 : r0;
+                const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+                if (EALL) {
+                    if (nbP == 4 || phi < nbP) op[iP] = tot;
+                } else {
+                    const long long tp = tBase + iP + phi;
+                    if (sOk && phi < nbP && tp >= emit0 && tp < emit1) op[iP] = tot;
+                }
+            };
+            // step k: recursion of block k (its FIR output is in e), overlap-add + store of block k - 1 (its shuffle
+            // latencies hide under the recursion), then the FIR of block k + 1 into the same e (each e[j] is dead as soon as
+            // sample j entered the recursion, so one set of registers serves both). Even k writes cA, odd k cB.
+            WT* const e = eA;
+            (void)eB;
+            int k = 0;
+            if (nFull >= 2) {
+                fir(std::true_type{}, e, 0, 4);
+                iir(std::true_type{}, e, cA, 0, 4);
+                fir(std::true_type{}, e, 4, 4);
+                k = 1;
+                for (; k + 2 < nFull; k += 2) {  // blocks k, k + 1, k + 2 are full
+                    iir(std::true_type{}, e, cB, 4 * k, 4);
+                    ola(cA, 4 * k - 4, 4);
+                    fir(std::true_type{}, e, 4 * k + 4, 4);
+                    iir(std::true_type{}, e, cA, 4 * k + 4, 4);
+                    ola(cB, 4 * k, 4);
+                    fir(std::true_type{}, e, 4 * k + 8, 4);
+                }
+            } else {
+                fir(std::false_type{}, e, 0, min(4, hop));
+            }
+            // remaining blocks (at most 3 + the partial one), parity tracked at run time; k = next block to run through the
+            // recursion (its FIR output is in e); block k - 1 (if k > 0) awaits its overlap-add
+            for (; k < nblk; ++k) {
+                const int nb = min(4, hop - 4 * k), nb1 = min(4, hop - 4 * k - 4);
+                if (k & 1) {
+                    iir(std::false_type{}, e, cB, 4 * k, nb);
+                    ola(cA, 4 * k - 4, 4);
+                } else {
+                    iir(std::false_type{}, e, cA, 4 * k, nb);
+                    if (k > 0) ola(cB, 4 * k - 4, 4);
+                }
+                if (k + 1 < nblk) fir(std::false_type{}, e, 4 * k + 4, nb1);
+            }
+            {   // drain: the row's last block
+                const int kl = nblk - 1;
+                ola((kl & 1) ? cB : cA, 4 * kl, min(4, hop - 4 * kl));
+            }
+        };
+        if (rowEmit) rowBody(std::true_type{});
+        else rowBody(std::false_type{});
+        ++wrow;
+    }
+}
+
 // Generic-order fallback (orders other than the plug-in defaults): same tiling,
 // histories in local memory.
 __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, VPTables tb, const float* __restrict__ synth,
@@ -892,20 +1147,75 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
 
 bool vp_voc_synth_needs_clear(const VPGeom& g) { return !(g.ordV == 40 && g.ordS == 5); }
 
+// segments per stream group such that the grid is (at most) `waves` full waves of resident warps
+static int vs_segments(const VPGeom& g, int groups, int residentWarps, int* segFramesOut) {
+    int nSeg = (2 * residentWarps) / groups;                            // two waves: second one (nearly) full, no third
+    if (nSeg < 1) nSeg = 1;
+    int segFrames = (g.nFramesV + nSeg - 1) / nSeg;
+    if (segFrames < 16) segFrames = 16;                                  // keep the 3-row halo a small fraction
+    nSeg = (g.nFramesV + segFrames - 1) / segFrames;
+    if (nSeg < 1) nSeg = 1;                                              // no new frame: the carried frames still emit
+    *segFramesOut = segFrames;
+    return nSeg;
+}
+
+template <bool FIR32>
+static void launch_synth_rows(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
+                              const double* aV, const double* aS, const double* EeS, const double* G, float* outV) {
+    auto kern = k_voc_synth_rows<40, 5, FIR32>;
+    const int groups = (S + 7) / 8;
+    const int nblk = (g.hopV + 3) >> 2;
+    const int xPad = vr_pad4odd(g.hopV);
+    int wPad;
+    if (FIR32) wPad = vr_pad4odd(g.hopV);
+    else { wPad = 4 * nblk; if (((wPad >> 1) & 1) == 0) wPad += 2; }     // doubles: 16-byte rows, row stride / 16 B odd
+    const int cfStride = (40 + 1 + 5 + 1 + 2) | 1;
+    const size_t smem = (size_t)VR_WARPS * 2 * 8 * xPad * sizeof(float) + (size_t)4 * wPad * (FIR32 ? sizeof(float) : sizeof(double)) +
+                        (size_t)VR_WARPS * 8 * cfStride * sizeof(double);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int perSM = 4, dev = 0, nSM = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 32 * VR_WARPS, smem);
+    if (perSM < 1) perSM = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+    int segFrames = 0;
+    const int nSeg = vs_segments(g, groups, nSM * perSM * VR_WARPS, &segFrames);
+    const long long warps = (long long)groups * nSeg;
+    VP_LAUNCH(kern<<<(unsigned)((warps + VR_WARPS - 1) / VR_WARPS), 32 * VR_WARPS, smem, st>>>(
+        g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, wPad, xPad));
+}
+
+// VP_SYNTH = rows (default) | rows32 (FP32 whitening FIR + window) | stream (round-1 kernel)
+static int vs_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VP_SYNTH");
+        v = (e && strcmp(e, "stream") == 0) ? 2 : (e && strcmp(e, "rows32") == 0) ? 1 : 0;
+    }
+    return v;
+}
+
 void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
                          const double* aV, const double* aS, const double* EeS, const double* G, float* outV) {
+    if (g.ordV == 40 && g.ordS == 5 && vs_variant() != 2 && g.hopV >= 8) {
+        if (vs_variant() == 1) launch_synth_rows<true>(st, g, tb, S, synth, aV, aS, EeS, G, outV);
+        else launch_synth_rows<false>(st, g, tb, S, synth, aV, aS, EeS, G, outV);
+        return;
+    }
     if (g.ordV == 40 && g.ordS == 5) {
         const int groups = (S + 7) / 8;
-        int nSeg = (148 * 16 + groups - 1) / groups;                    // ~16 warps per SM in flight over the grid
-        int segFrames = (g.nFramesV + nSeg - 1) / nSeg;
-        if (segFrames < 16) segFrames = 16;                              // keep the 3-row halo a small fraction
-        nSeg = (g.nFramesV + segFrames - 1) / segFrames;
-        if (nSeg < 1) nSeg = 1;                                          // no new frame: the carried frames still emit
+        int perSM = 4, dev = 0, nSM = 148;
         const int rowPad = g.hopV | 1;
         const int cfStride = (40 + 1 + 5 + 1 + 2) | 1;
         const size_t smem = ((size_t)4 * rowPad + (size_t)VT_WARPS * 32 * cfStride) * sizeof(double);
-        const long long warps = (long long)groups * nSeg;
         cudaFuncSetAttribute(k_voc_synth_stream<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_voc_synth_stream<40, 5>, 32 * VT_WARPS, smem);
+        if (perSM < 1) perSM = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+        int segFrames = 0;
+        const int nSeg = vs_segments(g, groups, nSM * perSM * VT_WARPS, &segFrames);
+        const long long warps = (long long)groups * nSeg;
         VP_LAUNCH(k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
             g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, rowPad));
         return;
