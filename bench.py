@@ -194,7 +194,7 @@ def run_reference(args, wl, group):
 
 def run_engine(args, wl, group):
     os.environ["VP_STAGE_TIMING"] = "1"      # CUDA events between the engine's kernels (per-kernel durations)
-    os.environ["VP_KEEP_DECISIONS"] = "0"    # decisions of all streams are not read back in the bench
+    os.environ["VP_KEEP_DECISIONS"] = "1"    # per-frame decisions of every stream stay on the device: the parity check below reads a spread of them
     import vocoderproject_b200 as vp
     fs, B = wl["fs"], wl["B"]
     n = int(fs * wl["seconds"]) // B * B
@@ -238,6 +238,12 @@ def run_engine(args, wl, group):
     audio_rank = S * n / fs * args.steps
     value, t_max, audio_total = vp.shard.aggregate_throughput(group, audio_rank, dev_s)
 
+    # ---- parity at the benchmarked size: a spread of streams of the LAST timed step, full length, against the reference
+    # on the host cores (oracle/_ref, else the C port). Test infrastructure used as the checker only.
+    parity, picks, dev_rows = None, [], {}
+    if not args.no_parity:
+        parity, picks, dev_rows = parity_check(vp, eng, args, wl, S, n, dv, dl, do, group)
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
     e2e = None
     if not args.no_e2e:
@@ -273,6 +279,9 @@ def run_engine(args, wl, group):
         te = time.time() - te0
         group.barrier()
         e_val, e_t, _ = vp.shard.aggregate_throughput(group, audio_rank_e, te)
+        if parity is not None:  # the host path must return what the device-resident path left in HBM, bit for bit
+            same = all(np.array_equal(ho.array[s_], dev_rows[s_]) for s_ in picks if s_ < Se)
+            parity["e2e_rows_equal_device_rows"] = bool(group.min(1.0 if same else 0.0) > 0.5)
         e2e = {"value": e_val, "unit": "audio-s/s", "h2d_bytes_per_step": 2 * nb_e * group.world, "d2h_bytes_per_step": nb_e * group.world,
                "streams_per_gpu": Se,
                "ms_per_step": 1e3 * e_t / args.steps, "timer": "host wall clock around vp_engine_process_host, max over ranks",
@@ -367,6 +376,8 @@ def run_engine(args, wl, group):
                 "roofline": roofline}
         if e2e is not None:
             line["e2e"] = e2e
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
     eng.close()
@@ -377,6 +388,64 @@ def run_engine(args, wl, group):
             except Exception as ex:  # the throughput line must not depend on the latency sub-test
                 line["streaming"] = {"error": str(ex)}
         print(json.dumps(line), flush=True)
+
+
+def parity_check(vp, eng, args, wl, S, n, dv, dl, do, group):
+    """>= 16 streams spread over this rank's [0, S) -- incl. the first and last stream of every pass -- for their full
+    length: inputs and outputs copied back from HBM, the reference run on the same inputs on the host cores, audio SNR /
+    max |err| and every pitch decision compared (tests/common.py). Returns (parity dict aggregated over ranks, picks, rows)."""
+    from common import MAXABS_MAX, SNR_MIN_DB, compare_decisions, maxabs, oracle_decisions, reference_runs, snr_db
+    fs, B = wl["fs"], wl["B"]
+    Sc = eng.info()["streams_per_pass"]
+    picks = set()
+    for p0 in range(0, S, Sc):
+        picks |= {p0, min(p0 + Sc, S) - 1}
+    want = max(args.parity_streams, len(picks))
+    for x in np.linspace(0, S - 1, want):
+        if len(picks) >= want:
+            break
+        picks.add(int(round(x)))
+    picks = sorted(picks)
+    ins, outs = [], {}
+    for s_ in picks:
+        v, l, o_ = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        for arr, base in ((v, dv), (l, dl), (o_, do)):
+            eng._check(eng.lib.vp_memcpy_d2h(eng.h, arr.ctypes.data, C.c_void_p(base + s_ * n * 4), n * 4))
+        ins.append((fs, B, v, l, None, wl["params"]))
+        outs[s_] = o_
+    t0 = time.time()
+    refs, kind = reference_runs(ins)
+    cpu_s = time.time() - t0
+    worst_snr, worst_abs, tot, chk, flg, exc, bad = 1e9, 0.0, 0, 0, 0, 0, 0
+    first = None
+    prm_pitch = wl["params"].get("pitchBool", 1)
+    for s_, r in zip(picks, refs):
+        worst_snr = min(worst_snr, snr_db(r["outL"], outs[s_]))
+        worst_abs = max(worst_abs, maxabs(r["outL"], outs[s_]))
+        if prm_pitch:
+            dec = compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s_))
+            tot += dec.n; chk += dec.checked; flg += dec.flagged; exc += dec.excused; bad += dec.bad
+            if dec.bad and first is None:
+                first = "stream %d: %s" % (s_, dec.first)
+    st = eng.stats()
+    res = {"streams": int(group.sum(len(picks))), "streams_per_rank": len(picks), "seconds": n / fs, "reference": kind,
+           "worst_snr_db": group.min(worst_snr), "worst_maxabs": group.max(worst_abs),
+           "frames": int(group.sum(tot)), "frames_compared": int(group.sum(chk)), "frames_flagged": int(group.sum(flg)),
+           "frames_excused": int(group.sum(exc)), "mismatches": int(group.sum(bad)),
+           "recheck_list_overflow": False,  # vp_engine_sync turns an overflow into an error (and the list holds every frame)
+           "yin_rechecked_frac": (st["yin_rechecked"] / float(S * ((n + eng.sizes["hopP"] - 1) // eng.sizes["hopP"]))) if prm_pitch else 0.0,
+           "tolerance": {"snr_db_min": SNR_MIN_DB, "maxabs_max": MAXABS_MAX, "decisions": "bit-exact, checked >= 98 % of frames"},
+           "streams_checked_rank0": picks, "cpu_seconds": cpu_s}
+    ok = (res["worst_snr_db"] >= SNR_MIN_DB and res["worst_maxabs"] <= MAXABS_MAX and res["mismatches"] == 0 and
+          res["frames_compared"] >= 0.98 * res["frames"])
+    res["ok"] = bool(ok)
+    if first:
+        res["first_mismatch"] = first
+    if not ok:
+        if group.rank == 0:
+            print(json.dumps({"parity_failed": res}), file=sys.stderr, flush=True)
+        raise SystemExit("bench.py: parity check at the benchmarked size FAILED: %r" % ({k: res[k] for k in ("worst_snr_db", "worst_maxabs", "mismatches", "frames", "frames_compared")},))
+    return res, picks, outs
 
 
 def run_streaming(args, group):
@@ -424,6 +493,8 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
     ap.add_argument("--seconds", type=float, default=0.0, help="seconds per stream (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the benchmarked size")
+    ap.add_argument("--parity-streams", type=int, default=16, help="streams per rank compared with the reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-streams", type=int, default=0)
     ap.add_argument("--ref-streams", type=int, default=0)

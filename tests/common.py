@@ -157,3 +157,27 @@ def golden_index():
 
 def golden_load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def reference_runs(jobs, threads=None):
+    """Runs the CPU reference on many streams at once (host threads; ctypes releases the GIL).
+    jobs: [(fs, B, voice, synthL, synthR or None, params dict)]. Uses oracle/_ref (the reference's own C++) when it is
+    built on this machine, else the C oracle port (bit-identical to it, tests/test_oracle.py). Returns (results, kind)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    import oraclebind
+    import refbind
+    use_ref = refbind.available("strict")
+    if not use_ref:
+        oraclebind.load()
+
+    def one(job):
+        fs, B, v, l, r, params = job
+        prm = refbind.default_params(**params)
+        if use_ref:
+            return refbind.run(fs, B, v, l, synthR=r, params=prm, log=True)
+        return oraclebind.run(fs, B, v, l, synthR=r, params=prm, log=True)
+    threads = threads or max(1, len(os.sched_getaffinity(0)))
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(one, jobs))
+    return res, ("reference" if use_ref else "port")

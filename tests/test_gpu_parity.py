@@ -14,7 +14,7 @@ import pytest
 
 import refbind
 from cases import CASES, KAT, KAT_BETA, KAT_MARKS, KAT_NOTE, KAT_PERIOD, KAT_PERIODNEW, case_inputs, case_schedule
-from common import MAXABS_MAX, SNR_MIN_DB, assert_decisions, compare_decisions, golden_index, golden_load, kat_inputs, maxabs, oracle_decisions, snr_db, stats
+from common import MAXABS_MAX, SNR_MIN_DB, assert_decisions, compare_decisions, reference_runs, golden_index, golden_load, kat_inputs, maxabs, oracle_decisions, snr_db, stats
 
 pytestmark = pytest.mark.gpu
 
@@ -357,6 +357,43 @@ def test_many_streams_spot_parity(vp, oracle):
         st = eng.stats()
         assert st["kernel_launches"] >= 10 and st["yin_frames"] == S * len(eng.pitch_frames(0))
         assert st["yin_rechecked"] < 0.02 * st["yin_frames"]
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("fs,S,secs,params,ws_mb", [
+    (48000.0, 64, 60.0, dict(), 2048),             # the bench's own stream length (chain, 60 s @ 48 kHz), >= 3 passes
+    (44100.0, 32, 30.0, dict(pitchBool=0), 512),   # BASELINE configs[1] flavour: vocoder only, 30 s
+    (44100.0, 32, 30.0, dict(vocBool=0), 512),     # BASELINE configs[2] flavour: pitch corrector only, 30 s
+])
+def test_long_streams_match_oracle(vp, fs, S, secs, params, ws_mb):
+    """Parity at the size that is benchmarked: full-length streams (20 716 vocoder / 3 453 pitch frames per stream at 60 s),
+    a workspace small enough to force several passes, EVERY stream against the reference on the host cores -- audio within
+    tolerance, every pitch decision compared (checked-frame floor), the mark chain over thousands of sequential frames."""
+    B = 1024
+    n = int(fs * secs) // B * B
+    voice, sl, _ = vp.synth_host(fs, S, n, flavour=0, first_stream=2000, want_right=False)
+    eng = vp.Engine(fs, B, S, n // B, params=vp.default_params(**params), workspace_bytes=ws_mb << 20)
+    try:
+        assert eng.info()["streams_per_pass"] * 3 <= S + 2, "workspace too large: fewer than 3 passes"
+        outL, _ = eng.process(voice, sl, None, want_right=False)
+        refs, kind = reference_runs([(fs, B, voice[s], sl[s], None, params) for s in range(S)])
+        tot = chk = flg = 0
+        worst = (1e9, 0.0)
+        for s in range(S):
+            sn, mx = assert_audio(refs[s]["outL"], outL[s], "stream %d (%s)" % (s, kind))
+            worst = (min(worst[0], sn), max(worst[1], mx))
+            if params.get("pitchBool", 1):
+                dec = compare_decisions(vp, oracle_decisions(refs[s]["pitch"]), eng.pitch_frames(s))
+                assert dec.n == len(refs[s]["pitch"]) == (n + eng.sizes["hopP"] - 1) // eng.sizes["hopP"]
+                assert_decisions(dec, "stream %d" % s)
+                tot += dec.n; chk += dec.checked; flg += dec.flagged
+            if params.get("vocBool", 1):
+                vf = eng.voc_frames(s)
+                assert list(vf["gated"]) == [x.gated for x in refs[s]["voc"]]
+        print("long streams %s: %d x %.0f s, worst SNR %.1f dB, max|err| %.2e, %d / %d pitch frames compared, %d flagged (%s)" % (
+            params or "chain", S, n / fs, worst[0], worst[1], chk, tot, flg, kind))
+        assert flg <= max(2, tot // 200)
     finally:
         eng.close()
 

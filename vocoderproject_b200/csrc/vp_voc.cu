@@ -227,12 +227,19 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
     double* sw = xw + FS;                                                     // [FS] synth ch0 * window
     const VPRow v = vp_row(voice, g.histV, s, g), y = vp_row(synth, g.histS, s, g);
     for (int j = wlen + lane; j < FS; j += 32) { xw[j] = 0.0; sw[j] = 0.0; }
-    const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;  // grp 0..2: voice lag groups, grp 3: side-chain
-    const double* sig = (grp < 3 ? xw : sw);
-    // lag offsets 0 / 13 / 27 (lag 13 computed twice): odd - even offsets inside each half-warp keep the 64-bit window
-    // loads of two groups on disjoint banks (segLen = 2 mod 4 puts the 8 segments on the 8 even / 8 odd banks)
-    const int m0 = (grp == 1) ? AC_R - 1 : (grp == 2) ? 2 * AC_R - 1 : 0;
-    const int order = (grp < 3) ? g.ordV : g.ordS;
+    // lane groups of 8 segments: 0 = voice lags 0-13, 1 = side-chain lags 0-13, 2 = voice lags 14-27, 3 = voice lags 27-40
+    // (lag 27 is computed twice, identically). Bank layout of the 64-bit loads, which go out per half-warp over 16 banks:
+    // segLen = 2 (mod 4) spreads the 8 segments of a group over the 8 even (or 8 odd) banks. Half-warp 0 = voice group 0 +
+    // side-chain: the side-chain copy starts an ODD number of doubles after the voice copy (FS = 1 mod 16), so its `a` loads
+    // sit on the odd banks and its window loads (+13) on the even ones, opposite to voice group 0. Half-warp 1 = voice
+    // groups 2 and 3: their `a` loads are the same addresses (broadcast), their window loads start 27 and 40 doubles on.
+    // (Round 1 paired voice group 2 with the side-chain at an even offset: their `a` loads met on the even banks -- the
+    // 14 % conflict wavefronts of profiles/ncu_r01fin4_kernels.md.)
+    const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;
+    const bool isSynth = grp == 1;
+    const double* sig = isSynth ? sw : xw;
+    const int m0 = (grp == 2) ? AC_R : (grp == 3) ? 2 * AC_R - 1 : 0;
+    const int order = isSynth ? g.ordS : g.ordV;
     for (int fb = 0; fb < AV_BATCH; ++fb) {
         const int k = k0 + fb;
         if (k >= g.nFramesV) break;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
         double* rowV = rV + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordV);
         double* rowS = rS + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordS);
         if (seg == 0) {
-            double* r = (grp < 3) ? rowV : rowS;
+            double* r = isSynth ? rowS : rowV;
 #pragma unroll
             for (int j = 0; j < AC_R; ++j) {
                 const int m = m0 + j;
@@ -295,7 +302,7 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
-    const int FS2 = (FS + 15) / 16 * 16 + 2;  // even frame stride: side-chain group on the even banks, voice group 2 (offset 27) on the odd
+    const int FS2 = (FS + 15) / 16 * 16 + 1;  // odd distance between the voice and the side-chain copy (see k_voc_autocorr2)
     const int ringLen = 0;   // (no raw-sample ring any more: see k_voc_autocorr2)
     const size_t smem2 = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS2 + ringLen)) * sizeof(double);
     // the streaming form needs its seven warps' windows + rings in shared memory (fits up to 88.2 kHz frames)

@@ -59,6 +59,9 @@ class Group:
     def max(self, value):
         return self._reduce(value, self.dist.ReduceOp.MAX if self.dist else None)
 
+    def min(self, value):
+        return self._reduce(value, self.dist.ReduceOp.MIN if self.dist else None)
+
     def sum(self, value):
         return self._reduce(value, self.dist.ReduceOp.SUM if self.dist else None)
 
