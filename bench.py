@@ -75,6 +75,87 @@ def slot_model(sz, prm):
             "voc_per_sample": sum(voc.values()) / hopV, "pitch_per_sample": sum(pitch.values()) / hopP}
 
 
+def mix_capture(workload):
+    """Executed FP64 / FP32 thread-instructions and DRAM bytes per audio sample of every stage, from the newest committed
+    ncu capture (profiles/ncu_mix_*.json, tools/ncu_mix.py). None when there is none for this workload."""
+    import glob
+    try:
+        with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_mix_*.json")))[-1]) as f:
+            mj = json.load(f)
+        w = mj["workloads"].get(workload)
+        if w:
+            w = dict(w, source=mj["source"])
+        return w
+    except Exception:
+        return None
+
+
+def mix_roofline(workload, samples_per_step, ms_per_step, peaks_fp, sm_mhz, n_sm=148):
+    """Instruction-mix roofline of a step: the FP64 and FP32 arithmetic instructions the kernels EXECUTE (ncu), each at the
+    issue rate of its pipe. A DFMA holds the SM sub-partition's dispatch port for two cycles and nothing else issues next to
+    it (profiles/ubench_mix_r02a.txt), so the two terms add: lower_bound = fp64_ops / fp64_rate + fp32_ops / fp32_rate."""
+    w = mix_capture(workload)
+    if not w:
+        return None
+    f64, f32 = w["total"]["fp64_ops_per_sample"], w["total"]["fp32_ops_per_sample"]
+    p64, p32 = peaks_fp["fp64_fma_per_s"], peaks_fp["fp32_fma_per_s"]
+    lb_ms = 1e3 * samples_per_step * (f64 / p64 + f32 / p32)
+    clk = (sm_mhz or 1965.0) * 1e6
+    th64, th32 = n_sm * 64 * clk, n_sm * 128 * clk
+    lb_th = 1e3 * samples_per_step * (f64 / th64 + f32 / th32)
+    return {"fp64_ops_per_sample": f64, "fp32_ops_per_sample": f32, "thread_inst_per_sample": w["total"]["thread_inst_per_sample"],
+            "dram_bytes_per_sample": w["total"]["dram_bytes_per_sample"], "lower_bound_ms": lb_ms, "ms_per_step": ms_per_step,
+            "frac": lb_ms / ms_per_step if ms_per_step else None,
+            "lower_bound_ms_theoretical_rates": lb_th, "frac_theoretical_rates": lb_th / ms_per_step if ms_per_step else None,
+            "issue_rates_per_s": {"fp64_measured": p64, "fp32_measured": p32, "fp64_theoretical": th64, "fp32_theoretical": th32,
+                                  "theoretical": "%d SMs x 64 (FP64) / 128 (FP32) lanes x %.0f MHz" % (n_sm, clk / 1e6)},
+            "per_stage": {k: {"fp64": round(v["fp64_ops_per_sample"], 2), "fp32": round(v["fp32_ops_per_sample"], 2),
+                              "dram_bytes": round(v["dram_bytes_per_sample"], 2)} for k, v in w["stages"].items()},
+            "source": w["source"], "note": "executed arithmetic thread-instructions per audio sample (ncu, %d samples per captured pass) x samples "
+                                           "of a step; DADD / DMUL / FADD / FMUL count like an FMA of their pipe" % w["samples_per_pass_capture"]}
+
+
+def run_sub(vp, args, name, group, peaks_fp, sm_mhz):
+    """Short device-resident run of another BASELINE configuration (5 timed steps) for the driver-observed line."""
+    wl = WORKLOADS[name]
+    fs, B = wl["fs"], wl["B"]
+    n = int(fs * wl["seconds"]) // B * B
+    S = wl["streams"]
+    prm = vp.default_params(**wl["params"])
+    eng = vp.Engine(fs, B, S, n // B, params=prm, device=group.local_rank)
+    try:
+        nb = S * n * 4
+        dv, dl, do = eng.device_alloc(nb), eng.device_alloc(nb), eng.device_alloc(nb)
+        eng.synth_device(0, group.rank * S, S, n, n, dv, dl, None)
+        for _ in range(3):
+            eng.reset()
+            eng.process_device(n // B, dv, dl, None, do, None, n, sync=False)
+        eng.sync()
+        steps = 5
+        eng.timer_record(0)
+        for _ in range(steps):
+            eng.reset()
+            eng.process_device(n // B, dv, dl, None, do, None, n, sync=False)
+        eng.timer_record(1)
+        eng.sync()
+        sec = eng.timer_elapsed_ms(0, 1) * 1e-3
+        sm = slot_model(eng.sizes, prm)
+        slots = (sm["voc_per_sample"] if prm.vocBool else 0.0) + (sm["pitch_per_sample"] if prm.pitchBool else 0.0)
+        ms = 1e3 * sec / steps
+        res = {"workload": wl["desc"], "value": S * n / fs * steps / sec, "unit": "audio-s/s", "ms_per_step": ms, "steps": steps, "warmup": 3,
+               "streams": S, "seconds_per_stream": n / fs,
+               "chain_frac": slots * S * n * steps / sec / peaks_fp["fp32_fma_per_s"], "slots_per_sample": slots}
+        mx = mix_roofline(name, float(S) * n, ms, peaks_fp, sm_mhz)
+        if mx:
+            res["mix_frac"] = mx["frac"]
+            res["mix_lower_bound_ms"] = mx["lower_bound_ms"]
+        for p_ in (dv, dl, do):
+            eng.device_free(p_)
+        return res
+    finally:
+        eng.close()
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons of one GPU, sampled every 200 ms while running."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -339,7 +420,13 @@ def run_engine(args, wl, group):
         io_bytes = 12.0 * samples_rank  # voice + synth ch0 in, one channel out (float32)
         # DRAM bytes of that kernel from the committed ncu --set full capture (per sample there), scaled to one launch here
         traffic, traffic_note = None, None
+        mcap = mix_capture(args.workload)
+        if mcap and kname in mcap["stages"]:
+            traffic = mcap["stages"][kname]["dram_bytes_per_sample"] * samples_rank / kcnt
+            traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum of the %s kernels in %s, per sample x samples of one launch" % (kname, mcap["source"])
         try:
+            if traffic is not None:
+                raise LookupError
             import glob
             with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))[-1]) as f:  # newest capture
                 tj = json.load(f)
@@ -359,7 +446,10 @@ def run_engine(args, wl, group):
                                                          "frac": kdfma / (kms * 1e-3) / peaks_fp["fp64_fma_per_s"],
                                                          "note": "this kernel is FP64-pipe bound: algorithmic DFMAs / event time vs the measured DFMA issue rate"}),
                     "chain": {"slots_per_sample": chain_slots, "achieved_tflops": 2.0 * chain_slots * samples_rank / dev_s / 1e12,
-                              "frac": chain_slots * samples_rank / dev_s / p32 if p32 else None},
+                              "frac": chain_slots * samples_rank / dev_s / p32 if p32 else None,
+                              "note": "direct-form op count of SURVEY App. C.5 (the contract number); roofline.mix is the same step against "
+                                      "the instructions the kernels execute"},
+                    "mix": mix_roofline(args.workload, float(S) * n, 1e3 * dev_s / args.steps, peaks_fp, clocks.get("sm_max_mhz")),
                     "hbm": {"achieved_gbs": io_bytes / dev_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src,
                             "frac": io_bytes / dev_s / 1e9 / peaks.get("hbm_gbs", 1.0), "algorithmic_bytes_per_sample": 12},
                     "fp64_fma_per_s": peaks_fp["fp64_fma_per_s"], "fp32_fma_per_s": p32,
@@ -381,6 +471,14 @@ def run_engine(args, wl, group):
         if cpu is not None:
             line["cpu_baseline"] = cpu
     eng.close()
+    if group.world == 1 and not args.no_sub and not args.streams and args.workload == "chain48":
+        # the other BASELINE configurations, driver-observed: chain @ 44.1 kHz is the north_star target line
+        line["other_workloads"] = {}
+        for name in ("chain44", "voc44", "pitch44"):
+            try:
+                line["other_workloads"][name] = run_sub(vp, args, name, group, peaks_fp, clocks.get("sm_max_mhz"))
+            except Exception as ex:
+                line["other_workloads"][name] = {"error": str(ex)}
     if group.rank == 0:
         if group.world == 1 and not args.no_stream and not args.streams:
             try:
@@ -496,6 +594,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the benchmarked size")
     ap.add_argument("--parity-streams", type=int, default=16, help="streams per rank compared with the reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--cpu-streams", type=int, default=0)
     ap.add_argument("--ref-streams", type=int, default=0)
     ap.add_argument("--stream-blocks", type=int, default=1500, help="blocks timed by the streaming latency test")

@@ -102,6 +102,12 @@ int vp_engine_create(vp_engine** e, int device);
 void vp_engine_destroy(vp_engine* e);
 const char* vp_last_error(const vp_engine* e);
 
+/* Largest lpcVoice / lpcSynth that vp_engine_set_params may be given on a RUNNING stream (the reference re-reads both orders
+ * at every vocoder frame, VocoderProcess.cpp:193-194, and sizes its vectors for the ends of the parameter ranges, :50-57).
+ * Call before vp_engine_prepare: the coefficient rows of the workspace are sized for it. Without it the maximum is what the
+ * parameters say at vp_engine_prepare. 0 = no reservation. */
+int vp_engine_reserve_orders(vp_engine* e, int maxLpcVoice, int maxLpcSynth);
+
 /* prepareToPlay(sampleRate, samplesPerBlock) for nStreams independent
  * plug-in instances. maxBlocks bounds nBlocks of later process calls.
  * workspaceBytes: device memory the engine may use for intermediates
@@ -110,10 +116,13 @@ int vp_engine_prepare(vp_engine* e, double sampleRate, int samplesPerBlock, int 
                       size_t workspaceBytes);
 /* Replaces the reference's parameter pulls (treeState.getRawParameterValue(id)->load(); VocoderProcess.cpp:193-194,291,
  * PitchProcess.cpp:70,206,336, PluginProcessor.cpp:212-230). Before prepare: anything in the plug-in's ranges. Between
- * process calls of a running stream (automation): the four gains and keyPitch take effect exactly as in the reference
- * (gainVoc per vocoder frame, gainPitch per emitted chunk, gainVoice / gainSynth per block, keyPitch per pitch frame);
- * lpcVoice / lpcSynth / vocBool / pitchBool changes return VP_E_STATE until vp_engine_reset; lpcPitch is fixed at prepare
- * (as in the reference, PitchProcess.cpp:70). */
+ * process calls of a running stream (automation) every parameter takes effect where the reference reads it: gainVoc per
+ * vocoder frame, gainPitch per emitted chunk, gainVoice / gainSynth per block, keyPitch per pitch frame, lpcVoice / lpcSynth
+ * per vocoder frame (frames in flight keep the order they started with; VP_E_STATE beyond vp_engine_reserve_orders / the
+ * orders at prepare), vocBool / pitchBool per block: a block with vocBool off skips VocoderProcess::process (its frame grid
+ * freezes relative to the block, frames in flight still come out), a block with pitchBool off is PitchProcess::silence()
+ * (PluginProcessor.cpp:214-221, PitchProcess.cpp:146-158). lpcPitch is read in PitchProcess::prepare only (:70): a change on
+ * a running stream is ignored until the next vp_engine_prepare, as in the reference. */
 int vp_engine_set_params(vp_engine* e, const vp_params* p);
 int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out);
 /* Layout the engine chose in vp_engine_prepare: streams processed per pass (nStreams / streamsPerPass passes per call),
@@ -125,6 +134,22 @@ int vp_engine_get_info(const vp_engine* e, int* streamsPerPass, int* historySamp
  * nBlocks = a then nBlocks = b gives the output of one call with nBlocks = a + b (the carried per-stream state is what
  * MyBuffer / VocoderProcess / PitchProcess keep between processBlock calls). */
 int vp_engine_reset(vp_engine* e);
+
+/* Host-only helper (no CUDA): the frame grids a sequence of process calls produces -- call c processes nBlocks[c] blocks
+ * with params[c] in force (only vocBool, pitchBool, lpcVoice, lpcSynth matter). For hosts that want to know how many frame
+ * records a call will report, and for the CPU tests of the grid bookkeeping. */
+typedef struct vp_call_plan {
+    long long firstBlock;        /* blocks processed before this call */
+    int offV, nFramesV;          /* first new vocoder frame (samples after the call's start) and how many start in the call */
+    int carriedV;                /* vocoder frames of earlier calls that lie on this call's grid */
+    int rowOrderV, rowOrderS;    /* width - 1 of the call's coefficient rows (>= lpcVoice / lpcSynth in force) */
+    int offP, nFramesP;          /* same for the pitch frames */
+    int vocMix, pitchMix;        /* the call's output contains vocoder / pitch-corrector samples */
+    int rowsOrphaned, orphansLive; /* vocoder frames left off the grid by a vocBool-off block: moved at this call / emitting in it */
+    int carryPosP[2], carryChunksP[2]; /* carried pitch frames: start relative to the call, chunks of theirs that are ever processed */
+} vp_call_plan;
+int vp_grid_plan(double sampleRate, int samplesPerBlock, int nCalls, const int* nBlocks, const vp_params* params,
+                 vp_call_plan* out);
 
 /* ---- processing ----------------------------------------------------------- */
 /* Device-resident batch. Layouts (row stride = strideSamples floats):

@@ -28,6 +28,27 @@ CASES = {
                                schedule=[(40, dict(gainVoc=-6.0, gainPitch=3.0)), (97, dict(keyPitch=12)),
                                          (150, dict(gainVoice=-60.0, gainSynth=-10.0, keyPitch=7)),
                                          (201, dict(gainVoc=2.0, gainPitch=-4.0, keyPitch=0))]),
+    # every parameter automated, incl. the LPC orders (per vocoder frame, VocoderProcess.cpp:193-194) and the two enables (per
+    # block, PluginProcessor.cpp:214-221; pitchBool off = PitchProcess::silence()); lpcPitch mid-stream is ignored (read in
+    # prepare only). The schedule of tests/test_oracle.py::test_oracle_automation_bit_exact_vs_reference_build.
+    "chain44_toggles": dict(fs=44100.0, B=256, seconds=2.5, input=("synth", 0, 77), params=dict(keyPitch=5, gainSynth=-25.0),
+                            reserve=(64, 9),
+                            schedule=[(30, dict(lpcVoice=20, lpcSynth=9)), (77, dict(gainVoc=-4.0, keyPitch=12, gainVoice=-12.0)),
+                                      (120, dict(pitchBool=0)), (160, dict(pitchBool=1, lpcVoice=64, keyPitch=1)), (200, dict(vocBool=0)),
+                                      (260, dict(vocBool=1, gainPitch=-7.0, lpcSynth=3)), (330, dict(lpcPitch=9))]),
+    # 48 kHz, block 128: hop 139 and chunk 278 are larger than the block, so a skipped block makes the frame grids slip
+    # against the blocks, frames in flight outlive short off-stretches (orphaned vocoder frames, cut pitch frames)
+    "chain48_b128_toggles": dict(fs=48000.0, B=128, seconds=2.0, input=("synth", 0, 8), params=dict(keyPitch=3),
+                                 reserve=(48, 8),
+                                 schedule=[(100, dict(vocBool=0)), (101, dict(vocBool=1)), (140, dict(vocBool=0)), (143, dict(vocBool=1, lpcVoice=24)),
+                                           (200, dict(pitchBool=0)), (201, dict(pitchBool=1)), (260, dict(pitchBool=0, vocBool=0)),
+                                           (263, dict(pitchBool=1)), (266, dict(vocBool=1, lpcVoice=48, lpcSynth=8)),
+                                           (400, dict(pitchBool=0)), (407, dict(pitchBool=1, lpcVoice=40, lpcSynth=5)),
+                                           (500, dict(vocBool=0, gainVoice=-10.0)), (520, dict(vocBool=1)), (600, dict(vocBool=0)), (601, dict(vocBool=1))]),
+    # 48 kHz, block 1024: whole blocks of vocoder / pitch corrector switched off
+    "chain48_b1024_toggles": dict(fs=48000.0, B=1024, seconds=2.5, input=("synth", 0, 9), params=dict(),
+                                  schedule=[(20, dict(vocBool=0)), (22, dict(vocBool=1)), (40, dict(pitchBool=0)), (41, dict(pitchBool=1)),
+                                            (60, dict(vocBool=0, pitchBool=0)), (63, dict(vocBool=1, pitchBool=1)), (90, dict(pitchBool=0))]),
     # leading silence -> gates (vocoder + pitch) then voiced onset; KAT-style inputs delayed by 0.5 s
     "gate_onset": dict(fs=44100.0, B=1024, seconds=2.0, input=("kat_delayed", 22050), params=dict(keyPitch=3)),
 }

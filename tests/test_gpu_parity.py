@@ -64,7 +64,8 @@ def run_engine_scheduled(vp, case, voice, sl, sr, extra_cuts=()):
     nb = len(voice) // B
     sched = dict(case_schedule(case))
     cuts = sorted(set([0, nb]) | set(sched) | set(extra_cuts))
-    eng = vp.Engine(fs, B, 1, max(b - a for a, b in zip(cuts, cuts[1:])), params=vp.default_params(**case["params"]))
+    eng = vp.Engine(fs, B, 1, max(b - a for a, b in zip(cuts, cuts[1:])), params=vp.default_params(**case["params"]),
+                    reserve_orders=case.get("reserve"))
     try:
         outL, outR, pf = [], [], []
         vf = {"gated": [], "EeVoice": [], "EeSynth": [], "g": []}
@@ -274,26 +275,58 @@ def test_consecutive_calls_continue_the_streams(vp, fs, B, pieces, params):
         eng.close()
 
 
-def test_automation_is_independent_of_call_splitting_and_rejects_layout_changes(vp):
+def test_automation_is_independent_of_call_splitting(vp):
     """Parameter changes between calls: the result depends on WHERE (which block) they happen, not on how the blocks in
-    between are grouped into calls; orders / enables mid-stream are refused until a reset."""
+    between are grouped into calls -- gains / key, and the LPC orders and enables too (frames in flight across a call
+    boundary keep their order; orphaned vocoder frames and cut pitch frames come out the same)."""
+    for name, cuts in (("chain44_automation", (1, 39, 41, 98, 149, 151, 200, 257)),
+                       ("chain44_toggles", (1, 29, 31, 119, 121, 122, 161, 199, 201, 202, 203, 259, 261, 262, 400)),
+                       ("chain48_b128_toggles", tuple(range(95, 150)) + (261, 262, 264, 265, 267, 268, 401, 499, 501, 519, 521, 599, 602, 603)),
+                       ("chain48_b1024_toggles", (1, 19, 21, 23, 24, 42, 43, 61, 62, 64, 65, 91, 92))):
+        case = CASES[name]
+        voice, sl, sr = case_inputs(vp, case)
+        aL, aR, fa = run_engine_scheduled(vp, case, voice, sl, sr)
+        bL, bR, fb = run_engine_scheduled(vp, case, voice, sl, sr, extra_cuts=cuts)
+        assert np.array_equal(aL, bL) and np.array_equal(aR, bR), name
+        key = lambda f: (f.flags, f.period, f.note, list(f.anMarks[:f.nAn]), list(f.stMarks[:f.nSt]))
+        assert [key(f) for f in fa.pitch_frames(0)] == [key(f) for f in fb.pitch_frames(0)], name
+
+
+def test_orders_beyond_the_reservation_are_refused_and_lpc_pitch_is_ignored_mid_stream(vp):
     case = CASES["chain44_automation"]
     voice, sl, sr = case_inputs(vp, case)
-    aL, aR, _ = run_engine_scheduled(vp, case, voice, sl, sr)
-    bL, bR, _ = run_engine_scheduled(vp, case, voice, sl, sr, extra_cuts=(1, 39, 41, 98, 149, 151, 200, 257))
-    assert np.array_equal(aL, bL) and np.array_equal(aR, bR)
+    n4 = 4 * 512
     eng = vp.Engine(case["fs"], case["B"], 1, 8, params=vp.default_params(**case["params"]))
     try:
-        eng.process(voice[None, :4 * 512], sl[None, :4 * 512], sr[None, :4 * 512])
-        for bad in (dict(lpcVoice=30), dict(lpcSynth=7), dict(vocBool=0), dict(pitchBool=0)):
+        eng.process(voice[None, :n4], sl[None, :n4], sr[None, :n4])
+        for bad in (dict(lpcVoice=41), dict(lpcSynth=6)):  # beyond the orders at prepare and nothing reserved
             with pytest.raises(vp.EngineError) as ei:
                 eng.set_params(vp.default_params(**dict(case["params"], **bad)))
             assert ei.value.code == vp.VP_E_STATE
+        for fine in (dict(lpcVoice=30), dict(lpcSynth=3), dict(vocBool=0), dict(pitchBool=0), dict(lpcPitch=9)):
+            eng.set_params(vp.default_params(**dict(case["params"], **fine)))
+            eng.process(voice[None, n4:2 * n4], sl[None, n4:2 * n4], sr[None, n4:2 * n4])
         eng.reset()
-        eng.set_params(vp.default_params(**dict(case["params"], lpcVoice=30)))  # fine after prepareToPlay
-        eng.process(voice[None, :4 * 512], sl[None, :4 * 512], sr[None, :4 * 512])
+        eng.set_params(vp.default_params(**dict(case["params"], lpcVoice=64)))  # after prepareToPlay: re-sized by the next prepare
+        with pytest.raises(vp.EngineError) as ei:
+            eng.process(voice[None, :n4], sl[None, :n4], sr[None, :n4])
+        assert ei.value.code == vp.VP_E_STATE
     finally:
         eng.close()
+    # lpcPitch on a running stream changes nothing (PitchProcess.cpp:70: read in prepare only)
+    a = vp.Engine(case["fs"], case["B"], 1, 8, params=vp.default_params(keyPitch=3))
+    b = vp.Engine(case["fs"], case["B"], 1, 8, params=vp.default_params(keyPitch=3))
+    try:
+        outs = []
+        for eng, change in ((a, False), (b, True)):
+            l1, _ = eng.process(voice[None, :n4], sl[None, :n4], sr[None, :n4])
+            if change:
+                eng.set_params(vp.default_params(keyPitch=3, lpcPitch=9))
+            l2, _ = eng.process(voice[None, n4:3 * n4], sl[None, n4:3 * n4], sr[None, n4:3 * n4])
+            outs.append(np.concatenate([l1, l2], axis=1))
+        assert np.array_equal(outs[0], outs[1])
+    finally:
+        a.close(); b.close()
 
 
 def test_block_by_block_streaming_matches_oracle(vp, oracle):
@@ -375,7 +408,7 @@ def test_long_streams_match_oracle(vp, fs, S, secs, params, ws_mb):
     voice, sl, _ = vp.synth_host(fs, S, n, flavour=0, first_stream=2000, want_right=False)
     eng = vp.Engine(fs, B, S, n // B, params=vp.default_params(**params), workspace_bytes=ws_mb << 20)
     try:
-        assert eng.info()["streams_per_pass"] * 3 <= S + 2, "workspace too large: fewer than 3 passes"
+        assert -(-S // eng.info()["streams_per_pass"]) >= 3, "workspace too large: fewer than 3 passes"
         outL, _ = eng.process(voice, sl, None, want_right=False)
         refs, kind = reference_runs([(fs, B, voice[s], sl[s], None, params) for s in range(S)])
         tot = chk = flg = 0
@@ -459,9 +492,8 @@ def test_errors_are_codes(vp):
         assert ei.value.code == vp.VP_E_RANGE
         z4 = z[:, :4 * 1024]
         eng.process(z4, z4, z4)
-        with pytest.raises(vp.EngineError) as ei:
-            eng.set_params(vp.default_params(lpcPitch=16))  # read in prepare only (PitchProcess.cpp:70): not mid-stream
-        assert ei.value.code == vp.VP_E_STATE
+        eng.set_params(vp.default_params(lpcPitch=16))  # read in prepare only (PitchProcess.cpp:70): ignored mid-stream
+        eng.process(z4, z4, z4)
         # on a reset engine it is accepted, but the workspace has to be sized again before the next block
         eng.reset()
         eng.set_params(vp.default_params(lpcPitch=16))

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
     "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset", "vp_engine_stream_buffers", "vp_engine_stream_block",
-    "vp_engine_stream_stats", "vp_engine_get_info",
+    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan",
 ]
 
 
@@ -51,6 +51,13 @@ class PitchFrame(C.Structure):
                 ("periodNew", C.c_int32), ("note", C.c_int32), ("nAn", C.c_int32), ("nSt", C.c_int32),
                 ("anStale", C.c_int32), ("nAnOv", C.c_int32), ("anMarks", C.c_int32 * VP_MAX_MARKS),
                 ("stMarks", C.c_int32 * VP_MAX_MARKS), ("beta", C.c_double)]
+
+
+class CallPlan(C.Structure):
+    _fields_ = [("firstBlock", C.c_longlong), ("offV", C.c_int), ("nFramesV", C.c_int), ("carriedV", C.c_int),
+                ("rowOrderV", C.c_int), ("rowOrderS", C.c_int), ("offP", C.c_int), ("nFramesP", C.c_int),
+                ("vocMix", C.c_int), ("pitchMix", C.c_int), ("rowsOrphaned", C.c_int), ("orphansLive", C.c_int),
+                ("carryPosP", C.c_int * 2), ("carryChunksP", C.c_int * 2)]
 
 
 class EngineError(RuntimeError):
@@ -84,6 +91,8 @@ def load_library(path=None):
         "vp_engine_set_params": (i, [vp, C.POINTER(Params)]),
         "vp_engine_get_sizes": (i, [vp, C.POINTER(Sizes)]),
         "vp_engine_get_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]),
+        "vp_engine_reserve_orders": (i, [vp, i, i]),
+        "vp_grid_plan": (i, [dbl, i, i, C.POINTER(i), C.POINTER(Params), C.POINTER(CallPlan)]),
         "vp_engine_process_device": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_process_host": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_sync": (i, [vp]),
@@ -135,6 +144,20 @@ def sizes_for(sample_rate, block, key=12):
     if rc != VP_OK:
         raise EngineError(rc, "vp_sizes_for(%r, %r, %r)" % (sample_rate, block, key))
     return s.as_dict()
+
+
+def grid_plan(sample_rate, block, calls):
+    """calls: [(nBlocks, Params), ...] -> list of CallPlan (host-only: the frame grids those process calls produce)."""
+    n = len(calls)
+    nb = (C.c_int * n)(*[int(c[0]) for c in calls])
+    ps = (Params * n)()
+    for k, (_, q) in enumerate(calls):
+        C.memmove(C.byref(ps[k]), C.byref(q), C.sizeof(Params))
+    out = (CallPlan * n)()
+    rc = load_library().vp_grid_plan(float(sample_rate), int(block), n, nb, ps, out)
+    if rc != VP_OK:
+        raise EngineError(rc, "vp_grid_plan")
+    return list(out)
 
 
 def synth_host(sample_rate, n_streams, n_samples, flavour=0, first_stream=0, want_right=True):
@@ -192,7 +215,7 @@ class Engine:
     Engine(...) ~ construct + set parameters + prepareToPlay(sampleRate, samplesPerBlock);
     process(...) ~ nBlocks consecutive processBlock calls per stream."""
 
-    def __init__(self, sample_rate, block, n_streams, max_blocks, params=None, device=0, workspace_bytes=0):
+    def __init__(self, sample_rate, block, n_streams, max_blocks, params=None, device=0, workspace_bytes=0, reserve_orders=None):
         self.lib = load_library()
         self.h = C.c_void_p()
         rc = self.lib.vp_engine_create(C.byref(self.h), int(device))
@@ -201,6 +224,8 @@ class Engine:
             raise EngineError(rc, "vp_engine_create failed (no usable CUDA device %d; there is no CPU fallback)" % device)
         self.sample_rate, self.block, self.n_streams, self.max_blocks = float(sample_rate), int(block), int(n_streams), int(max_blocks)
         self.params = params or default_params()
+        if reserve_orders:  # (maxLpcVoice, maxLpcSynth) that set_params may be given while the streams run
+            self._check(self.lib.vp_engine_reserve_orders(self.h, int(reserve_orders[0]), int(reserve_orders[1])))
         self._check(self.lib.vp_engine_set_params(self.h, C.byref(self.params)))
         self._check(self.lib.vp_engine_prepare(self.h, self.sample_rate, self.block, self.n_streams, self.max_blocks,
                                                int(workspace_bytes)))

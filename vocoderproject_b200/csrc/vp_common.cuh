@@ -11,6 +11,10 @@
 
 #define VP_ORDER_MAX 100  // PluginProcessor.cpp:53-59 (parameter range ends)
 #define VP_SLOTS 32       // >= anCap (20 at 44.1/48 kHz); one warp lane per storage slot
+#define VP_VC 4           // vocoder frames of earlier calls that can still overlap a call's first positions (wlen = 4 hop)
+#define VP_PC 2           // pitch frames of earlier calls that can still own output positions of a call (L = 4 chunks, hop = 3)
+#define VP_ORPH 8         // slots for vocoder frames that are off the current frame grid (see VPGeom::orphPos)
+#define VP_NOFRAME (-(1 << 30))
 
 // Geometry + parameters of one prepared engine, passed by value to kernels.
 struct VPGeom {
@@ -37,7 +41,28 @@ struct VPGeom {
     int offV, offP;      // local position of the first vocoder / pitch frame that starts inside this call
     int kV0, fP0;        // global index of that frame (frames before it belong to earlier calls)
     int hasPrev;         // 1 = an earlier call exists (carry rows / pending pitch frame are valid)
+    // ---- parameters that change between calls of a running stream (VocoderProcess.cpp:193-194, PluginProcessor.cpp:214-221)
+    // Coefficient rows of this call are synV + 1 / synS + 1 doubles wide: the analysis order of the call's own frames
+    // (ordV / ordS) or, when a frame carried from an earlier call had a larger order, that one -- rows are zero padded,
+    // and a zero tap changes neither the whitening FIR nor the all-pole recursion.
+    int synV, synS;
+    int vocMix, pitchMix;  // the mix adds the vocoder / pitch plane: the path is on, or frames of earlier calls still emit
+    // Vocoder frames of earlier calls that are NOT on this call's frame grid: VocoderProcess::process was skipped for some
+    // blocks in between (vocBool off), and its startSample -- hence the grid -- froze relative to the block. Their output
+    // was already in the reference's ring; here a small kernel finishes them from their carried rows ("orphan" store).
+    int orphPos[VP_ORPH];            // call-local start (VP_NOFRAME = empty slot)
+    int orphOrdV[VP_ORPH], orphOrdS[VP_ORPH];
+    // Carried pitch frames (slot j <-> frame index f = j - VP_PC): call-local start and how many of their 4 chunks are ever
+    // processed -- PitchProcess::silence() (pitchBool off, PitchProcess.cpp:146-158) clears the marks, and the chunks of the
+    // frame in flight that had not been handled yet then do nothing (processChunkCont, :253-271).
+    int carryPosP[VP_PC], carryLimP[VP_PC];
 };
+
+// start of pitch frame f in call-local coordinates / number of its chunks that are processed
+__host__ __device__ inline long long vp_ppos(const VPGeom& g, int f) {
+    return f >= 0 ? (long long)f * g.hopP + g.offP : (long long)g.carryPosP[f + VP_PC];
+}
+__host__ __device__ inline int vp_plim(const VPGeom& g, int f) { return f >= 0 ? 4 : g.carryLimP[f + VP_PC]; }
 
 // Per-frame row of the vocoder's autocorrelation workspace: lags 0..order (raw sums) followed by the frame's last
 // `order` windowed samples (the Levinson kernel's residual-energy correction reads them instead of re-gathering).
@@ -50,11 +75,9 @@ __host__ __device__ inline int vp_rowlen(int order) { return 2 * order + 1; }
 
 // Frame-indexed vocoder workspace (coefficient rows, energies, gains): per stream VP_VC carry rows (the last frames
 // of the previous call: they still overlap this call's first output positions) followed by this call's frames.
-#define VP_VC 4
 __host__ __device__ inline size_t vp_vrow(const VPGeom& g, int s, int k) { return (size_t)s * (size_t)(g.nFramesV + VP_VC) + VP_VC + k; }
 // Pitch frames: two carry slots (the last two frames of earlier calls can still own output positions of this call:
 // frame length 4 chunks, hop 3 chunks), then this call's frames.
-#define VP_PC 2
 __host__ __device__ inline size_t vp_prow(const VPGeom& g, int s, int f) { return (size_t)s * (size_t)(g.nFramesP + VP_PC) + VP_PC + f; }
 
 // PitchProcess state that survives from one frame to the next (PitchProcess.cpp:76-92, :415-425) and therefore from one
@@ -195,9 +218,17 @@ void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
 void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
                    const float* synthR, const float* outV, const float* outP, float* outL, float* outR);
 
-void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int rowBytes, int C, long long wsRowsPerStream);
-void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int rowBytes, int C, long long nNew,
+// rows of wsRowBytes in the workspace <-> rows of carryRowBytes in the carried store (the shorter length is copied, the rest
+// of the destination row is zero filled)
+void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int wsRowBytes, int carryRowBytes, int C,
+                        long long wsRowsPerStream);
+void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int wsRowBytes, int carryRowBytes, int C, long long nNew,
                          long long wsRowsPerStream);
+// row `srcRow` of every stream's C-row carried store -> slot `dstSlot` of its D-slot store (same row bytes)
+void vp_launch_row_move(cudaStream_t st, void* dst, const void* src, int S, int rowBytes, int C, int srcRow, int D, int dstSlot);
+void vp_launch_marks_silence(cudaStream_t st, VPMarkState* carry, int S);
+void vp_launch_voc_orphans(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth, const double* oAV,
+                           const double* oAS, const double* oEeS, const double* oG, float* outV, int capV, int capS);
 void vp_launch_hist_update(cudaStream_t st, float* hNew, const float* hOld, const float* x, int S, int H, long long n,
                            long long stride);
 

@@ -22,6 +22,33 @@ static const char* kStageNames[VP_NSTAGES] = {"gate", "voc_autocorr", "voc_levin
 
 thread_local cudaError_t g_vpLaunchError = cudaSuccess;  // per host thread: engines driven from different threads do not see each other's launch failures
 
+// ---------------------------------------------------------------------------
+// Frame grids: absolute positions on the delayed timeline. Every stream of an engine shares them (one parameter set per
+// engine), so this is plain host state; it is what VocoderProcess::startSample, PitchProcess::startSample and
+// PitchProcess::nChunk are in the reference, plus the bookkeeping of the frames that outlive the call they started in.
+// Pure host logic (no CUDA): vp_grid_plan runs it stand-alone.
+// ---------------------------------------------------------------------------
+struct GridState {
+    int B = 0;
+    vp_sizes z;
+    long long blocksDone = 0;          // host blocks processed since prepare / reset
+    long long nextFrameV = 0;          // start of the next vocoder frame = block start + VocoderProcess::startSample
+    int alignedV = 0;                  // carried vocoder frames that lie on the current grid: carry rows VP_VC - alignedV .. VP_VC - 1
+    int alignedOrdV[VP_VC] = {0}, alignedOrdS[VP_VC] = {0};  // their analysis orders, by carry row
+    long long orphAbs[VP_ORPH];        // frames left off the grid by a vocBool-off stretch: absolute start, -1 = free slot
+    int orphOrdV[VP_ORPH] = {0}, orphOrdS[VP_ORPH] = {0};
+    long long nextChunkP = 0;          // start of the next pitch chunk = block start + PitchProcess::startSample
+    int nChunk = 0;                    // PitchProcess::nChunk
+    long long carryAbsP[VP_PC];        // carried pitch frames: absolute start (-1 = none) and chunks that are processed at all
+    int carryLimP[VP_PC] = {0};
+    void reset() {
+        blocksDone = 0; nextFrameV = 0; alignedV = 0; nextChunkP = 0; nChunk = 0;
+        for (int j = 0; j < VP_ORPH; ++j) orphAbs[j] = -1;
+        for (int j = 0; j < VP_PC; ++j) { carryAbsP[j] = -1; carryLimP[j] = 0; }
+    }
+};
+struct GridMove { int srcRow, dstSlot; };  // carry row -> orphan slot (device rows follow the host bookkeeping)
+
 struct vp_engine {
     int device = 0;
     bool prepared = false;
@@ -48,7 +75,6 @@ struct vp_engine {
     uint8_t* dGate = nullptr;
     double* dGatePart = nullptr;
     // ---- state carried from call to call, for all S streams (vp_engine_reset zeroes it = prepareToPlay)
-    long long blocksDone = 0;          // host blocks processed since prepare / reset
     int H = 0;                         // input history length
     int gateCarry = 0;                 // carried gate block partials per stream (inSize / B + 1)
     int histCur = 0;                   // which of the two history buffers is current
@@ -92,6 +118,9 @@ struct vp_engine {
     uint64_t launches = 0, yinRechecked = 0, yinFrames = 0;
     int passCount = 0;      // passes of the current call
     int capV = 0, capS = 0, capP = 0;  // LPC orders the workspace was sized for
+    int reserveV = 0, reserveS = 0;    // vp_engine_reserve_orders: largest lpcVoice / lpcSynth that may be set mid-stream
+    GridState gs;                      // frame grids and carried-frame bookkeeping (host side, shared by all streams)
+    double *oAV = nullptr, *oAS = nullptr, *oEeS = nullptr, *oG = nullptr;  // orphan store [S][VP_ORPH][...]
     std::vector<cudaEvent_t> ev;
     std::vector<int> evStage;
     size_t evUsed = 0;
@@ -245,7 +274,7 @@ static int build_tables(vp_engine* e) {
 
 static void free_workspace(vp_engine* e) {
     void** cptrs[] = {(void**)&e->cGate, (void**)&e->cAV, (void**)&e->cAS, (void**)&e->cEeS, (void**)&e->cG, (void**)&e->cGainHist,
-                      (void**)&e->cFrames, (void**)&e->cMarks};
+                      (void**)&e->cFrames, (void**)&e->cMarks, (void**)&e->oAV, (void**)&e->oAS, (void**)&e->oEeS, (void**)&e->oG};
     for (void** p : cptrs) if (*p) { cudaFree(*p); *p = nullptr; }
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) if (e->cHist[i][j]) { cudaFree(e->cHist[i][j]); e->cHist[i][j] = nullptr; }
     void** ptrs[] = {(void**)&e->dGate, (void**)&e->dRV, (void**)&e->dRS, (void**)&e->dAV, (void**)&e->dAS, (void**)&e->dEeV,
@@ -333,27 +362,39 @@ static int check_params(const vp_params* p) {
     return VP_OK;
 }
 
+extern "C" int vp_engine_reserve_orders(vp_engine* e, int maxLpcVoice, int maxLpcSynth) {
+    if (!e) return VP_E_ARG;
+    if (maxLpcVoice < 0 || maxLpcVoice > 100 || maxLpcSynth < 0 || maxLpcSynth > 30) return vp_err(e, VP_E_RANGE, "order outside the plug-in's range");
+    e->reserveV = maxLpcVoice; e->reserveS = maxLpcSynth;
+    if (e->prepared && (maxLpcVoice > e->capV || maxLpcSynth > e->capS)) {
+        if (e->gs.blocksDone > 0) return vp_err(e, VP_E_STATE, "vp_engine_reserve_orders on a running stream: call it before vp_engine_prepare");
+        e->prepared = false;
+    }
+    return VP_OK;
+}
+
 extern "C" int vp_engine_set_params(vp_engine* e, const vp_params* p) {
     if (!e) return VP_E_ARG;
     int rc = check_params(p);
     if (rc) return vp_err(e, rc, "parameter outside the plug-in's range");
     const bool keyChanged = p->keyPitch != e->prm.keyPitch;
-    // LPC orders size the workspace; lpcPitch is read in prepare only in the reference too (PitchProcess.cpp:70)
-    if (e->prepared && (p->lpcVoice > e->capV || p->lpcSynth > e->capS || p->lpcPitch != e->capP)) {
-        if (e->blocksDone > 0)
-            return vp_err(e, VP_E_STATE, "LPC order beyond what vp_engine_prepare sized (lpcPitch is fixed at prepare): "
-                                         "vp_engine_reset, set the parameters, then vp_engine_prepare again");
+    vp_params q = *p;
+    const bool running = e->prepared && e->gs.blocksDone > 0;
+    // lpcPitch is read in PitchProcess::prepare only (PitchProcess.cpp:70): a change on a running stream has no effect until
+    // the next prepareToPlay, exactly as in the reference
+    if (running) q.lpcPitch = e->capP;
+    // The workspace rows are sized for capV / capS (the orders at vp_engine_prepare, or vp_engine_reserve_orders). On a running
+    // stream an order within that range takes effect at the next vocoder frame (VocoderProcess.cpp:193-194); beyond it the
+    // reference would run past its orderMax vectors (its assert at :141-147) and the engine refuses.
+    if (e->prepared && (q.lpcVoice > e->capV || q.lpcSynth > e->capS || q.lpcPitch != e->capP)) {
+        if (running)
+            return vp_err(e, VP_E_STATE, "lpcVoice / lpcSynth beyond what vp_engine_prepare sized: vp_engine_reserve_orders before "
+                                         "vp_engine_prepare, or vp_engine_reset, set the parameters, vp_engine_prepare");
         e->prepared = false;  // freshly prepared / reset engine: accepted, the workspace must be sized again (vp_engine_prepare)
     }
-    // Mid-stream automation (between two process calls of a running stream) is exact for the gains and the key: every
-    // one of those is read per block / per frame / per chunk in the reference (PluginProcessor.cpp:226-230,
-    // VocoderProcess.cpp:291, PitchProcess.cpp:206,336) and the engine keeps per-frame copies where a frame outlives
-    // the call it started in. The LPC orders and the two enables change the layout of the carried per-stream state
-    // (coefficient rows, frame phase): those need vp_engine_reset (= prepareToPlay) first.
-    if (e->prepared && e->blocksDone > 0 &&
-        (p->lpcVoice != e->prm.lpcVoice || p->lpcSynth != e->prm.lpcSynth || (p->vocBool != 0) != (e->prm.vocBool != 0) ||
-         (p->pitchBool != 0) != (e->prm.pitchBool != 0)))
-        return vp_err(e, VP_E_STATE, "lpcVoice / lpcSynth / vocBool / pitchBool cannot change mid-stream: call vp_engine_reset first");
+    // Every parameter is read where the reference reads it: gains per block / frame / chunk, keyPitch per pitch frame, the
+    // LPC orders per vocoder frame, vocBool / pitchBool per block (PluginProcessor.cpp:214-221).
+    p = &q;
     if (memcmp(&e->prm, p, sizeof *p) != 0) {  // kernel arguments are baked into the captured graphs
         for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
         e->graphs.clear();
@@ -394,7 +435,10 @@ static int reset_state(vp_engine* e) {
     for (size_t i = 0; i < S; ++i) ms[i].beta = 1.0;
     VP_CUDA_OK(cudaMemcpyAsync(e->cMarks, ms.data(), S * sizeof(VPMarkState), cudaMemcpyHostToDevice, e->st));
     VP_CUDA_OK(cudaStreamSynchronize(e->st));
-    e->blocksDone = 0;
+    VP_CUDA_OK(cudaMemsetAsync(e->oEeS, 0, S * VP_ORPH * sizeof(double), e->st));
+    VP_CUDA_OK(cudaStreamSynchronize(e->st));
+    e->gs.B = e->B; e->gs.z = e->sz;
+    e->gs.reset();
     e->histCur = 0;
     e->failed = false;
     return VP_OK;
@@ -428,6 +472,8 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     const long long n = (long long)maxBlocks * B;
     int nV, nP;
     frame_counts(z, n, &nV, &nP);
+    nV += 1; nP += 1;  // a frame grid that a vocBool / pitchBool-off stretch has shifted can put one more frame into a call
+    const int capV = std::max(e->prm.lpcVoice, e->reserveV), capS = std::max(e->prm.lpcSynth, e->reserveS), capP = e->prm.lpcPitch;
     {
         const char* ym = getenv("VP_YIN_MODE");
         e->yinDirect = (ym && strcmp(ym, "direct") == 0) ? 1 : 0;
@@ -437,8 +483,8 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     gy.tauMax = z.tauMax; gy.nFramesP = nP;
     const size_t yinP = e->yinDirect ? 0 : (size_t)vp_yin_corr_chunks(gy) * (size_t)vp_yin_corr_lagpad(gy);
     // bytes of intermediates per stream
-    const size_t perStream = (size_t)maxBlocks * 33 + (size_t)nV * 8 * (size_t)(3 * (e->prm.lpcVoice + 1) + 3 * (e->prm.lpcSynth + 1) + 3) +
-                             (size_t)nP * (12 + sizeof(vp_pitch_frame) + 16 * (size_t)(e->prm.lpcPitch + 1) + 4 * (size_t)z.frameLenP) +
+    const size_t perStream = (size_t)maxBlocks * 33 + (size_t)nV * 8 * (size_t)(3 * (capV + 1) + 3 * (capS + 1) + 3) +
+                             (size_t)nP * (12 + sizeof(vp_pitch_frame) + 16 * (size_t)(capP + 1) + 4 * (size_t)z.frameLenP) +
                              (size_t)n * 8 + yinP * 4 + (size_t)(3 * nP + 1) * 8;
     if (workspaceBytes == 0) {
         // default: up to 64 GiB, never more than 40 % of what is free now (the caller's I/O arrays come on top)
@@ -462,10 +508,10 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     e->H = (z.latency + z.frameLenP + 3 * z.chunk + VP_ORDER_MAX + 3) & ~3;
     if ((rc = wsalloc(e, &e->dGate, (size_t)Sc * maxBlocks))) return rc;
     if ((rc = wsalloc(e, &e->dGatePart, (size_t)Sc * (maxBlocks + e->gateCarry) * 4))) return rc;
-    if ((rc = wsalloc(e, &e->dRV, fV * vp_rowlen(e->prm.lpcVoice)))) return rc;
-    if ((rc = wsalloc(e, &e->dRS, fV * vp_rowlen(e->prm.lpcSynth)))) return rc;
-    if ((rc = wsalloc(e, &e->dAV, fVc * (e->prm.lpcVoice + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dAS, fVc * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dRV, fV * vp_rowlen(capV)))) return rc;
+    if ((rc = wsalloc(e, &e->dRS, fV * vp_rowlen(capS)))) return rc;
+    if ((rc = wsalloc(e, &e->dAV, fVc * (capV + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dAS, fVc * (capS + 1)))) return rc;
     if ((rc = wsalloc(e, &e->dEeV, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dEeS, fVc))) return rc;
     if ((rc = wsalloc(e, &e->dG, fVc))) return rc;
@@ -477,8 +523,8 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     if ((rc = wsalloc(e, &e->dListCount, 1024))) return rc;
     VP_CUDA_OK(cudaMemset(e->dListCount, 0, 1024 * sizeof(int)));
     if ((rc = wsalloc(e, &e->dFrames, fPc))) return rc;
-    if ((rc = wsalloc(e, &e->dAP, fPc * (e->prm.lpcPitch + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->dRP, fPc * (e->prm.lpcPitch + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dAP, fPc * (capP + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->dRP, fPc * (capP + 1)))) return rc;
     if ((rc = wsalloc(e, &e->dOutE, fPc * (size_t)z.frameLenP))) return rc;
     if ((rc = wsalloc(e, &e->dYinP, (size_t)Sc * yinP))) return rc;
     if ((rc = wsalloc(e, &e->dYinE, e->yinDirect ? 1 : (size_t)Sc * vp_yin_corr_chunks(gy)))) return rc;
@@ -500,17 +546,20 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     // carried state, all S streams
     for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) if ((rc = wsalloc(e, &e->cHist[i][j], (size_t)S * e->H))) return rc;
     if ((rc = wsalloc(e, &e->cGate, (size_t)S * e->gateCarry * 4))) return rc;
-    if ((rc = wsalloc(e, &e->cAV, (size_t)S * VP_VC * (e->prm.lpcVoice + 1)))) return rc;
-    if ((rc = wsalloc(e, &e->cAS, (size_t)S * VP_VC * (e->prm.lpcSynth + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->cAV, (size_t)S * VP_VC * (capV + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->cAS, (size_t)S * VP_VC * (capS + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->oAV, (size_t)S * VP_ORPH * (capV + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->oAS, (size_t)S * VP_ORPH * (capS + 1)))) return rc;
+    if ((rc = wsalloc(e, &e->oEeS, (size_t)S * VP_ORPH))) return rc;
+    if ((rc = wsalloc(e, &e->oG, (size_t)S * VP_ORPH))) return rc;
     if ((rc = wsalloc(e, &e->cEeS, (size_t)S * VP_VC))) return rc;
     if ((rc = wsalloc(e, &e->cG, (size_t)S * VP_VC))) return rc;
     if ((rc = wsalloc(e, &e->cGainHist, (size_t)S * 20))) return rc;
     if ((rc = wsalloc(e, &e->cFrames, (size_t)S * VP_PC))) return rc;
     if ((rc = wsalloc(e, &e->cMarks, (size_t)S))) return rc;
-    e->capV = e->prm.lpcVoice; e->capS = e->prm.lpcSynth; e->capP = e->prm.lpcPitch;
+    e->capV = capV; e->capS = capS; e->capP = capP;
     if ((rc = reset_state(e))) return rc;
     e->launches = e->yinRechecked = e->yinFrames = 0;
-    e->capV = e->prm.lpcVoice; e->capS = e->prm.lpcSynth; e->capP = e->prm.lpcPitch;
     e->prepared = true;
     e->lastBlocks = 0;
     return VP_OK;
@@ -545,6 +594,8 @@ static void side_mark(vp_engine* e) {
     cudaEventRecord(e->evSide[e->evSideUsed++], e->st2);
 }
 
+static void grid_geom(const GridState& gs, VPGeom* g);
+
 static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     const vp_sizes& z = e->sz;
     memset(g, 0, sizeof *g);
@@ -553,21 +604,12 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     g->nBlocks = nBlocks; g->n = (long long)nBlocks * e->B; g->stride = (long long)stride;
     g->wstride = (long long)e->maxBlocks * e->B;
     g->vstride = g->pstride = g->wstride;
-    {   // call-local frame grid: the timeline continues where the previous call ended
-        const long long u0 = e->blocksDone * (long long)e->B;
-        g->offV = (int)((z.hopV - (u0 % z.hopV)) % z.hopV);
-        g->offP = (int)((z.hopP - (u0 % z.hopP)) % z.hopP);
-        g->kV0 = (int)((u0 + z.hopV - 1) / z.hopV);
-        g->fP0 = (int)((u0 + z.hopP - 1) / z.hopP);
-        g->nFramesV = (g->n > g->offV) ? (int)((g->n - g->offV + z.hopV - 1) / z.hopV) : 0;
-        g->nFramesP = (g->n > g->offP) ? (int)((g->n - g->offP + z.hopP - 1) / z.hopP) : 0;
-        g->hasPrev = e->blocksDone > 0;
-        g->H = e->H;
-    }
-    g->ordV = e->prm.lpcVoice; g->ordS = e->prm.lpcSynth; g->ordP = e->prm.lpcPitch;
+    g->vocOn = e->prm.vocBool != 0; g->pitchOn = e->prm.pitchBool != 0;
+    g->ordV = e->prm.lpcVoice; g->ordS = e->prm.lpcSynth; g->ordP = e->capP;
+    g->H = e->H;
+    grid_geom(e->gs, g);
     g->gainVocF = db_to_gain(e->prm.gainVoc); g->gainPitchF = db_to_gain(e->prm.gainPitch);
     g->gainVoiceF = db_to_gain(e->prm.gainVoice); g->gainSynthF = db_to_gain(e->prm.gainSynth);
-    g->vocOn = e->prm.vocBool != 0; g->pitchOn = e->prm.pitchBool != 0;
     g->dryOn = e->prm.gainVoice > -59.0f; g->synthOn = e->prm.gainSynth > -59.0f;
     g->yinEps = 1e-4;
     if (const char* ye = getenv("VP_YIN_EPS")) g->yinEps = atof(ye);
@@ -591,28 +633,36 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     int* listCount = e->dListCount + (e->passCount % 1024);
     e->passCount++;
     const size_t fP = (size_t)Sp * g.nFramesP;
-    const int ordV1 = g.ordV + 1, ordS1 = g.ordS + 1;
+    const int synV1 = g.synV + 1, synS1 = g.synS + 1, capV1 = e->capV + 1, capS1 = e->capS + 1;
     const long long rowsV = g.nFramesV + VP_VC, rowsP = g.nFramesP + VP_PC, rowsG = g.nBlocks + e->gateCarry;
     stage_mark(e, ST_OTHER);
-    // ---- carried rows of the previous call in front of this call's rows
-    vp_launch_carry_in(st, e->dGatePart, e->cGate + sb * e->gateCarry * 4, Sp, 32, e->gateCarry, rowsG);
+    // ---- carried rows of the previous call in front of this call's rows (coefficient rows: from the store's width to the
+    // call's row width; rows of narrower orders are zero padded)
+    vp_launch_carry_in(st, e->dGatePart, e->cGate + sb * e->gateCarry * 4, Sp, 32, 32, e->gateCarry, rowsG);
     if (g.vocOn) {
-        vp_launch_carry_in(st, e->dAV, e->cAV + sb * VP_VC * ordV1, Sp, 8 * ordV1, VP_VC, rowsV);
-        vp_launch_carry_in(st, e->dAS, e->cAS + sb * VP_VC * ordS1, Sp, 8 * ordS1, VP_VC, rowsV);
-        vp_launch_carry_in(st, e->dEeS, e->cEeS + sb * VP_VC, Sp, 8, VP_VC, rowsV);
-        vp_launch_carry_in(st, e->dGs, e->cG + sb * VP_VC, Sp, 8, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dAV, e->cAV + sb * VP_VC * capV1, Sp, 8 * synV1, 8 * capV1, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dAS, e->cAS + sb * VP_VC * capS1, Sp, 8 * synS1, 8 * capS1, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dEeS, e->cEeS + sb * VP_VC, Sp, 8, 8, VP_VC, rowsV);
+        vp_launch_carry_in(st, e->dGs, e->cG + sb * VP_VC, Sp, 8, 8, VP_VC, rowsV);
     }
-    if (g.pitchOn) vp_launch_carry_in(st, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
+    if (g.pitchMix) vp_launch_carry_in(st, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
     vp_launch_gate(st, g, Sp, voice, synthL, e->dGate, e->dGatePart, (int)rowsG);
     e->launches += 2;
     stage_mark(e, ST_GATE);
     // Order: YIN -> [side stream: pitch-mark chain, sequential per stream, latency-bound, few warps] running UNDER
     // [main stream: the vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.
     bool forked = false;
-    if (g.pitchOn) {
+    if (g.pitchMix) {
         VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), st));
         VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
         stage_mark(e, ST_CLEAR);
+    }
+    if (!g.pitchOn) {
+        // pitchBool off for these blocks: PitchProcess::silence() (PluginProcessor.cpp:218-221)
+        vp_launch_marks_silence(st, e->cMarks + sb, Sp);
+        e->launches++;
+    }
+    if (g.pitchOn) {
         if (g.nFramesP > 0) {
             if (e->yinDirect) {
                 vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
@@ -682,8 +732,21 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dAV, e->dAS, e->dEeS, e->dGs, vDst);
         stage_mark(e, ST_VOC_SYN);
         e->launches += 1;
+    } else if (g.vocMix) {
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.wstride * sizeof(float), st));
+        stage_mark(e, ST_CLEAR);
     }
-    if (g.pitchOn) {
+    if (g.vocMix) {
+        bool any = false;
+        for (int j = 0; j < VP_ORPH; ++j) any = any || g.orphPos[j] != VP_NOFRAME;
+        if (any) {  // frames of earlier calls that a vocBool-off stretch left off this call's grid
+            vp_launch_voc_orphans(st, g, tb, Sp, synthL, e->oAV + sb * VP_ORPH * capV1, e->oAS + sb * VP_ORPH * capS1, e->oEeS + sb * VP_ORPH,
+                                  e->oG + sb * VP_ORPH, vDst, e->capV, e->capS);
+            stage_mark(e, ST_VOC_SYN);
+            e->launches += 1;
+        }
+    }
+    if (g.pitchMix) {
         if (forked) {
             VP_CUDA_OK(cudaStreamWaitEvent(st, e->evJoin, 0));
             stage_mark(e, ST_OTHER);  // whatever of the mark chain was not hidden under the vocoder kernels
@@ -701,14 +764,14 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     e->launches++;
     stage_mark(e, ST_MIX);
     // ---- state for the next call: last rows of (carry ++ new), and the last H input samples
-    vp_launch_carry_out(st, e->cGate + sb * e->gateCarry * 4, e->dGatePart, Sp, 32, e->gateCarry, g.nBlocks, rowsG);
+    vp_launch_carry_out(st, e->cGate + sb * e->gateCarry * 4, e->dGatePart, Sp, 32, 32, e->gateCarry, g.nBlocks, rowsG);
     if (g.vocOn) {
-        vp_launch_carry_out(st, e->cAV + sb * VP_VC * ordV1, e->dAV, Sp, 8 * ordV1, VP_VC, g.nFramesV, rowsV);
-        vp_launch_carry_out(st, e->cAS + sb * VP_VC * ordS1, e->dAS, Sp, 8 * ordS1, VP_VC, g.nFramesV, rowsV);
-        vp_launch_carry_out(st, e->cEeS + sb * VP_VC, e->dEeS, Sp, 8, VP_VC, g.nFramesV, rowsV);
-        vp_launch_carry_out(st, e->cG + sb * VP_VC, e->dGs, Sp, 8, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cAV + sb * VP_VC * capV1, e->dAV, Sp, 8 * synV1, 8 * capV1, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cAS + sb * VP_VC * capS1, e->dAS, Sp, 8 * synS1, 8 * capS1, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cEeS + sb * VP_VC, e->dEeS, Sp, 8, 8, VP_VC, g.nFramesV, rowsV);
+        vp_launch_carry_out(st, e->cG + sb * VP_VC, e->dGs, Sp, 8, 8, VP_VC, g.nFramesV, rowsV);
     }
-    if (g.pitchOn) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
+    if (g.pitchMix) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
     vp_launch_hist_update(st, e->cHist[hc ^ 1][0] + sb * e->H, g.histV, voice, Sp, e->H, g.n, g.stride);
     vp_launch_hist_update(st, e->cHist[hc ^ 1][1] + sb * e->H, g.histS, synthL, Sp, e->H, g.n, g.stride);
     // channel 1 of the side-chain ring is filled on every block whatever gainSynth is (MyBuffer.cpp:69-92): the history
@@ -733,9 +796,174 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     return VP_OK;
 }
 
-// after the last pass of a call: the timeline has advanced
-static void finish_call(vp_engine* e, int nBlocks) {
-    e->blocksDone += nBlocks;
+// Before the first pass of a call: what a block with vocBool / pitchBool off does to the state every stream shares.
+// Returns the carry rows that have to move to the orphan store (the caller moves the device rows).
+static int grid_begin(GridState& gs, int vocBool, int pitchBool, GridMove* moves) {
+    const vp_sizes& z = gs.z;
+    const long long u0 = gs.blocksDone * (long long)gs.B;
+    int nMoves = 0;
+    for (int j = 0; j < VP_ORPH; ++j)  // frames that have emitted everything
+        if (gs.orphAbs[j] >= 0 && gs.orphAbs[j] + z.wlenV <= u0) gs.orphAbs[j] = -1;
+    if (!vocBool && gs.alignedV > 0) {
+        // VocoderProcess::process is skipped (PluginProcessor.cpp:214-215): its startSample freezes, so the frames carried
+        // from the previous call are no longer on the grid of whatever call runs the vocoder next. Their rows move to the
+        // orphan store (those that still reach into this call), where k_voc_orphans finishes them.
+        for (int i = VP_VC - gs.alignedV; i < VP_VC; ++i) {
+            const long long pos = gs.nextFrameV - (long long)(VP_VC - i) * z.hopV;
+            if (pos + z.wlenV <= u0) continue;
+            int slot = -1;
+            for (int j = 0; j < VP_ORPH && slot < 0; ++j) if (gs.orphAbs[j] < 0) slot = j;
+            if (slot < 0) continue;  // cannot happen: frames are at least a hop apart, at most 4 reach any position
+            moves[nMoves].srcRow = i; moves[nMoves].dstSlot = slot; ++nMoves;
+            gs.orphAbs[slot] = pos;
+            gs.orphOrdV[slot] = gs.alignedOrdV[i];
+            gs.orphOrdS[slot] = gs.alignedOrdS[i];
+        }
+        gs.alignedV = 0;
+    }
+    if (!pitchBool) {
+        // PitchProcess::silence() (PitchProcess.cpp:146-158): the chunks of a frame in flight that have not been handled yet
+        // find anMarks empty and do nothing (:253-271); the chunks handled before this block keep their output
+        for (int j = 0; j < VP_PC; ++j) {
+            if (gs.carryAbsP[j] < 0) continue;
+            int done = 0;
+            for (int n = 0; n < 4; ++n) if (gs.carryAbsP[j] + (long long)n * z.chunk < u0) ++done;
+            gs.carryLimP[j] = std::min(gs.carryLimP[j], done);
+        }
+    }
+    return nMoves;
+}
+
+// call-local frame grids of a call of n samples from the grid state (the timeline continues where the previous call ended)
+static void grid_geom(const GridState& gs, VPGeom* g) {
+    const vp_sizes& z = gs.z;
+    const long long u0 = gs.blocksDone * (long long)gs.B;
+    g->hasPrev = gs.blocksDone > 0;
+    // vocoder (VocoderProcess::process, :173-183): frames at nextFrameV + k hop while they start inside the call
+    g->synV = g->ordV; g->synS = g->ordS;
+    if (g->vocOn) {
+        g->offV = (int)(gs.nextFrameV - u0);
+        g->nFramesV = (g->n > g->offV) ? (int)((g->n - g->offV + z.hopV - 1) / z.hopV) : 0;
+        g->kV0 = gs.alignedV;  // carried rows -kV0 .. -1 are frames on this grid
+        for (int i = VP_VC - gs.alignedV; i < VP_VC; ++i) {
+            g->synV = std::max(g->synV, gs.alignedOrdV[i]);
+            g->synS = std::max(g->synS, gs.alignedOrdS[i]);
+        }
+    } else {
+        g->offV = 0; g->nFramesV = 0; g->kV0 = 0;
+    }
+    bool orphLive = false;
+    for (int j = 0; j < VP_ORPH; ++j) {
+        const bool live = gs.orphAbs[j] >= 0 && gs.orphAbs[j] + z.wlenV > u0;
+        g->orphPos[j] = live ? (int)(gs.orphAbs[j] - u0) : VP_NOFRAME;
+        g->orphOrdV[j] = gs.orphOrdV[j]; g->orphOrdS[j] = gs.orphOrdS[j];
+        orphLive = orphLive || live;
+    }
+    g->vocMix = g->vocOn || orphLive;
+    // pitch (PitchProcess::process, :166-196): a frame starts at the chunk for which nChunk is 0 or 3
+    if (g->pitchOn) {
+        const int j0 = (gs.nChunk == 0 || gs.nChunk == 3) ? 0 : 3 - gs.nChunk;
+        g->offP = (int)(gs.nextChunkP + (long long)j0 * z.chunk - u0);
+        g->nFramesP = (g->n > g->offP) ? (int)((g->n - g->offP + z.hopP - 1) / z.hopP) : 0;
+    } else {
+        g->offP = 0; g->nFramesP = 0;
+    }
+    g->fP0 = 0;
+    bool carryLive = false;
+    for (int j = 0; j < VP_PC; ++j) {
+        const bool have = gs.carryAbsP[j] >= 0;
+        g->carryPosP[j] = have ? (int)(gs.carryAbsP[j] - u0) : VP_NOFRAME;
+        g->carryLimP[j] = have ? gs.carryLimP[j] : 0;
+        // chunks are added to the output when they are handled, also beyond the block (MyBuffer::addOutSample): a carried
+        // frame still owns positions of this call while one of its processed chunks reaches past the call's start
+        if (have && g->carryLimP[j] > 0 && g->carryPosP[j] + (long long)std::min(g->carryLimP[j], 4) * z.chunk > 0) carryLive = true;
+    }
+    g->pitchMix = g->pitchOn || carryLive;
+}
+
+// after the last pass of a call: the timeline and the frame grids have advanced
+static void grid_finish(GridState& gs, const VPGeom& g) {
+    const vp_sizes& z = gs.z;
+    const long long u0 = gs.blocksDone * (long long)gs.B;
+    if (g.vocOn) {
+        // orders of the rows the device carried out: the last VP_VC of (carried ++ new)
+        int ov[2 * VP_VC], os[2 * VP_VC], cnt = 0;
+        for (int i = VP_VC - gs.alignedV; i < VP_VC; ++i) { ov[cnt] = gs.alignedOrdV[i]; os[cnt] = gs.alignedOrdS[i]; ++cnt; }
+        const int add = std::min(g.nFramesV, VP_VC);
+        for (int i = 0; i < add; ++i) { ov[cnt] = g.ordV; os[cnt] = g.ordS; ++cnt; }
+        const int keep = std::min(cnt, VP_VC);
+        for (int i = 0; i < keep; ++i) { gs.alignedOrdV[VP_VC - keep + i] = ov[cnt - keep + i]; gs.alignedOrdS[VP_VC - keep + i] = os[cnt - keep + i]; }
+        gs.alignedV = std::min(VP_VC, gs.alignedV + g.nFramesV);
+        gs.nextFrameV = u0 + g.offV + (long long)g.nFramesV * z.hopV;
+    } else {
+        gs.nextFrameV += g.n;  // startSample is relative to the block: it does not move while process() is skipped
+    }
+    if (g.pitchOn) {
+        // chunks that started inside the call (PitchProcess::process, :169-192), and nChunk after them
+        const long long K = (gs.nextChunkP < u0 + g.n) ? (u0 + g.n - gs.nextChunkP + z.chunk - 1) / z.chunk : 0;
+        gs.nextChunkP += K * z.chunk;
+        if (K > 0) {  // nChunk: 0 -> 1 -> 2 -> 3 -> 1 -> 2 -> 3 ...
+            int nc = gs.nChunk;
+            const long long steps = (K > 6) ? 6 + (K - 6) % 3 : K;
+            for (long long i = 0; i < steps; ++i) nc = (nc == 0 || nc == 3) ? 1 : nc + 1;
+            gs.nChunk = nc;
+        }
+        // the records the device carried out: the last VP_PC of (carried ++ new)
+        for (int f = std::max(0, g.nFramesP - VP_PC); f < g.nFramesP; ++f) {
+            for (int j = 0; j + 1 < VP_PC; ++j) { gs.carryAbsP[j] = gs.carryAbsP[j + 1]; gs.carryLimP[j] = gs.carryLimP[j + 1]; }
+            gs.carryAbsP[VP_PC - 1] = u0 + g.offP + (long long)f * z.hopP;
+            gs.carryLimP[VP_PC - 1] = 4;
+        }
+    } else {
+        gs.nextChunkP += g.n;
+    }
+    gs.blocksDone += g.nBlocks;
+}
+
+extern "C" int vp_grid_plan(double sampleRate, int samplesPerBlock, int nCalls, const int* nBlocks, const vp_params* params,
+                           vp_call_plan* out) {
+    if (nCalls < 0 || (nCalls > 0 && (!nBlocks || !params || !out))) return VP_E_ARG;
+    GridState gs;
+    if (vp_sizes_for(sampleRate, samplesPerBlock, 12, &gs.z) != VP_OK) return VP_E_ARG;
+    gs.B = samplesPerBlock;
+    gs.reset();
+    for (int c = 0; c < nCalls; ++c) {
+        if (nBlocks[c] <= 0) return VP_E_ARG;
+        GridMove mv[VP_VC];
+        const int nm = grid_begin(gs, params[c].vocBool, params[c].pitchBool, mv);
+        VPGeom g;
+        memset(&g, 0, sizeof g);
+        g.B = gs.B; g.hopV = gs.z.hopV; g.wlenV = gs.z.wlenV; g.hopP = gs.z.hopP; g.L = gs.z.frameLenP; g.c = gs.z.chunk;
+        g.nBlocks = nBlocks[c]; g.n = (long long)nBlocks[c] * gs.B;
+        g.vocOn = params[c].vocBool != 0; g.pitchOn = params[c].pitchBool != 0;
+        g.ordV = params[c].lpcVoice; g.ordS = params[c].lpcSynth;
+        grid_geom(gs, &g);
+        vp_call_plan& o = out[c];
+        memset(&o, 0, sizeof o);
+        o.firstBlock = gs.blocksDone; o.offV = g.offV; o.nFramesV = g.nFramesV; o.carriedV = g.kV0; o.rowOrderV = g.synV; o.rowOrderS = g.synS;
+        o.offP = g.offP; o.nFramesP = g.nFramesP; o.vocMix = g.vocMix; o.pitchMix = g.pitchMix; o.rowsOrphaned = nm;
+        for (int j = 0; j < VP_ORPH; ++j) if (g.orphPos[j] != VP_NOFRAME) o.orphansLive++;
+        for (int j = 0; j < 2; ++j) { o.carryPosP[j] = g.carryPosP[j]; o.carryChunksP[j] = g.carryLimP[j]; }
+        grid_finish(gs, g);
+    }
+    return VP_OK;
+}
+
+static void begin_call(vp_engine* e) {
+    GridMove mv[VP_VC];
+    const int nm = grid_begin(e->gs, e->prm.vocBool, e->prm.pitchBool, mv);
+    const int capV1 = e->capV + 1, capS1 = e->capS + 1;
+    for (int i = 0; i < nm; ++i) {
+        vp_launch_row_move(e->st, e->oAV, e->cAV, e->S, 8 * capV1, VP_VC, mv[i].srcRow, VP_ORPH, mv[i].dstSlot);
+        vp_launch_row_move(e->st, e->oAS, e->cAS, e->S, 8 * capS1, VP_VC, mv[i].srcRow, VP_ORPH, mv[i].dstSlot);
+        vp_launch_row_move(e->st, e->oEeS, e->cEeS, e->S, 8, VP_VC, mv[i].srcRow, VP_ORPH, mv[i].dstSlot);
+        vp_launch_row_move(e->st, e->oG, e->cG, e->S, 8, VP_VC, mv[i].srcRow, VP_ORPH, mv[i].dstSlot);
+        e->launches += 4;
+    }
+}
+
+static void finish_call(vp_engine* e, const VPGeom& g) {
+    grid_finish(e->gs, g);
     e->histCur ^= 1;
 }
 
@@ -771,6 +999,7 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
         if (ranges_overlap(outL, span, outR, span)) return vp_err(e, VP_E_ARG, "outL and outR must not overlap");
     }
     VP_CUDA_OK(cudaSetDevice(e->device));
+    begin_call(e);
     VPGeom g;
     make_geom(e, nBlocks, stride, &g);
     e->lastBlocks = nBlocks;
@@ -784,7 +1013,7 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
                       outR ? outR + off : nullptr);
         if (rc) { e->failed = true; return rc; }  // some streams' carried state has advanced, others' has not
     }
-    finish_call(e, nBlocks);
+    finish_call(e, g);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
     return VP_OK;
 }
@@ -851,6 +1080,7 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
         const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
         for (int i = 0; i < 3; ++i) if ((rc = wsalloc(e, &e->hOut[i][1], cnt))) return rc;
     }
+    begin_call(e);
     VPGeom g;
     make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense
     e->lastBlocks = nBlocks;
@@ -895,7 +1125,7 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
                                          cudaMemcpyDeviceToHost, e->stOut));
         VP_CUDA_OK(cudaEventRecord(e->evOut[bi], e->stOut));
     }
-    finish_call(e, nBlocks);
+    finish_call(e, g);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
     return vp_engine_sync(e);
 }
@@ -926,12 +1156,16 @@ extern "C" int vp_engine_stream_block(vp_engine* e) {
     if (!e->prepared || !e->sHostV) return vp_err(e, VP_E_STATE, "call vp_engine_prepare and vp_engine_stream_buffers first");
     if (e->prm.gainSynth > -59.0f) return vp_err(e, VP_E_ARG, "streaming mode carries side-chain channel 0 only: gainSynth must be off");
     VP_CUDA_OK(cudaSetDevice(e->device));
+    begin_call(e);
     VPGeom g;
     make_geom(e, 1, (size_t)e->B, &g);
     e->lastBlocks = 1;
     e->lastG = g;
     // everything that shapes the launch sequence or is baked into kernel arguments
-    const std::vector<long long> key = {e->blocksDone > 0 ? 1 : 0, e->histCur, g.offV, g.offP, g.nFramesV, g.nFramesP, g.kV0 < VP_VC ? g.kV0 : VP_VC};
+    std::vector<long long> key = {e->gs.blocksDone > 0 ? 1 : 0, e->histCur, g.offV, g.offP, g.nFramesV, g.nFramesP, g.kV0, g.synV, g.synS,
+                                  g.vocOn, g.pitchOn, g.vocMix, g.pitchMix};
+    for (int j = 0; j < VP_ORPH; ++j) { key.push_back(g.orphPos[j]); key.push_back(g.orphOrdV[j]); key.push_back(g.orphOrdS[j]); }
+    for (int j = 0; j < VP_PC; ++j) { key.push_back(g.carryPosP[j]); key.push_back(g.carryLimP[j]); }
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
         const bool st = e->stageTiming;
@@ -965,7 +1199,7 @@ extern "C" int vp_engine_stream_block(vp_engine* e) {
     }
     VP_CUDA_OK(cudaGraphLaunch(it->second, e->st));
     e->graphLaunches++;
-    finish_call(e, 1);
+    finish_call(e, g);
     VP_CUDA_OK(cudaStreamSynchronize(e->st));
     return VP_OK;
 }

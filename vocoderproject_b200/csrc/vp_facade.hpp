@@ -111,8 +111,10 @@ public:
         beginBlock();
     }
     void setParams(const vp_params& p) { params = p; engine.check(vp_engine_set_params(engine.h, &params)); }
-    // prepareToPlay on a running instance: back to the freshly prepared state first, so that parameters which re-lay the
-    // carried state (LPC orders, enables) are accepted again
+    // largest lpcVoice / lpcSynth that may be set while the streams run (before prepare; VocoderProcess.cpp:50-57 sizes its
+    // vectors for the ends of the parameter ranges: 100 / 30)
+    void reserveOrders(int maxLpcVoice, int maxLpcSynth) { engine.check(vp_engine_reserve_orders(engine.h, maxLpcVoice, maxLpcSynth)); }
+    // prepareToPlay on a running instance: back to the freshly prepared state first
     void restart() { if (B > 0) engine.check(vp_engine_reset(engine.h)); }
     const vp_params& getParams() const { return params; }
 
@@ -185,7 +187,9 @@ public:
     }
     int getLatency(int /*samplesPerBlock*/) const { return frameLen; }  // PitchProcess.cpp:37
     void process(MyBuffer& myBuffer) { myBuffer.pitchRequested = true; }
-    // silence(): pitchBool off for this block (PitchProcess.cpp:146-158). The engine keeps the vocoder / dry paths only.
+    // silence(): pitchBool off for this block (PitchProcess.cpp:146-158). Nothing to record: a block whose
+    // PitchProcess::process was not requested reaches the engine with pitchBool = 0, and the engine then does what silence()
+    // does -- both mark vectors cleared, pitch / period zeroed, the frame in flight cut -- for every stream.
     void silence() {}
 
 private:
@@ -199,7 +203,9 @@ class VocoderBatchProcessor {
 public:
     explicit VocoderBatchProcessor(int device = 0) : myBuffer(device) { vp_default_params(&params); }
 
-    void prepareToPlay(double sampleRate, int samplesPerBlock, int nStreams, int maxBlocksPerCall = 1) {
+    // maxLpcVoice / maxLpcSynth: the largest orders the parameters may take while the streams run (0 = the current ones)
+    void prepareToPlay(double sampleRate, int samplesPerBlock, int nStreams, int maxBlocksPerCall = 1, int maxLpcVoice = 0,
+                       int maxLpcSynth = 0) {
         const double ratioSR = sampleRate / 44100.0;                       // :160
         const int hopVoc = (int)std::floor(128.0 * ratioSR);               // :163
         const int wlenVoc = 4 * hopVoc;                                    // :164
@@ -207,6 +213,7 @@ public:
         const int hopPitch = 3 * c256, frameLenPitch = 4 * c256;           // :169-170
         const double silenceDb = -60.0;                                    // :148
         myBuffer.restart();
+        myBuffer.reserveOrders(maxLpcVoice, maxLpcSynth);
         myBuffer.setParams(params);
         pitchProcess.prepare(sampleRate, 100.0, 800.0, frameLenPitch, hopPitch, samplesPerBlock, silenceDb);   // :172
         vocoderProcess.prepare(wlenVoc, hopVoc, "sine", silenceDb);                                             // :173

@@ -46,7 +46,9 @@ public:
     void prepareToPlay(Proc& p, double sampleRate, int samplesPerBlock) {
         dsp.params = pullParams(p);
         fs = sampleRate; B = samplesPerBlock;
-        dsp.prepareToPlay(sampleRate, samplesPerBlock, /*nStreams*/ 1);   // same size derivation, :160-176
+        // same size derivation, :160-176; rows sized for the ends of the lpcVoice / lpcSynth ranges (:53-59), like the
+        // reference's orderMax vectors, so that the order knobs can move while audio runs
+        dsp.prepareToPlay(sampleRate, samplesPerBlock, /*nStreams*/ 1, /*maxBlocksPerCall*/ 1, 100, 30);
         p.setLatencySamples(dsp.getLatencySamples());                      // :183
         outL.assign((size_t)samplesPerBlock, 0.0f);
         outR.assign((size_t)samplesPerBlock, 0.0f);
@@ -62,13 +64,9 @@ public:
             B = n;
             prepareToPlay(p, fs, n);
         }
+        // every parameter is pushed per block and takes effect where the reference reads it (orders per vocoder frame,
+        // enables per block, ...): no restart, no state loss when a knob or a bypass button moves
         const vp_params q = pullParams(p);
-        const vp_params& cur = dsp.params;
-        // LPC orders and the two enables re-lay the carried state: the engine wants a reset for those (VP_E_STATE
-        // otherwise). For a plug-in that means what the host's own restart means: prepareToPlay again.
-        if (q.lpcVoice != cur.lpcVoice || q.lpcSynth != cur.lpcSynth || q.lpcPitch != cur.lpcPitch ||
-            q.vocBool != cur.vocBool || q.pitchBool != cur.pitchBool)
-            prepareToPlay(p, fs, n);
         dsp.params = q;
         dsp.processBlock(voice.getReadPointer(0), synth.getReadPointer(0), synth.getReadPointer(1), outL.data(), outR.data(),
                          (size_t)n);                    // :212-232 in one engine call

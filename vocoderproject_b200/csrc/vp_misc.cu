@@ -22,16 +22,16 @@ __global__ void __launch_bounds__(256) k_mix(VPGeom g, const float* __restrict__
 #pragma unroll
         for (int k = 0; k < MU; ++k) {
             const long long u = u0 + k * step;
-            a[k] = (g.vocOn && u < g.n) ? __ldg(outV + wrow + u) : 0.0f;
-            b[k] = (g.pitchOn && u < g.n) ? __ldg(outP + wrow + u) : 0.0f;
+            a[k] = (g.vocMix && u < g.n) ? __ldg(outV + wrow + u) : 0.0f;
+            b[k] = (g.pitchMix && u < g.n) ? __ldg(outP + wrow + u) : 0.0f;
         }
 #pragma unroll
         for (int k = 0; k < MU; ++k) {
             const long long u = u0 + k * step;
             if (u >= g.n) break;
             float l = 0.0f;
-            if (g.vocOn) l += a[k];
-            if (g.pitchOn) l += b[k];
+            if (g.vocMix) l += a[k];
+            if (g.pitchMix) l += b[k];
             float r = l;
             if (g.dryOn) {
                 const float d = g.gainVoiceF * vp_x(vp_row(voice, g.histV, s, g), u, g);
@@ -63,35 +63,68 @@ void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, 
 // Rows are counted in 4-byte words.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_carry_in(uint32_t* __restrict__ ws, const uint32_t* __restrict__ carry, int S,
-                                                  int rowWords, int C, long long wsRowsPerStream) {
-    const long long tot = (long long)S * C * rowWords;
+                                                  int wsWords, int cWords, int C, long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * wsWords;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
-        const int s = (int)(i / ((long long)C * rowWords));
-        const long long r = i - (long long)s * C * rowWords;
-        ws[(size_t)s * wsRowsPerStream * rowWords + r] = carry[i];
+        const int s = (int)(i / ((long long)C * wsWords));
+        const long long r = i - (long long)s * C * wsWords;
+        const int row = (int)(r / wsWords), w = (int)(r - (long long)row * wsWords);
+        ws[(size_t)s * wsRowsPerStream * wsWords + r] = (w < cWords) ? carry[((size_t)s * C + row) * cWords + w] : 0u;
     }
 }
 __global__ void __launch_bounds__(256) k_carry_out(uint32_t* __restrict__ carry, const uint32_t* __restrict__ ws, int S,
-                                                   int rowWords, int C, long long nNew, long long wsRowsPerStream) {
-    const long long tot = (long long)S * C * rowWords;
+                                                   int wsWords, int cWords, int C, long long nNew, long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * cWords;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
-        const int s = (int)(i / ((long long)C * rowWords));
-        const long long r = i - (long long)s * C * rowWords;
-        carry[i] = ws[((size_t)s * wsRowsPerStream + nNew) * rowWords + r];
+        const int s = (int)(i / ((long long)C * cWords));
+        const long long r = i - (long long)s * C * cWords;
+        const int row = (int)(r / cWords), w = (int)(r - (long long)row * cWords);
+        carry[i] = (w < wsWords) ? ws[((size_t)s * wsRowsPerStream + nNew + row) * wsWords + w] : 0u;
     }
 }
-void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int rowBytes, int C, long long wsRowsPerStream) {
-    const long long tot = (long long)S * C * (rowBytes / 4);
+void vp_launch_carry_in(cudaStream_t st, void* ws, const void* carry, int S, int wsRowBytes, int carryRowBytes, int C,
+                        long long wsRowsPerStream) {
+    const long long tot = (long long)S * C * (wsRowBytes / 4);
     if (tot <= 0) return;
     VP_LAUNCH(k_carry_in<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)ws, (const uint32_t*)carry, S,
-                                                                                       rowBytes / 4, C, wsRowsPerStream));
+                                                                                       wsRowBytes / 4, carryRowBytes / 4, C, wsRowsPerStream));
 }
-void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int rowBytes, int C, long long nNew,
+void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, int wsRowBytes, int carryRowBytes, int C, long long nNew,
                          long long wsRowsPerStream) {
-    const long long tot = (long long)S * C * (rowBytes / 4);
+    const long long tot = (long long)S * C * (carryRowBytes / 4);
     if (tot <= 0) return;
     VP_LAUNCH(k_carry_out<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)carry, (const uint32_t*)ws, S,
-                                                                                        rowBytes / 4, C, nNew, wsRowsPerStream));
+                                                                                        wsRowBytes / 4, carryRowBytes / 4, C, nNew, wsRowsPerStream));
+}
+
+// row `srcRow` of every stream's C-row store -> slot `dstSlot` of its D-slot store
+__global__ void __launch_bounds__(256) k_row_move(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int S, int words,
+                                                  int C, int srcRow, int D, int dstSlot) {
+    const long long tot = (long long)S * words;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / words), w = (int)(i - (long long)s * words);
+        dst[((size_t)s * D + dstSlot) * words + w] = src[((size_t)s * C + srcRow) * words + w];
+    }
+}
+void vp_launch_row_move(cudaStream_t st, void* dst, const void* src, int S, int rowBytes, int C, int srcRow, int D, int dstSlot) {
+    const long long tot = (long long)S * (rowBytes / 4);
+    if (tot <= 0) return;
+    VP_LAUNCH(k_row_move<<<(unsigned)std::min<long long>((tot + 255) / 256, 4096), 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, S,
+                                                                                       rowBytes / 4, C, srcRow, D, dstSlot));
+}
+
+// PitchProcess::silence() (PitchProcess.cpp:146-158) for every stream: both mark vectors cleared (their storage keeps its
+// values), pitch = prevPitch = 0, period = prevPeriod = 0. prevVoicedPeriod, periodNew and beta are not touched.
+__global__ void __launch_bounds__(128) k_marks_silence(VPMarkState* __restrict__ carry, int S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    VPMarkState* c = carry + s;
+    c->nAn = 0; c->nSt = 0;
+    c->period = 0; c->prevPeriod = 0;
+    c->voiced = 0; c->prevVoiced = 0;
+}
+void vp_launch_marks_silence(cudaStream_t st, VPMarkState* carry, int S) {
+    VP_LAUNCH(k_marks_silence<<<(S + 127) / 128, 128, 0, st>>>(carry, S));
 }
 
 // history update: the H input samples that precede the NEXT call = the last H of (old history ++ this call's input)

@@ -1033,8 +1033,9 @@ __device__ __forceinline__ bool pf_live(const VPGeom& g, const vp_pitch_frame* r
     if ((flags & VP_PF_GATED) || !(flags & VP_PF_HAS_MARKS)) return false;
     if (f >= 0) return true;
     if (!g.hasPrev) return false;
-    const long long p = (long long)f * g.hopP + g.offP;
-    for (int n = 0; n < 4; ++n) {
+    const long long p = vp_ppos(g, f);
+    const int lim = vp_plim(g, f);  // chunks of a carried frame that are processed at all (silence() cuts the rest)
+    for (int n = 0; n < lim; ++n) {
         const long long q = p + (long long)n * g.c;
         if (q < g.n && q + g.c > 0) return true;
     }
@@ -1053,7 +1054,7 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
     const int L = g.L, ord = g.ordP;
     double* xd = smd + (size_t)warp * xdLen;  // frame samples as double, zero beyond L (rectangular window, LPC.cpp:44-97)
     const VPRow v = vp_row(voice, g.histV, s, g);
-    const long long p = (long long)f * g.hopP + g.offP;
+    const long long p = vp_ppos(g, f);
     {   // frame samples -> double. Common case (frame inside this call's input): plain coalesced loads, 8 in flight per lane.
         // No float landing zone in shared memory: the 9.5 KB of xd per warp alone decide how many warps an SM holds.
         const long long t0 = p - g.lat;
@@ -1201,7 +1202,8 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     double* oE = (double*)xfBase;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
     const VPRow v = vp_row(voice, g.histV, s, g);
-    const long long p = (long long)f * g.hopP + g.offP;
+    const long long p = vp_ppos(g, f);
+    const int chunkLim = vp_plim(g, f);
     const int tid = threadIdx.x;
 
     // ---- frame samples global -> shared without a register round trip. Common case (the whole span lies inside this
@@ -1248,7 +1250,7 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
             const int d = stMark - T;
             const int n = (d < c) ? 0 : d / c;
             const long long Pn = p + (long long)n * c;
-            if (n <= 3 && Pn < g.n) {
+            if (n < chunkLim && Pn < g.n) {
                 const int stale = rec->anStale;
                 const int startSample = (int)(((Pn % g.B) + g.B) % g.B);  // Pn < 0: a chunk emitted by an earlier call
                 const int lookahead = g.lat + g.B - startSample;  // bufferIdxMax - startSample (PitchProcess.cpp:800)
@@ -1433,8 +1435,9 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
         s = (int)(fidx / (g.nFramesP + VP_PC));
         f = (int)(fidx - (long long)s * (g.nFramesP + VP_PC)) - VP_PC;
         active = pf_live(g, frames + fidx, f);
-        const long long p = (long long)f * g.hopP + g.offP;
-        for (int n = 0; n < 4; ++n) if (p + (long long)n * c < g.n) nSteps += c;  // chunks handled up to the end of this call
+        const long long p = vp_ppos(g, f);
+        const int lim = vp_plim(g, f);
+        for (int n = 0; n < lim; ++n) if (p + (long long)n * c < g.n) nSteps += c;  // chunks handled up to the end of this call
     }
     if (!active) nSteps = 0;
     constexpr int PA = (P > 0) ? P : VP_ORDER_MAX;
@@ -1445,7 +1448,7 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
         for (int k = 0; k <= order; ++k) a[k] = ap[k];
     }
     // per-lane metadata shared through shuffles for the cooperative slab moves
-    const long long myP = (long long)f * g.hopP + g.offP;
+    const long long myP = vp_ppos(g, f);
     // frame-relative output range that lands inside this call: positions before 0 went out with an earlier call, beyond
     // n go out with a later one; and the frame's base offset in the output plane
     const int myLo = (int)max(0LL, -myP), myHi = (int)min((long long)nSteps, (long long)g.n - myP);

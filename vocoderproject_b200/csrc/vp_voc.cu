@@ -383,16 +383,16 @@ __global__ void __launch_bounds__(128) k_voc_levinson(VPGeom g, VPTables tb, con
         const double* rp = rV + (size_t)idx * vp_rowlen(g.ordV);
         for (int m = 0; m <= g.ordV; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordV);
-        double* ap = aV + row * (g.ordV + 1);
-        for (int m = 0; m <= g.ordV; ++m) ap[m] = a[m];
+        double* ap = aV + row * (g.synV + 1);
+        for (int m = 0; m <= g.synV; ++m) ap[m] = (m <= g.ordV) ? a[m] : 0.0;  // zero padded up to the call's row order
         EeV[row] = fir_energy(r, a, g.ordV, g.wlenV, rp + g.ordV + 1);
     }
     {
         const double* rp = rS + (size_t)idx * vp_rowlen(g.ordS);
         for (int m = 0; m <= g.ordS; ++m) r[m] = rp[m] / (double)g.wlenV;
         lev_solve(r, a, g.ordS);
-        double* ap = aS + row * (g.ordS + 1);
-        for (int m = 0; m <= g.ordS; ++m) ap[m] = a[m];
+        double* ap = aS + row * (g.synS + 1);
+        for (int m = 0; m <= g.synS; ++m) ap[m] = (m <= g.ordS) ? a[m] : 0.0;
         const double eS = fir_energy(r, a, g.ordS, g.wlenV, rp + g.ordS + 1);
         // a frame skipped by the silence gate (VocoderProcess.cpp:199-204) is marked with EeSynth = -1
         const int b = (int)(((unsigned)k * (unsigned)g.hopV + (unsigned)g.offV) / (unsigned)g.B);
@@ -509,7 +509,7 @@ void vp_launch_voc_levinson(cudaStream_t st, const VPGeom& g, const VPTables& tb
                             const float* synth, const uint8_t* gate, const double* rV, const double* rS, double* aV,
                             double* aS, double* EeV, double* EeS) {
     const long long tot = (long long)S * g.nFramesV;
-    if (g.ordV == 40 && g.ordS == 5 && g.wlenV >= 40)
+    if (g.ordV == 40 && g.ordS == 5 && g.synV == 40 && g.synS == 5 && g.wlenV >= 40)
     {
         const size_t smem = (size_t)LV_THREADS * ((vp_rowlen(40) + vp_rowlen(5)) | 1) * sizeof(double);
         cudaFuncSetAttribute(k_voc_levinson_static<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1102,7 +1102,7 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
     const int s = live ? (int)(tile / tilesPerStream) : 0;
     // tiles start VP_VC frames early: the previous call's last frames (carry rows) still reach into this call
     const int k0 = (live ? (int)(tile - (long long)s * tilesPerStream) * 32 : 0) - VP_VC;
-    const int P = g.ordV, PS = g.ordS;
+    const int P = g.synV, PS = g.synS;  // row orders (>= the frames' own analysis orders; rows are zero padded)
     float* sbuf = smf + (size_t)warp * 2 * spanPad;
     float* obuf = sbuf + spanPad;
     const int hop = g.hopV, wlen = g.wlenV;
@@ -1152,7 +1152,52 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
     }
 }
 
-bool vp_voc_synth_needs_clear(const VPGeom& g) { return !(g.ordV == 40 && g.ordS == 5); }
+bool vp_voc_synth_needs_clear(const VPGeom& g) { return !(g.synV == 40 && g.synS == 5); }
+
+// ---------------------------------------------------------------------------
+// Frames of earlier calls that are off this call's frame grid (VPGeom::orphPos): finished from their carried rows, one
+// thread per stream, frames in slot order, added to the plane the grid kernel has already written. Rare (only around a
+// vocBool toggle) and short (at most 4 live frames per stream), so it is written for clarity: the same transposed-form
+// FIR + IIR with the states in local memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_voc_orphans(VPGeom g, VPTables tb, const float* __restrict__ synth,
+                                                    const double* __restrict__ oAV, const double* __restrict__ oAS,
+                                                    const double* __restrict__ oEeS, const double* __restrict__ oG,
+                                                    float* __restrict__ outV, int S, int capV, int capS) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const VPRow y = vp_row(synth, g.histS, s, g);
+    float* o = outV + (size_t)s * g.vstride;
+    double st[VP_ORDER_MAX + 1], t[32];
+    for (int j = 0; j < VP_ORPH; ++j) {
+        const int pos = g.orphPos[j];
+        if (pos == VP_NOFRAME || pos + g.wlenV <= 0 || pos >= g.n) continue;
+        const size_t slot = (size_t)s * VP_ORPH + j;
+        if (oEeS[slot] < 0.0) continue;  // gated frame
+        const int P = g.orphOrdV[j], PS = g.orphOrdS[j];
+        const double* a = oAV + slot * (size_t)(capV + 1);
+        const double* as = oAS + slot * (size_t)(capS + 1);
+        const double gain = oG[slot];
+        for (int k = 0; k <= P; ++k) st[k] = 0.0;
+        for (int k = 0; k <= PS; ++k) t[k] = 0.0;
+        for (int i = 0; i < g.wlenV; ++i) {
+            const long long u = (long long)pos + i;
+            if (u >= g.n) break;
+            const double w = tb.wV[i];
+            const double x = (double)vp_x(y, u, g) * w;
+            const double e = fma(gain * as[0], x, t[0]);
+            for (int q = 0; q < PS; ++q) t[q] = fma(gain * as[q + 1], x, t[q + 1]);
+            const double ov = e + st[0];
+            for (int k = 0; k < P; ++k) st[k] = fma(-a[k + 1], ov, st[k + 1]);
+            if (u >= 0) o[u] += (float)(ov * w);
+        }
+    }
+}
+
+void vp_launch_voc_orphans(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth, const double* oAV,
+                           const double* oAS, const double* oEeS, const double* oG, float* outV, int capV, int capS) {
+    VP_LAUNCH(k_voc_orphans<<<(S + 63) / 64, 64, 0, st>>>(g, tb, synth, oAV, oAS, oEeS, oG, outV, S, capV, capS));
+}
 
 // segments per stream group such that the grid is (at most) `waves` full waves of resident warps
 static int vs_segments(const VPGeom& g, int groups, int residentWarps, int* segFramesOut) {
@@ -1204,12 +1249,12 @@ static int vs_variant() {
 
 void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth,
                          const double* aV, const double* aS, const double* EeS, const double* G, float* outV) {
-    if (g.ordV == 40 && g.ordS == 5 && vs_variant() != 2 && g.hopV >= 8) {
+    if (g.synV == 40 && g.synS == 5 && vs_variant() != 2 && g.hopV >= 8) {
         if (vs_variant() == 1) launch_synth_rows<true>(st, g, tb, S, synth, aV, aS, EeS, G, outV);
         else launch_synth_rows<false>(st, g, tb, S, synth, aV, aS, EeS, G, outV);
         return;
     }
-    if (g.ordV == 40 && g.ordS == 5) {
+    if (g.synV == 40 && g.synS == 5) {
         const int groups = (S + 7) / 8;
         int perSM = 4, dev = 0, nSM = 148;
         const int rowPad = g.hopV | 1;
