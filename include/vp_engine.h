@@ -68,6 +68,7 @@ typedef struct vp_sizes {
 /* Per pitch frame decisions (one record per processChunkStart call,
  * PitchProcess.cpp:203-247). */
 #define VP_MAX_MARKS 24
+#define VP_NO_MARK (-2147483647 - 1)
 #define VP_PF_GATED 1u       /* silence gate fired (PitchProcess.cpp:208-214) */
 #define VP_PF_VOICED 2u      /* pitch > 1 */
 #define VP_PF_HAS_MARKS 4u   /* anMarks non-empty -> frame is synthesised */
@@ -84,6 +85,8 @@ typedef struct vp_pitch_frame {
     int32_t nAn, nSt;
     int32_t anStale;          /* storage slot anMarks[nAn] (PitchProcess.cpp:818) */
     int32_t nAnOv;
+    int32_t prevAnLast;       /* last mark of the previous frame that does not overlap this one, in this frame's
+                                 coordinates (what PitchProcess.cpp:812 means to fall back to); VP_NO_MARK if none */
     int32_t anMarks[VP_MAX_MARKS];
     int32_t stMarks[VP_MAX_MARKS];
     double beta;              /* closestFreq / pitch, carried over unvoiced frames */
@@ -124,6 +127,22 @@ int vp_engine_prepare(vp_engine* e, double sampleRate, int samplesPerBlock, int 
  * (PluginProcessor.cpp:214-221, PitchProcess.cpp:146-158). lpcPitch is read in PitchProcess::prepare only (:70): a change on
  * a running stream is ignored until the next vp_engine_prepare, as in the reference. */
 int vp_engine_set_params(vp_engine* e, const vp_params* p);
+/* Behaviour at the places where the reference's C++ has undefined behaviour:
+ *   VP_MODE_PARITY  (default) what the reference build actually does: the stale vector slot of PitchProcess.cpp:818 and the
+ *                   popped table slot of Notes.cpp:99 are modelled, the other sites keep going and the frame is flagged VP_PF_UB;
+ *   VP_MODE_DEFINED every such site takes the bounds-correct reading of what the code says it wants:
+ *                   :818  the completeness test looks at the mark it is about to return (the last one), not one past the end;
+ *                   :812  "last non-overlapping mark of the previous frame" = prevAnMarks[size - nOv - 1] (vp_pitch_frame.prevAnLast),
+ *                         the frame's first mark when there is none;
+ *                   :435  the descent ends at the last lag;   :487  "previous frame voiced" without previous marks searches the
+ *                         frame like a first voiced frame;    :856  the interval search restarts at begin();
+ *                   Notes.cpp:99  above the note table the closest note is the last one.
+ *                   No frame is flagged VP_PF_UB for these sites. Identical to VP_MODE_PARITY wherever none of them is reached
+ *                   with a different outcome. The CPU oracle has the same switch (oracle/vp_oracle.h).
+ * May be called between process calls; takes effect with the next call. */
+#define VP_MODE_PARITY 0
+#define VP_MODE_DEFINED 1
+int vp_engine_set_mode(vp_engine* e, int mode);
 int vp_engine_get_sizes(const vp_engine* e, vp_sizes* out);
 /* Layout the engine chose in vp_engine_prepare: streams processed per pass (nStreams / streamsPerPass passes per call),
  * carried input history per stream (samples) and the device workspace in use. Any pointer may be NULL. */

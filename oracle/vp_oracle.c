@@ -121,6 +121,16 @@ static void levinson(const double* r, double* a, double* ap, int order) {
     for (int i = 1; i <= order; ++i) a[i] *= -1.;
 }
 
+/* ---- defined-behaviour mode ------------------------------------------------------------------
+ * 0 (default): the reference as it runs, undefined-behaviour sites modelled (U1, U6) or flagged (U2-U5).
+ * 1: every such site takes the bounds-correct reading of what the code says it wants -- the same rules as the engine's
+ *    VP_MODE_DEFINED (include/vp_engine.h), so the two can be compared. vpo_defined_deviations() counts how often a
+ *    defined-mode choice differed from what mode 0 would have done on the same state (0 => both modes agree exactly). */
+static int g_defined = 0;
+static long g_deviations = 0;
+void vpo_set_defined(int on) { g_defined = on ? 1 : 0; g_deviations = 0; }
+long vpo_defined_deviations(void) { return g_deviations; }
+
 /* ---- Notes ---------------------------------------------------------------- */
 
 /* Notes.cpp:43-70 buildFreqVect. freq[nFreq] keeps the popped value (U6). */
@@ -146,6 +156,10 @@ static double notes_closest(const vpo_t* o, double pitch, int* idxOut) {
     int idx = lo, pick;
     if (idx > 0) pick = (fabs(o->freq[idx] - pitch) <= fabs(o->freq[idx - 1] - pitch)) ? idx : idx - 1;
     else pick = idx;
+    if (g_defined && idx == o->nFreq) { /* Notes.cpp:99 reads freq[size]: above the table the closest note is the last one */
+        if (pick != idx - 1) g_deviations++;
+        pick = idx - 1;
+    }
     *idxOut = pick;
     return o->freq[pick];
 }
@@ -245,7 +259,7 @@ static void yin(vpo_t* o, long p) {
     while (tau < tauMax) {
         if (y[tau] < o->yinTol) {
             for (;;) {
-                if (tau + 1 >= tauMax) { o->ub |= VPO_UB_YIN_END; break; } /* U3: reads yinTemp[tauMax] */
+                if (tau + 1 >= tauMax) { if (!g_defined) o->ub |= VPO_UB_YIN_END; break; } /* U3: reads yinTemp[tauMax]; defined: the descent ends at the last lag */
                 if (!(y[tau + 1] < y[tau])) break;
                 tau += 1;
                 if (tau + 1 >= tauMax) break;
@@ -268,7 +282,9 @@ static void pitch_marks(vpo_t* o, long p) {
     if (o->pitch > 1) {
         sw_c = (int)floor(o->delta * o->period);
         sw_f = (int)ceil((2.0 - o->delta) * o->period);
-        if (o->prevPitch > 1) {
+        /* defined: "previous frame voiced" needs previous marks to continue from; without any (a gated frame cleared them,
+         * :208-214) the frame is searched like the first voiced frame after an unvoiced one */
+        if (o->prevPitch > 1 && !(g_defined && o->nPan == 0)) {
             if (o->nAnOv == 0) {
                 if (o->nPan == 0) { o->ub |= VPO_UB_PREV_EMPTY; lastMark = 0; } /* U4 */
                 else lastMark = o->pan[o->nPan - 1];
@@ -279,7 +295,7 @@ static void pitch_marks(vpo_t* o, long p) {
                 r_lim = lastMark + (sw_f > a2 ? sw_f : a2); if (r_lim > L) r_lim = L;
                 t = arg_min(o, p, l_lim, r_lim);
             } else t = o->pan[o->nPan - o->nAnOv];
-        } else { searchLeft = 1; t = arg_min(o, p, 0, L); }
+        } else { if (o->prevPitch > 1) g_deviations++; searchLeft = 1; t = arg_min(o, p, 0, L); }
         an_push(o, t);
         while (o->an[o->nAn - 1] + sw_c < L) {
             int bk = o->an[o->nAn - 1];
@@ -326,7 +342,7 @@ static void place_st_marks(vpo_t* o, int* noteIdx) {
     if (o->pitch > 1) {
         if (o->prevPitch > 1) {
             if (o->nStOv > 0) firstMark = o->pst[o->nPst - o->nStOv];
-            else if (o->nPst == 0) { o->ub |= VPO_UB_PREV_EMPTY; firstMark = o->an[0]; }
+            else if (o->nPst == 0) { if (!g_defined) o->ub |= VPO_UB_PREV_EMPTY; firstMark = o->an[0]; } /* defined: start from the first analysis mark */
             else if (o->pst[o->nPst - 1] + o->periodNew >= 0) firstMark = o->pst[o->nPst - 1] + o->periodNew;
             else firstMark = o->an[0];
         } else firstMark = o->an[0];
@@ -393,6 +409,13 @@ static int closest_an(vpo_t* o, int stMark, int T, int lookahead, int* bad) {
         else return -o->nAnOv - 1;
     } else if (idx == 0) return idx;
     else { /* idx == size: reads the stale storage slot an[size] (U1) */
+        if (g_defined) {
+            /* the completeness test is meant for the mark it is about to return: the last one */
+            const int parity = (o->an[idx] + T - nc < lookahead) ? idx - 1 : (idx - 2 >= 0 ? idx - 2 : -99);
+            const int pick = (o->an[idx - 1] + T - nc < lookahead) ? idx - 1 : (idx - 2 >= 0 ? idx - 2 : idx - 1);
+            if (pick != parity) g_deviations++;
+            return pick;
+        }
         if (o->an[idx] + T - nc < lookahead) return idx - 1;
         else if (idx - 2 >= 0) return idx - 2;
         else { *bad = 1; return 0; }
@@ -405,7 +428,7 @@ static void interp(vpo_t* o, const double* x, const double* y, int len, int star
     for (int i = startIdx; i < stopIdx; ++i) {
         if (i >= x[0] && i <= x[len - 1]) {
             int lo = search, hi = len;
-            if (lo < 0) { o->ub |= VPO_UB_INTERP; lo = 0; }
+            if (lo < 0) { if (!g_defined) o->ub |= VPO_UB_INTERP; lo = 0; } /* U5; defined: the search restarts at begin() */
             while (lo < hi) { int mid = (lo + hi) / 2; if (x[mid] < (double)i) lo = mid + 1; else hi = mid; }
             int lb = lo;
             search = lb - 1;
@@ -432,6 +455,13 @@ static void psola(vpo_t* o, int startSample) {
         int clIdx = closest_an(o, stMark, T, lookahead, &bad);
         if (bad) { o->ub |= VPO_UB_ASSERT; clAnMark = o->an[0]; }
         else if (clIdx >= 0) clAnMark = o->an[clIdx];
+        else if (g_defined) {
+            /* :812 "take last element of non overlapping of prevAnMarks": prevAnMarks[size - nOv - 1] (the code's sign slip
+             * makes it size + nOv + 1); without such a mark, the frame's first one */
+            const int k = o->nPan - o->nAnOv - 1;
+            clAnMark = (k >= 0) ? o->pan[k] : o->an[0];
+            g_deviations++;
+        }
         else { o->ub |= VPO_UB_CLOSEST_PREV; clAnMark = 0; } /* U2: out-of-bounds prevAnMarks read */
         int first = (o->stMarkIdx == 0), last = (o->stMarkIdx == o->nSt - 1);
         for (int j = 0; j < len; ++j) {

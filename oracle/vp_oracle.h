@@ -58,6 +58,12 @@ typedef struct {
 #define VPO_UB_CAPACITY 16    /* mark vector would have re-allocated */
 #define VPO_UB_ASSERT 32      /* a reference assert(false) site was reached */
 
+/* Defined-behaviour mode (process-global, not thread-safe: set it before the runs it should apply to). 0 = the reference as
+ * it runs (default), 1 = every undefined-behaviour site takes its bounds-correct reading (the engine's VP_MODE_DEFINED).
+ * vpo_defined_deviations: how often, since vpo_set_defined, a defined-mode choice differed from the mode-0 one. */
+void vpo_set_defined(int on);
+long vpo_defined_deviations(void);
+
 void vpo_default_params(vpo_params* p);
 void vpo_sizes_for(double fs, int B, int key, vpo_sizes* s);
 

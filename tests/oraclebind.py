@@ -45,6 +45,10 @@ def load():
     lib.vpo_notes.restype = C.c_int
     lib.vpo_notes.argtypes = [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int,
                               C.POINTER(C.c_double)]
+    lib.vpo_set_defined.restype = None
+    lib.vpo_set_defined.argtypes = [C.c_int]
+    lib.vpo_defined_deviations.restype = C.c_long
+    lib.vpo_defined_deviations.argtypes = []
     lib.vpo_sizes_for.restype = None
     lib.vpo_sizes_for.argtypes = [C.c_double, C.c_int, C.c_int, C.POINTER(Sizes)]
     _lib = lib
@@ -80,6 +84,15 @@ def run(fs, B, voice, synthL, synthR=None, params=None, log=False, schedule=None
         res["pitch"] = [plog[i] for i in range(min(nP.value, pcap))]
         res["voc"] = [vlog[i] for i in range(min(nV.value, vcap))]
     return res
+
+
+def set_defined(on):
+    """Defined-behaviour mode of the oracle (process-global; resets the deviation counter)."""
+    load().vpo_set_defined(1 if on else 0)
+
+
+def defined_deviations():
+    return int(load().vpo_defined_deviations())
 
 
 def bench(fs, B, voice, synthL, synthR=None, params=None, threads=1, want_out=False):

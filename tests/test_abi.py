@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(vp):
 
 def test_struct_layouts_match_header(vp):
     assert C.sizeof(vp.Params) == 40 and C.sizeof(vp.Sizes) == 13 * 4
-    assert C.sizeof(vp.PitchFrame) == 4 * 9 + 4 * 2 * vp.VP_MAX_MARKS + 4 + 8  # 4 bytes padding before the double
+    assert C.sizeof(vp.PitchFrame) == 4 * 10 + 4 * 2 * vp.VP_MAX_MARKS + 8 == 240
 
 
 def test_default_params_are_the_plugin_defaults(vp):

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libvp_engine.so")
 
 VP_OK, VP_E_ARG, VP_E_STATE, VP_E_CUDA, VP_E_NOMEM, VP_E_RANGE = 0, -1, -2, -3, -4, -5
 VP_MAX_MARKS = 24
+VP_MODE_PARITY, VP_MODE_DEFINED = 0, 1
 VP_NSTAGES = 16
 PF_GATED, PF_VOICED, PF_HAS_MARKS = 1, 2, 4
 PF_NEAR_GATE, PF_NEAR_YIN, PF_UB, PF_YIN_RECHECKED = 16, 32, 64, 128
@@ -28,7 +29,7 @@ ABI_SYMBOLS = [
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
     "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset", "vp_engine_stream_buffers", "vp_engine_stream_block",
-    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan",
+    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan", "vp_engine_set_mode",
 ]
 
 
@@ -49,7 +50,7 @@ class Sizes(C.Structure):
 class PitchFrame(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("period", C.c_int32), ("periodPsola", C.c_int32),
                 ("periodNew", C.c_int32), ("note", C.c_int32), ("nAn", C.c_int32), ("nSt", C.c_int32),
-                ("anStale", C.c_int32), ("nAnOv", C.c_int32), ("anMarks", C.c_int32 * VP_MAX_MARKS),
+                ("anStale", C.c_int32), ("nAnOv", C.c_int32), ("prevAnLast", C.c_int32), ("anMarks", C.c_int32 * VP_MAX_MARKS),
                 ("stMarks", C.c_int32 * VP_MAX_MARKS), ("beta", C.c_double)]
 
 
@@ -92,6 +93,7 @@ def load_library(path=None):
         "vp_engine_get_sizes": (i, [vp, C.POINTER(Sizes)]),
         "vp_engine_get_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]),
         "vp_engine_reserve_orders": (i, [vp, i, i]),
+        "vp_engine_set_mode": (i, [vp, i]),
         "vp_grid_plan": (i, [dbl, i, i, C.POINTER(i), C.POINTER(Params), C.POINTER(CallPlan)]),
         "vp_engine_process_device": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_process_host": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
@@ -278,6 +280,10 @@ class Engine:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._check(self.lib.vp_engine_stream_stats(self.h, C.byref(a), C.byref(b)))
         return {"graph_launches": a.value, "graph_captures": b.value}
+
+    def set_mode(self, mode):
+        """VP_MODE_PARITY (the reference as it runs) or VP_MODE_DEFINED (bounds-correct at its undefined-behaviour sites)."""
+        self._check(self.lib.vp_engine_set_mode(self.h, int(mode)))
 
     def set_params(self, params):
         self._check(self.lib.vp_engine_set_params(self.h, C.byref(params)))

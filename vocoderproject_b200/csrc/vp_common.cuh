@@ -46,6 +46,7 @@ struct VPGeom {
     // (ordV / ordS) or, when a frame carried from an earlier call had a larger order, that one -- rows are zero padded,
     // and a zero tap changes neither the whitening FIR nor the all-pole recursion.
     int synV, synS;
+    int defined;           // VP_MODE_DEFINED: bounds-correct behaviour at the reference's undefined-behaviour sites
     int vocMix, pitchMix;  // the mix adds the vocoder / pitch plane: the path is on, or frames of earlier calls still emit
     // Vocoder frames of earlier calls that are NOT on this call's frame grid: VocoderProcess::process was skipped for some
     // blocks in between (vocBool off), and its startSample -- hence the grid -- froze relative to the block. Their output

@@ -52,6 +52,8 @@ struct GridMove { int srcRow, dstSlot; };  // carry row -> orphan slot (device r
 struct vp_engine {
     int device = 0;
     bool prepared = false;
+    int mode = VP_MODE_PARITY;  // vp_engine_set_mode
+    int lutMode = -1;
     bool failed = false;  // a process call failed half way: the carried state is undefined until vp_engine_reset / vp_engine_prepare
     cudaStream_t st = nullptr, stIn = nullptr, stOut = nullptr;
     cudaStream_t st2 = nullptr;   // the sequential pitch-mark chain runs here, under the vocoder kernels of the same pass
@@ -223,6 +225,7 @@ static int build_note_lut(vp_engine* e) {
         int pick;
         if (idx > 0) pick = (fabs(freq[idx] - pitch) <= fabs(freq[idx - 1] - pitch)) ? idx : idx - 1;  // idx == nf reads the popped slot
         else pick = idx;
+        if (e->mode == VP_MODE_DEFINED && idx == nf) pick = nf - 1;  // above the table the closest note is the last one
         const double closest = freq[pick];
         beta[tau] = closest / pitch;
         pnew[tau] = (int)round(tau / beta[tau]);
@@ -233,6 +236,7 @@ static int build_note_lut(vp_engine* e) {
     if ((rc = upload(e, &e->dLutPeriodNew, pnew))) return rc;
     if ((rc = upload(e, &e->dLutNote, note))) return rc;
     e->lutKey = e->prm.keyPitch;
+    e->lutMode = e->mode;
     e->sz.nFreq = nf;
     return VP_OK;
 }
@@ -359,6 +363,22 @@ static int check_params(const vp_params* p) {
     if (p->keyPitch < 0 || p->keyPitch > 12) return VP_E_RANGE;
     const float gs[4] = {p->gainPitch, p->gainVoice, p->gainSynth, p->gainVoc};
     for (float g : gs) if (!(g >= -60.0f && g <= 6.0f)) return VP_E_RANGE;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_set_mode(vp_engine* e, int mode) {
+    if (!e) return VP_E_ARG;
+    if (mode != VP_MODE_PARITY && mode != VP_MODE_DEFINED) return vp_err(e, VP_E_ARG, "unknown mode");
+    if (mode != e->mode) {
+        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);  // the mode is baked into the captured kernel arguments
+        e->graphs.clear();
+    }
+    e->mode = mode;
+    if (e->prepared && e->lutMode != mode) {
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->st);
+        return build_note_lut(e);
+    }
     return VP_OK;
 }
 
@@ -607,6 +627,7 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     g->vocOn = e->prm.vocBool != 0; g->pitchOn = e->prm.pitchBool != 0;
     g->ordV = e->prm.lpcVoice; g->ordS = e->prm.lpcSynth; g->ordP = e->capP;
     g->H = e->H;
+    g->defined = e->mode == VP_MODE_DEFINED;
     grid_geom(e->gs, g);
     g->gainVocF = db_to_gain(e->prm.gainVoc); g->gainPitchF = db_to_gain(e->prm.gainPitch);
     g->gainVoiceF = db_to_gain(e->prm.gainVoice); g->gainSynthF = db_to_gain(e->prm.gainSynth);

@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
             }
             const uint32_t yf = yflags[fidx];
             if (yf & YF_NEAR) flags |= VP_PF_NEAR_YIN;
-            if (yf & YF_UB) ub = true;
+            if ((yf & YF_UB) && !g.defined) ub = true;  // U3; defined: the descent simply ends at the last lag
             if (yf & YF_DONE64) flags |= VP_PF_YIN_RECHECKED;
             // ---- pitchMarks() (PitchProcess.cpp:455-567)
             pan = an; nPan = nAn;  // prevAnMarks = anMarks (element copy)
@@ -853,7 +853,9 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
                 const int sw_f = (int)ceil((2.0 - 0.94) * period);
                 bool searchLeft = false;
                 int t;
-                if (prevVoiced) {
+                // defined mode: "previous frame voiced" without previous marks (a gated frame cleared them) searches the frame
+                // like the first voiced frame after an unvoiced one
+                if (prevVoiced && !(g.defined && nPan == 0)) {
                     if (nAnOv == 0) {
                         int lastMark = 0;
                         if (nPan == 0) ub = true;  // U4: prevAnMarks.back() on an empty vector
@@ -938,7 +940,7 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
                 else if (voiced) {
                     if (prevVoiced) {
                         if (nStOv > 0) firstMark = SLOT(pst, nPst - nStOv);
-                        else if (nPst == 0) { ub = true; firstMark = SLOT(an, 0); }
+                        else if (nPst == 0) { if (!g.defined) ub = true; firstMark = SLOT(an, 0); }
                         else {
                             const int bk = SLOT(pst, nPst - 1);
                             firstMark = (bk + periodNew >= 0) ? bk + periodNew : SLOT(an, 0);
@@ -966,6 +968,9 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
         if (ub) flags |= VP_PF_UB;
         // ---- record
         const int stale = (nAn < cap) ? SLOT(an, nAn) : 0;
+        // last mark of the previous frame that does not overlap this one (PitchProcess.cpp:812), in this frame's coordinates
+        const int kPrev = nPan - nAnOv - 1;
+        const int prevLast = ((flags & VP_PF_GATED) || kPrev < 0) ? VP_NO_MARK : SLOT(pan, kPrev);
         if (lane < VP_MAX_MARKS) {
             rec->anMarks[lane] = (lane < nAn) ? an : 0;
             rec->stMarks[lane] = (lane < nSt) ? st : 0;
@@ -980,6 +985,7 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
             rec->nSt = nSt;
             rec->anStale = stale;
             rec->nAnOv = nAnOv;
+            rec->prevAnLast = prevLast;
             rec->beta = beta;
         }
     }
@@ -1266,18 +1272,23 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
                     else if (idx - 2 > 0) cl = idx - 2;
                     else cl = -nAnOv - 1;
                 } else if (idx == 0) cl = 0;
-                else {
+                else if (g.defined) {
+                    // the completeness test is meant for the mark about to be returned: the last one
+                    if (sAn[idx - 1] + T - nc < lookahead) cl = idx - 1;
+                    else cl = (idx - 2 >= 0) ? idx - 2 : idx - 1;
+                } else {
                     if (stale + T - nc < lookahead) cl = idx - 1;  // anMarks[size]: stale storage slot (U1)
                     else if (idx - 2 >= 0) cl = idx - 2;
                     else { cl = 0; fl |= 8; }
                 }
                 int clAn;
                 if (cl >= 0) clAn = sAn[cl];
+                else if (g.defined) clAn = (rec->prevAnLast != VP_NO_MARK) ? rec->prevAnLast : sAn[0];  // what :812 means
                 else { clAn = 0; fl |= 8; }  // U2: out-of-bounds prevAnMarks read in the reference
                 const double dSt = (double)stMark;
                 const double x0 = dSt + (double)(-T) / beta;
                 const double xEnd = dSt + (double)(T) / beta;
-                if (x0 >= 0.0 && x0 == floor(x0)) fl |= 8;  // U5
+                if (!g.defined && x0 >= 0.0 && x0 == floor(x0)) fl |= 8;  // U5
                 gSt[tid] = stMark;
                 gCl[tid] = clAn;
                 // output indices i with x0 <= i <= xEnd (interp(), PitchProcess.cpp:850-852), i >= nc (chunk already
