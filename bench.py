@@ -208,6 +208,48 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def numa_bind(dev_index):
+    """Binds this process to the CPUs of the NUMA node the GPU hangs off (pinned buffers are then allocated, first touch, on
+    that node: a copy does not cross the inter-socket link). Returns a description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(dev_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return {"gpu_numa_node": node, "nodes": len(nodes), "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu_numa_node": node, "nodes": len(nodes), "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_numa_node": node, "nodes": len(nodes), "bound": True, "cpus": len(cpus)}
+    except Exception as ex:
+        return {"bound": False, "error": str(ex)[:80]}
+
+
+def link_ceiling(n_gpus):
+    """Duplex pinned-copy rates of the host link with n_gpus GPUs copying at once, from the newest committed probe log
+    (tools/link_probe.cu -> profiles/link_probe_*.jsonl). None when no log covers n_gpus."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "link_probe_*.jsonl"))):
+        for ln in open(path):
+            try:
+                j = json.loads(ln)
+            except ValueError:
+                continue
+            if j.get("gpus") == n_gpus and j.get("h2d") and j.get("d2h") and j.get("copy") == "1d" and j.get("pinned") == "default":
+                if best is None or j["duplex_gbs_total"] >= best["duplex_gbs_total"] or path != best["file"]:
+                    best = dict(j, file=path)
+    return best
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -327,6 +369,7 @@ def run_engine(args, wl, group):
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
     e2e = None
+    cpu_from_pinned = True
     if not args.no_e2e:
         # pinned host memory for the whole batch: 3 arrays per rank; fall back to fewer streams if the box is short
         Se = S
@@ -337,6 +380,7 @@ def run_engine(args, wl, group):
                 Se //= 2
         except Exception:
             pass
+        numa = numa_bind(dev)
         hv, hl, ho = vp.PinnedArray(Se, n), vp.PinnedArray(Se, n), vp.PinnedArray(Se, n)
         eng.d2h(hv.array, dv)
         eng.d2h(hl.array, dl)
@@ -363,11 +407,50 @@ def run_engine(args, wl, group):
         if parity is not None:  # the host path must return what the device-resident path left in HBM, bit for bit
             same = all(np.array_equal(ho.array[s_], dev_rows[s_]) for s_ in picks if s_ < Se)
             parity["e2e_rows_equal_device_rows"] = bool(group.min(1.0 if same else 0.0) > 0.5)
+        link = link_ceiling(group.world)
+        link_info = None
+        if link:
+            lb = max(2.0 * nb_e * group.world / (link["h2d_gbs_total"] * 1e9), 1.0 * nb_e * group.world / (link["d2h_gbs_total"] * 1e9))
+            link_info = {"h2d_gbs": link["h2d_gbs_total"], "d2h_gbs": link["d2h_gbs_total"], "lower_bound_ms": 1e3 * lb,
+                         "source": os.path.relpath(link["file"], ROOT) + ": pinned 1-D copies, both directions at once, %d GPU(s)" % group.world}
         e2e = {"value": e_val, "unit": "audio-s/s", "h2d_bytes_per_step": 2 * nb_e * group.world, "d2h_bytes_per_step": nb_e * group.world,
-               "streams_per_gpu": Se,
+               "streams_per_gpu": Se, "numa": numa, "link": link_info,
+               "link_frac": (link_info["lower_bound_ms"] / (1e3 * e_t / args.steps)) if link_info else None,
                "ms_per_step": 1e3 * e_t / args.steps, "timer": "host wall clock around vp_engine_process_host, max over ranks",
                "note": "voice + side-chain ch0 uploaded (the path reads ch0 only, VocoderProcess.cpp:211,218); one output channel "
                        "returned (L == R while gainSynth <= -59 dB)", "checksum": float(np.abs(ho.array[:, ::4097]).sum())}
+        if not args.no_pcm16:
+            # the same batch as 16-bit PCM across the link (vp_engine_process_host_pcm16): the float rows are quantised in
+            # place into the first half of their own pinned buffers (row s of the int16 view ends before row s of the floats)
+            qv = np.frombuffer((C.c_int16 * (Se * n)).from_address(hv.ptr), dtype=np.int16).reshape(Se, n)
+            ql = np.frombuffer((C.c_int16 * (Se * n)).from_address(hl.ptr), dtype=np.int16).reshape(Se, n)
+            def quantise(pair):  # rows in increasing order per array: row s of the int16 view never reaches an unread float row
+                q_, f_ = pair
+                for s_ in range(Se):
+                    q_[s_] = np.clip(np.rint(f_[s_] * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+            ths = [threading.Thread(target=quantise, args=(pr,)) for pr in ((qv, hv.array), (ql, hl.array))]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            ksteps = max(1, min(args.steps, 5))
+            eng.reset()
+            eng.process_host_pcm16_ptrs(nBlocks, hv.ptr, hl.ptr, None, ho.ptr, None, n)
+            group.barrier()
+            tq0 = time.time()
+            for _ in range(ksteps):
+                eng.reset()
+                eng.process_host_pcm16_ptrs(nBlocks, hv.ptr, hl.ptr, None, ho.ptr, None, n)
+            tq = time.time() - tq0
+            group.barrier()
+            q_val, q_t, _ = vp.shard.aggregate_throughput(group, Se * n / fs * ksteps, tq)
+            qo = np.frombuffer((C.c_int16 * (Se * n)).from_address(ho.ptr), dtype=np.int16).reshape(Se, n)
+            e2e["pcm16"] = {"value": q_val, "unit": "audio-s/s", "steps": ksteps, "ms_per_step": 1e3 * q_t / ksteps,
+                            "h2d_bytes_per_step": nb_e * group.world, "d2h_bytes_per_step": nb_e // 2 * group.world,
+                            "workload": "same batch, 16-bit PCM host arrays through vp_engine_process_host_pcm16 (int16 <-> float on the device, "
+                                        "bit-identical to csrc/vp_wav.hpp's host conversion); an extension for PCM sources, not a format of the reference's processBlock",
+                            "checksum": int(np.abs(qo[:, ::4097].astype(np.int64)).sum())}
+            cpu_from_pinned = False
+        else:
+            cpu_from_pinned = True
     sampler.stop()
 
     # ---- CPU baseline on rank 0 at N = 1: bounded sample of the same workload
@@ -377,8 +460,10 @@ def run_engine(args, wl, group):
         Sc = max(1, min(S if e2e is None else Se, args.cpu_streams or 8 * cores))
         secs_cpu = min(n / fs, 20.0)
         ncpu = int(fs * secs_cpu) // B * B
-        if e2e is not None:
+        if e2e is not None and cpu_from_pinned:
             cv, cl = np.ascontiguousarray(hv.array[:Sc, :ncpu]), np.ascontiguousarray(hl.array[:Sc, :ncpu])
+        elif e2e is not None:  # the pinned float inputs were quantised in place for the PCM16 leg: generate the sample again
+            cv, cl = gen_host_inputs(vp, fs, first, Sc, ncpu, cores)
         else:
             cv = np.zeros((Sc, n), np.float32); cl = np.zeros((Sc, n), np.float32)
             for s in range(Sc):  # row copies of the device inputs
@@ -591,6 +676,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
     ap.add_argument("--seconds", type=float, default=0.0, help="seconds per stream (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pcm16", action="store_true", help="skip the 16-bit PCM end-to-end leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the benchmarked size")
     ap.add_argument("--parity-streams", type=int, default=16, help="streams per rank compared with the reference")
     ap.add_argument("--no-cpu", action="store_true")

@@ -195,6 +195,15 @@ int vp_engine_process_device(vp_engine* e, int nBlocks, const float* voice, cons
 int vp_engine_process_host(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
                            const float* synthR, float* outL, float* outR, size_t strideSamples);
 
+/* Same call with 16-bit PCM host arrays (int16 [nStreams][stride]): the samples cross the host link as 2 bytes and are
+ * converted on the device exactly as the WAV front-end converts on the host (csrc/vp_wav.hpp: x / 32768 in,
+ * clamp(rint(y * 32768)) out), so the result is bit-identical to converting on the host and calling
+ * vp_engine_process_host, then quantising its output. For hosts whose audio is PCM anyway (files, capture devices): half
+ * the link bytes of the float call, and the link is what bounds the end-to-end rate. Not a format of the
+ * reference's processBlock (JUCE buffers are float): an extension of the WAV front-end of SURVEY.md 8(f)#3. */
+int vp_engine_process_host_pcm16(vp_engine* e, int nBlocks, const int16_t* voice, const int16_t* synthL,
+                                 const int16_t* synthR, int16_t* outL, int16_t* outR, size_t strideSamples);
+
 int vp_engine_sync(vp_engine* e);
 
 /* Low-latency streaming, one host block per call (BASELINE config 5). The engine owns pinned host buffers

@@ -485,6 +485,30 @@ def test_voiced_silent_voiced_transitions(vp, oracle):
         eng.close()
 
 
+def test_pcm16_host_path_equals_host_conversion(vp, oracle):
+    """vp_engine_process_host_pcm16 (int16 across the link, converted on the device) == converting on the host the way
+    csrc/vp_wav.hpp does and calling the float entry point: bit-identical int16 output; and within one LSB of the oracle's
+    output on the same quantised input."""
+    fs, B, S = 44100.0, 1024, 5
+    n = 60 * B + 0
+    voice, sl, sr = vp.synth_host(fs, S, n, flavour=0, first_stream=40)
+    q = lambda a: np.clip(np.rint(a * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+    qv, ql, qr = q(voice), q(sl), q(sr)
+    fv, fl, fr = (a.astype(np.float32) * np.float32(1.0 / 32768.0) for a in (qv, ql, qr))
+    for params, use_r in ((dict(keyPitch=3), False), (dict(gainSynth=-12.0, gainVoice=-9.0), True)):
+        eng = vp.Engine(fs, B, S, n // B, params=vp.default_params(**params), workspace_bytes=64 << 20)  # several passes / slices
+        try:
+            oL, oR = eng.process_pcm16(qv, ql, qr if use_r else None)
+            eng.reset()
+            rL, rR = eng.process(fv, fl, fr if use_r else None)
+            assert np.array_equal(oL, q(rL)) and np.array_equal(oR, q(rR))
+            assert oL.any() and (np.array_equal(oL, oR) != use_r)
+        finally:
+            eng.close()
+        r = oracle.run(fs, B, fv[2], fl[2], synthR=fr[2] if use_r else None, params=refbind.default_params(**params))
+        assert np.abs(oL[2].astype(np.int32) - q(r["outL"]).astype(np.int32)).max() <= 1
+
+
 def _run_mode(vp, fs, B, voice, synth, params, mode):
     eng = vp.Engine(fs, B, 1, len(voice) // B, params=vp.default_params(**params))
     try:

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
     "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset", "vp_engine_stream_buffers", "vp_engine_stream_block",
-    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan", "vp_engine_set_mode",
+    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan", "vp_engine_set_mode", "vp_engine_process_host_pcm16",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library(path=None):
         "vp_grid_plan": (i, [dbl, i, i, C.POINTER(i), C.POINTER(Params), C.POINTER(CallPlan)]),
         "vp_engine_process_device": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_process_host": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
+        "vp_engine_process_host_pcm16": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_sync": (i, [vp]),
         "vp_engine_get_pitch_frames": (i, [vp, i, C.POINTER(PitchFrame), i, C.POINTER(i)]),
         "vp_engine_get_voc_frames": (i, [vp, i, i, C.POINTER(i), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -305,6 +306,23 @@ class Engine:
                                                     _ptr(outL), _ptr(outR), n))
         m = nBlocks * self.block
         return outL[:, :m], (outR[:, :m] if outR is not None else None)
+
+    def process_pcm16(self, voice, synthL, synthR=None, want_right=True):
+        """int16 [S][n] host arrays in and out (vp_engine_process_host_pcm16): 16-bit PCM across the host link."""
+        voice = np.ascontiguousarray(voice, np.int16)
+        synthL = np.ascontiguousarray(synthL, np.int16)
+        if synthR is not None:
+            synthR = np.ascontiguousarray(synthR, np.int16)
+        S, n = voice.shape
+        nBlocks = n // self.block
+        outL = np.zeros((S, n), np.int16)
+        outR = np.zeros((S, n), np.int16) if want_right else None
+        self._check(self.lib.vp_engine_process_host_pcm16(self.h, nBlocks, _ptr(voice), _ptr(synthL), _ptr(synthR), _ptr(outL), _ptr(outR), n))
+        m = nBlocks * self.block
+        return outL[:, :m], (outR[:, :m] if outR is not None else None)
+
+    def process_host_pcm16_ptrs(self, n_blocks, voice, synthL, synthR, outL, outR, stride):
+        self._check(self.lib.vp_engine_process_host_pcm16(self.h, int(n_blocks), _ptr(voice), _ptr(synthL), _ptr(synthR), _ptr(outL), _ptr(outR), int(stride)))
 
     def process_host_ptrs(self, n_blocks, voice, synthL, synthR, outL, outR, stride):
         self._check(self.lib.vp_engine_process_host(self.h, int(n_blocks), _ptr(voice), _ptr(synthL), _ptr(synthR),

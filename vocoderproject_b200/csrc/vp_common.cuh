@@ -228,6 +228,9 @@ void vp_launch_carry_out(cudaStream_t st, void* carry, const void* ws, int S, in
 // row `srcRow` of every stream's C-row carried store -> slot `dstSlot` of its D-slot store (same row bytes)
 void vp_launch_row_move(cudaStream_t st, void* dst, const void* src, int S, int rowBytes, int C, int srcRow, int D, int dstSlot);
 void vp_launch_marks_silence(cudaStream_t st, VPMarkState* carry, int S);
+// 16-bit PCM <-> float exactly as vp_wav.hpp converts on the host: x / 32768 in, clamp(rint(x * 32768)) out
+void vp_launch_pcm16_to_float(cudaStream_t st, float* dst, const int16_t* src, long long count);
+void vp_launch_float_to_pcm16(cudaStream_t st, int16_t* dst, const float* src, long long count);
 void vp_launch_voc_orphans(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* synth, const double* oAV,
                            const double* oAS, const double* oEeS, const double* oG, float* outV, int capV, int capS);
 void vp_launch_hist_update(cudaStream_t st, float* hNew, const float* hOld, const float* x, int S, int H, long long n,

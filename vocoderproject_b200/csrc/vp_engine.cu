@@ -115,6 +115,8 @@ struct vp_engine {
     int Sh = 0;
     float* hIn[3][3] = {{nullptr}};
     float* hOut[3][2] = {{nullptr}};
+    int16_t* pIn[3][3] = {{nullptr}};   // 16-bit PCM landing buffers of vp_engine_process_host_pcm16
+    int16_t* pOut[3][2] = {{nullptr}};
     cudaEvent_t evIn[3] = {nullptr}, evComp[3] = {nullptr}, evOut[3] = {nullptr};
     // stats / timing
     uint64_t launches = 0, yinRechecked = 0, yinFrames = 0;
@@ -290,6 +292,8 @@ static void free_workspace(vp_engine* e) {
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) if (e->hIn[i][j]) { cudaFree(e->hIn[i][j]); e->hIn[i][j] = nullptr; }
         for (int j = 0; j < 2; ++j) if (e->hOut[i][j]) { cudaFree(e->hOut[i][j]); e->hOut[i][j] = nullptr; }
+        for (int j = 0; j < 3; ++j) if (e->pIn[i][j]) { cudaFree(e->pIn[i][j]); e->pIn[i][j] = nullptr; }
+        for (int j = 0; j < 2; ++j) if (e->pOut[i][j]) { cudaFree(e->pOut[i][j]); e->pOut[i][j] = nullptr; }
     }
     e->Sh = 0;
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
@@ -493,7 +497,7 @@ extern "C" int vp_engine_prepare(vp_engine* e, double fs, int B, int S, int maxB
     int nV, nP;
     frame_counts(z, n, &nV, &nP);
     nV += 1; nP += 1;  // a frame grid that a vocBool / pitchBool-off stretch has shifted can put one more frame into a call
-    const int capV = std::max(e->prm.lpcVoice, e->reserveV), capS = std::max(e->prm.lpcSynth, e->reserveS), capP = e->prm.lpcPitch;
+    const int capV = std::max(std::max(e->prm.lpcVoice, e->reserveV), 40), capS = std::max(std::max(e->prm.lpcSynth, e->reserveS), 5), capP = e->prm.lpcPitch;
     {
         const char* ym = getenv("VP_YIN_MODE");
         e->yinDirect = (ym && strcmp(ym, "direct") == 0) ? 1 : 0;
@@ -873,6 +877,10 @@ static void grid_geom(const GridState& gs, VPGeom* g) {
     } else {
         g->offV = 0; g->nFramesV = 0; g->kV0 = 0;
     }
+    // Rows are at least as wide as the tuned kernels' orders (40 / 5): a narrower order rides along zero padded, and the
+    // register-resident synthesis kernel serves every lpcVoice <= 40, lpcSynth <= 5 (the taps beyond the order are exact zeros)
+    if (g->synV < 40) g->synV = 40;
+    if (g->synS < 5) g->synS = 5;
     bool orphLive = false;
     for (int j = 0; j < VP_ORPH; ++j) {
         const bool live = gs.orphAbs[j] >= 0 && gs.orphAbs[j] + z.wlenV > u0;
@@ -1068,13 +1076,18 @@ extern "C" int vp_engine_get_info(const vp_engine* e, int* streamsPerPass, int* 
 }
 
 // Host path: slices of Sh streams, H2D on stIn, compute on st, D2H on stOut, three slice buffers in rotation.
-extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
-                                      const float* synthR, float* outL, float* outR, size_t stride) {
-    int rc = check_process_args(e, nBlocks, voice, synthL, synthR, outL, stride);
+// pcm16: the host arrays are 16-bit PCM; they cross the link as such (6 instead of 12 bytes per sample for the default
+// mono-voice + one side-chain channel in, one channel out) and are converted on the device.
+static int process_host_impl(vp_engine* e, int nBlocks, const void* voiceV, const void* synthLV, const void* synthRV, void* outLV,
+                             void* outRV, size_t stride, bool pcm16) {
+    int rc = check_process_args(e, nBlocks, (const float*)voiceV, (const float*)synthLV, (const float*)synthRV, (float*)outLV, stride);
     if (rc) return rc;
     VP_CUDA_OK(cudaSetDevice(e->device));
     const long long n = (long long)nBlocks * e->B;
     const bool synthOn = e->prm.gainSynth > -59.0f;
+    const size_t esz = pcm16 ? sizeof(int16_t) : sizeof(float);
+    const char *voice = (const char*)voiceV, *synthL = (const char*)synthLV, *synthR = (const char*)synthRV;
+    char *outL = (char*)outLV, *outR = (char*)outRV;
     if (e->Sh == 0) {
         // slice = at most Sc streams and at most ~3 GiB per array: large enough that a slice's vocoder kernels outlast
         // its (latency-bound, side-stream) pitch-mark chain, small enough that pipeline fill / drain stay short
@@ -1093,13 +1106,16 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     // the right side-chain travels whenever the caller has one (its ring is filled whatever gainSynth is); the right
     // output only when the dry side-chain is mixed in (otherwise L == R)
     const bool haveR = synthR != nullptr;
-    if (haveR && !e->hIn[0][2]) {
-        const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
+    const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
+    if (haveR && !e->hIn[0][2])
         for (int i = 0; i < 3; ++i) if ((rc = wsalloc(e, &e->hIn[i][2], cnt))) return rc;
-    }
-    if (synthOn && outR && !e->hOut[0][1]) {
-        const size_t cnt = (size_t)e->Sh * (size_t)e->maxBlocks * e->B;
+    if (synthOn && outR && !e->hOut[0][1])
         for (int i = 0; i < 3; ++i) if ((rc = wsalloc(e, &e->hOut[i][1], cnt))) return rc;
+    if (pcm16) {  // 16-bit landing / take-off buffers beside the float ones
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < (haveR ? 3 : 2); ++j) if (!e->pIn[i][j] && (rc = wsalloc(e, &e->pIn[i][j], cnt))) return rc;
+            for (int j = 0; j < ((synthOn && outR) ? 2 : 1); ++j) if (!e->pOut[i][j] && (rc = wsalloc(e, &e->pOut[i][j], cnt))) return rc;
+        }
     }
     begin_call(e);
     VPGeom g;
@@ -1107,7 +1123,7 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
     e->lastBlocks = nBlocks;
     e->lastG = g;
     e->passCount = 0;
-    const size_t rowB = (size_t)n * sizeof(float);
+    const size_t rowB = (size_t)n * esz;
     int slice = 0;
     if (!e->timingOpen) { e->evUsed = 0; e->evSideUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
     // Slice schedule: full slices of Sh streams, tapered at both ends (Sh/4, Sh/2, Sh ... Sh, Sh/2, Sh/4) -- the pipeline
@@ -1122,33 +1138,67 @@ extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* vo
         while (rem > 0) { const int k = std::min(Sh, rem); sizes.push_back(k); rem -= k; }
         if (taper) { sizes.push_back(h); sizes.push_back(q); }
     }
+    // dense host rows (stride == n) go as ONE 1-D copy per array and slice: the strided 2-D form is slower on the upload
+    // (39.7 vs 48.6 GB/s with the download running, profiles/link_probe_1gpu_r02a.jsonl)
+    auto copyIn = [&](void* dst, const char* src, int Sp) -> cudaError_t {
+        if (stride == (size_t)n) return cudaMemcpyAsync(dst, src, rowB * (size_t)Sp, cudaMemcpyHostToDevice, e->stIn);
+        return cudaMemcpy2DAsync(dst, rowB, src, stride * esz, rowB, Sp, cudaMemcpyHostToDevice, e->stIn);
+    };
+    auto copyOut = [&](char* dst, const void* src, int Sp) -> cudaError_t {
+        if (stride == (size_t)n) return cudaMemcpyAsync(dst, src, rowB * (size_t)Sp, cudaMemcpyDeviceToHost, e->stOut);
+        return cudaMemcpy2DAsync(dst, stride * esz, src, rowB, rowB, Sp, cudaMemcpyDeviceToHost, e->stOut);
+    };
     int s0 = 0;
     for (size_t si = 0; si < sizes.size(); s0 += sizes[si], ++si, ++slice) {
         const int Sp = sizes[si];
         const int bi = slice % 3;
         // the buffers of this rotation slot must have been drained (D2H of slice-3 done)
         if (slice >= 3) VP_CUDA_OK(cudaStreamWaitEvent(e->stIn, e->evOut[bi], 0));
-        const size_t hoff = (size_t)s0 * stride;
-        VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][0], rowB, voice + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
-        VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][1], rowB, synthL + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
-        if (haveR)
-            VP_CUDA_OK(cudaMemcpy2DAsync(e->hIn[bi][2], rowB, synthR + hoff, stride * 4, rowB, Sp, cudaMemcpyHostToDevice, e->stIn));
+        const size_t hoff = (size_t)s0 * stride * esz;
+        const long long cntS = (long long)Sp * n;
+        const char* srcs[3] = {voice, synthL, haveR ? synthR : nullptr};
+        for (int j = 0; j < 3; ++j) {
+            if (!srcs[j]) continue;
+            if (pcm16) {
+                VP_CUDA_OK(copyIn(e->pIn[bi][j], srcs[j] + hoff, Sp));
+                vp_launch_pcm16_to_float(e->stIn, e->hIn[bi][j], e->pIn[bi][j], cntS);
+                e->launches++;
+            } else {
+                VP_CUDA_OK(copyIn(e->hIn[bi][j], srcs[j] + hoff, Sp));
+            }
+        }
         VP_CUDA_OK(cudaEventRecord(e->evIn[bi], e->stIn));
         VP_CUDA_OK(cudaStreamWaitEvent(e->st, e->evIn[bi], 0));
-        rc = run_pass(e, g, Sp, s0, e->hIn[bi][0], e->hIn[bi][1], haveR ? e->hIn[bi][2] : nullptr, e->hOut[bi][0],
-                      (synthOn && outR) ? e->hOut[bi][1] : nullptr);
+        const bool wantR = synthOn && outR;
+        rc = run_pass(e, g, Sp, s0, e->hIn[bi][0], e->hIn[bi][1], haveR ? e->hIn[bi][2] : nullptr, e->hOut[bi][0], wantR ? e->hOut[bi][1] : nullptr);
         if (rc) { e->failed = true; return rc; }
+        if (pcm16) {
+            vp_launch_float_to_pcm16(e->st, e->pOut[bi][0], e->hOut[bi][0], cntS);
+            if (wantR) vp_launch_float_to_pcm16(e->st, e->pOut[bi][1], e->hOut[bi][1], cntS);
+            e->launches += wantR ? 2 : 1;
+        }
         VP_CUDA_OK(cudaEventRecord(e->evComp[bi], e->st));
         VP_CUDA_OK(cudaStreamWaitEvent(e->stOut, e->evComp[bi], 0));
-        VP_CUDA_OK(cudaMemcpy2DAsync(outL + hoff, stride * 4, e->hOut[bi][0], rowB, rowB, Sp, cudaMemcpyDeviceToHost, e->stOut));
-        if (outR)  // L == R unless the dry synth is mixed in (MyBuffer.cpp:380-448)
-            VP_CUDA_OK(cudaMemcpy2DAsync(outR + hoff, stride * 4, (synthOn && e->hOut[bi][1]) ? e->hOut[bi][1] : e->hOut[bi][0], rowB, rowB, Sp,
-                                         cudaMemcpyDeviceToHost, e->stOut));
+        const void* oL = pcm16 ? (const void*)e->pOut[bi][0] : (const void*)e->hOut[bi][0];
+        const void* oR = wantR ? (pcm16 ? (const void*)e->pOut[bi][1] : (const void*)e->hOut[bi][1]) : oL;  // L == R unless the dry synth is mixed in (MyBuffer.cpp:380-448)
+        VP_CUDA_OK(copyOut(outL + hoff, oL, Sp));
+        if (outR) VP_CUDA_OK(copyOut(outR + hoff, oR, Sp));
         VP_CUDA_OK(cudaEventRecord(e->evOut[bi], e->stOut));
     }
     finish_call(e, g);
     VP_CUDA_OK(cudaEventRecord(e->evT1, e->st));
+    VP_CUDA_OK(vp_take_launch_error());
     return vp_engine_sync(e);
+}
+
+extern "C" int vp_engine_process_host(vp_engine* e, int nBlocks, const float* voice, const float* synthL,
+                                      const float* synthR, float* outL, float* outR, size_t stride) {
+    return process_host_impl(e, nBlocks, voice, synthL, synthR, outL, outR, stride, false);
+}
+
+extern "C" int vp_engine_process_host_pcm16(vp_engine* e, int nBlocks, const int16_t* voice, const int16_t* synthL,
+                                            const int16_t* synthR, int16_t* outL, int16_t* outR, size_t stride) {
+    return process_host_impl(e, nBlocks, voice, synthL, synthR, outL, outR, stride, true);
 }
 
 // ---- low-latency streaming --------------------------------------------------------------------------------------

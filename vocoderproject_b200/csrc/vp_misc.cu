@@ -127,6 +127,58 @@ void vp_launch_marks_silence(cudaStream_t st, VPMarkState* carry, int S) {
     VP_LAUNCH(k_marks_silence<<<(S + 127) / 128, 128, 0, st>>>(carry, S));
 }
 
+// ---------------------------------------------------------------------------
+// 16-bit PCM on the host link (vp_engine_process_host_pcm16): exactly vp_wav.hpp's conversions -- int16 / 32768 in (exact),
+// clamp(nearbyint(x * 32768)) out (round to nearest even) -- so a PCM16 file run through the WAV front-end gives the same
+// bytes whichever side converts. 8 samples per thread, 16-byte accesses; the tail is scalar.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pcm16_to_float(float* __restrict__ dst, const int16_t* __restrict__ src, long long count) {
+    const long long n8 = count >> 3;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += step) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(src) + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = (float)(short)(w[k] & 0xffff) * (1.0f / 32768.0f);
+            f[2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
+        }
+        float4* d = reinterpret_cast<float4*>(dst) + 2 * i;
+        d[0] = make_float4(f[0], f[1], f[2], f[3]);
+        d[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += step)
+        dst[i] = (float)src[i] * (1.0f / 32768.0f);
+}
+__device__ __forceinline__ int vp_pcm16(float v) {
+    float s = rintf(v * 32768.0f);
+    s = fminf(fmaxf(s, -32768.0f), 32767.0f);
+    return (int)s;
+}
+__global__ void __launch_bounds__(256) k_float_to_pcm16(int16_t* __restrict__ dst, const float* __restrict__ src, long long count) {
+    const long long n8 = count >> 3;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += step) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        int w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = (vp_pcm16(f[2 * k]) & 0xffff) | (vp_pcm16(f[2 * k + 1]) << 16);
+        reinterpret_cast<int4*>(dst)[i] = make_int4(w[0], w[1], w[2], w[3]);
+    }
+    for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += step)
+        dst[i] = (int16_t)vp_pcm16(src[i]);
+}
+void vp_launch_pcm16_to_float(cudaStream_t st, float* dst, const int16_t* src, long long count) {
+    if (count <= 0) return;
+    VP_LAUNCH(k_pcm16_to_float<<<(unsigned)std::min<long long>((count / 8 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(dst, src, count));
+}
+void vp_launch_float_to_pcm16(cudaStream_t st, int16_t* dst, const float* src, long long count) {
+    if (count <= 0) return;
+    VP_LAUNCH(k_float_to_pcm16<<<(unsigned)std::min<long long>((count / 8 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(dst, src, count));
+}
+
 // history update: the H input samples that precede the NEXT call = the last H of (old history ++ this call's input)
 __global__ void __launch_bounds__(256) k_hist_update(float* __restrict__ hNew, const float* __restrict__ hOld,
                                                      const float* __restrict__ x, int S, int H, long long n, long long stride) {

@@ -306,7 +306,8 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     const int ringLen = 0;   // (no raw-sample ring any more: see k_voc_autocorr2)
     const size_t smem2 = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS2 + ringLen)) * sizeof(double);
     // the streaming form needs its seven warps' windows + rings in shared memory (fits up to 88.2 kHz frames)
-    if (g.ordV + 1 <= 3 * AC_R - 1 && g.ordV >= 2 * AC_R - 1 && Gs == 1 && smem2 <= (size_t)200 * 1024) {
+    // (any voice order up to 40 and side-chain order up to 13: lags beyond an order are computed and not stored)
+    if (g.ordV + 1 <= 3 * AC_R - 1 && Gs == 1 && smem2 <= (size_t)200 * 1024) {
         FS = FS2;
         const size_t smem = smem2;
         const int batchesPerStream = (g.nFramesV + AV_BATCH - 1) / AV_BATCH;
@@ -1201,7 +1202,9 @@ void vp_launch_voc_orphans(cudaStream_t st, const VPGeom& g, const VPTables& tb,
 
 // segments per stream group such that the grid is (at most) `waves` full waves of resident warps
 static int vs_segments(const VPGeom& g, int groups, int residentWarps, int* segFramesOut) {
-    int nSeg = (2 * residentWarps) / groups;                            // two waves: second one (nearly) full, no third
+    static int waves = 0;
+    if (waves == 0) { const char* w = getenv("VP_SYNTH_WAVES"); waves = (w && atoi(w) > 0) ? atoi(w) : 2; }
+    int nSeg = (waves * residentWarps) / groups;                        // whole waves of resident warps: the last one (nearly) full
     if (nSeg < 1) nSeg = 1;
     int segFrames = (g.nFramesV + nSeg - 1) / nSeg;
     if (segFrames < 16) segFrames = 16;                                  // keep the 3-row halo a small fraction
