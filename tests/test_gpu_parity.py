@@ -436,6 +436,28 @@ def test_long_streams_match_oracle(vp, fs, S, secs, params, ws_mb):
         eng.close()
 
 
+@pytest.mark.parametrize("params", [dict(lpcVoice=24, lpcSynth=8, lpcPitch=20),   # side-chain order > 5: generic synthesis kernel
+                                    dict(lpcVoice=20, lpcSynth=3, lpcPitch=9),    # below 40 / 5: tuned kernels on zero-padded rows
+                                    dict(lpcVoice=64, lpcSynth=12, lpcPitch=30)])  # above 40: generic kernels throughout
+def test_non_default_orders_at_scale(vp, params):
+    """LPC orders other than the plug-in's defaults on a batch that fills the GPU (256 streams x 10 s, 2 passes): a spread of
+    streams against the reference."""
+    fs, B, S = 44100.0, 1024, 256
+    n = int(fs * 10.0) // B * B
+    voice, sl, _ = vp.synth_host(fs, S, n, flavour=0, first_stream=3000, want_right=False)
+    eng = vp.Engine(fs, B, S, n // B, params=vp.default_params(**params), workspace_bytes=3 << 30)
+    try:
+        outL, _ = eng.process(voice, sl, None, want_right=False)
+        assert np.isfinite(outL).all()
+        picks = [0, 1, 63, 127, 128, 200, 254, 255]
+        refs, kind = reference_runs([(fs, B, voice[s], sl[s], None, params) for s in picks])
+        for s, r in zip(picks, refs):
+            assert_audio(r["outL"], outL[s], "stream %d (%s)" % (s, kind))
+            assert_decisions(compare_decisions(vp, oracle_decisions(r["pitch"]), eng.pitch_frames(s)), "stream %d" % s)
+    finally:
+        eng.close()
+
+
 def test_two_phase_yin_equals_single_pass(vp, monkeypatch):
     """The two-lag-phase YIN (phase 1 decides on lags < 240, phase 2 only for the frames that need more) is exact: same
     periods, same marks, bit-identical audio as one pass over all lags (VP_YIN_PHASES=1), on low and high voices."""

@@ -61,14 +61,16 @@ def test_frame_grids_follow_the_reference_through_enable_toggles(vp, oracle, fs,
 
 
 def test_orders_widen_the_rows_while_older_frames_are_in_flight(vp):
-    """lpcVoice 40 -> 20 between calls: the first call after the change still carries order-40 frames (rows stay 41 wide, the
-    new frames' rows are zero padded); once four order-20 frames have been carried the rows shrink. 20 -> 64: at once."""
+    """Rows are never narrower than the tuned kernels' 40 / 5 (a smaller order rides along zero padded). 40 -> 64 / 5 -> 9: the
+    rows widen at once; 64 -> 48: the first calls after the change still carry order-64 frames, so the rows stay 65 wide until
+    four order-48 frames have been carried."""
     fs, B = 44100.0, 128  # one vocoder frame per block
-    p40, p20, p64 = vp.default_params(), vp.default_params(lpcVoice=20, lpcSynth=3), vp.default_params(lpcVoice=64, lpcSynth=9)
-    plan = vp.grid_plan(fs, B, [(8, p40), (1, p20), (1, p20), (1, p20), (1, p20), (1, p20), (2, p64), (1, p64)])
-    assert [pl.rowOrderV for pl in plan] == [40, 40, 40, 40, 40, 20, 64, 64]
-    assert [pl.rowOrderS for pl in plan] == [5, 5, 5, 5, 5, 3, 9, 9]
-    assert [pl.carriedV for pl in plan] == [0, 4, 4, 4, 4, 4, 4, 4]
+    p40, p20, p64, p48 = (vp.default_params(), vp.default_params(lpcVoice=20, lpcSynth=3), vp.default_params(lpcVoice=64, lpcSynth=9),
+                          vp.default_params(lpcVoice=48, lpcSynth=7))
+    plan = vp.grid_plan(fs, B, [(8, p40), (1, p20), (2, p64), (1, p48), (1, p48), (1, p48), (1, p48), (1, p48), (1, p20)])
+    assert [pl.rowOrderV for pl in plan] == [40, 40, 64, 64, 64, 64, 64, 48, 48]
+    assert [pl.rowOrderS for pl in plan] == [5, 5, 9, 9, 9, 9, 9, 7, 7]
+    assert [pl.carriedV for pl in plan] == [0, 4, 4, 4, 4, 4, 4, 4, 4]
 
 
 def test_vocoder_frames_in_flight_become_orphans_when_the_vocoder_is_switched_off(vp):

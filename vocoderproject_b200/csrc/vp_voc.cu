@@ -302,7 +302,10 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // window reads reach n + m0 + 2R: pad, then round the frame stride to 1 (mod 16)
     int FS = AC_SEGS * segLen + (Gv > Gs ? Gv : Gs) * AC_R + 2 * AC_R + 2;
     while ((FS & 15) != 1) ++FS;
-    const int FS2 = (FS + 15) / 16 * 16 + 1;  // odd distance between the voice and the side-chain copy (see k_voc_autocorr2)
+    // (the streaming form always runs its three voice lag groups, whatever the order: pad for lag offsets up to 27 + 2 R)
+    int FSv = AC_SEGS * segLen + 3 * AC_R + 2 * AC_R + 2;
+    if (FSv < FS) FSv = FS;
+    const int FS2 = (FSv + 15) / 16 * 16 + 1;  // odd distance between the voice and the side-chain copy (see k_voc_autocorr2)
     const int ringLen = 0;   // (no raw-sample ring any more: see k_voc_autocorr2)
     const size_t smem2 = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS2 + ringLen)) * sizeof(double);
     // the streaming form needs its seven warps' windows + rings in shared memory (fits up to 88.2 kHz frames)
@@ -1200,10 +1203,12 @@ void vp_launch_voc_orphans(cudaStream_t st, const VPGeom& g, const VPTables& tb,
     VP_LAUNCH(k_voc_orphans<<<(S + 63) / 64, 64, 0, st>>>(g, tb, synth, oAV, oAS, oEeS, oG, outV, S, capV, capS));
 }
 
-// segments per stream group such that the grid is (at most) `waves` full waves of resident warps
+// segments per stream group such that the grid is (at most) `waves` full waves of resident warps. Measured on the default
+// workload (ms per step of this kernel): 1 wave 126.8, 2 waves 109.3, 3 waves 105.4, 4 waves 103.0 -- shorter segments let
+// the hardware's CTA scheduler even out the warps' run times; the 3-row halo of a segment stays below 1 %
 static int vs_segments(const VPGeom& g, int groups, int residentWarps, int* segFramesOut) {
     static int waves = 0;
-    if (waves == 0) { const char* w = getenv("VP_SYNTH_WAVES"); waves = (w && atoi(w) > 0) ? atoi(w) : 2; }
+    if (waves == 0) { const char* w = getenv("VP_SYNTH_WAVES"); waves = (w && atoi(w) > 0) ? atoi(w) : 4; }
     int nSeg = (waves * residentWarps) / groups;                        // whole waves of resident warps: the last one (nearly) full
     if (nSeg < 1) nSeg = 1;
     int segFrames = (g.nFramesV + nSeg - 1) / nSeg;
