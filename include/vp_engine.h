@@ -140,6 +140,13 @@ int vp_engine_set_params(vp_engine* e, const vp_params* p);
  *                   No frame is flagged VP_PF_UB for these sites. Identical to VP_MODE_PARITY wherever none of them is reached
  *                   with a different outcome. The CPU oracle has the same switch (oracle/vp_oracle.h).
  * May be called between process calls; takes effect with the next call. */
+/* Window type of VocoderProcess::prepare (VocoderProcess.cpp:35-71, setWindows :95-135): VP_WINDOW_SINE is what
+ * prepareToPlay passes (PluginProcessor.cpp:165); VP_WINDOW_HANN is the class's other branch (:116-124: no analysis window,
+ * Hann synthesis window). Before vp_engine_prepare (or after vp_engine_reset, followed by vp_engine_prepare). */
+#define VP_WINDOW_SINE 0
+#define VP_WINDOW_HANN 1
+int vp_engine_set_window(vp_engine* e, int window);
+
 #define VP_MODE_PARITY 0
 #define VP_MODE_DEFINED 1
 int vp_engine_set_mode(vp_engine* e, int mode);

@@ -55,7 +55,14 @@ void operator delete[](void* p, std::size_t) noexcept { std::free(p); }
 #include "PluginProcessor.h"
 #undef private
 
+static int g_window = 0;  // 0 = "sine" (what prepareToPlay passes, PluginProcessor.cpp:165), 1 = "hann"
+
 extern "C" {
+
+// Selects the vocoder window type for the instances created afterwards (process-global). "hann" is reachable in the
+// reference only by editing the string literal in prepareToPlay; the harness calls the reference's own setWindows("hann")
+// right after prepareToPlay instead.
+void vpref_set_window(int w) { g_window = w; }
 
 // Mirrors include/vp_engine.h's vp_params field for field (same order).
 struct vpref_params {
@@ -219,6 +226,7 @@ static int run_impl(double fs, int B, int nBlocks, const float* voice, const flo
     VocoderAudioProcessor proc;
     set_params(proc, *q);
     proc.prepareToPlay(fs, B);
+    if (g_window == 1) proc.vocoderProcess.setWindows("hann");  // the branch prepareToPlay never selects (VocoderProcess.cpp:116-124)
     if (sizes) fill_sizes(proc, sizes);
     AudioBuffer<float> buf(3, B);
     MidiBuffer midi;
@@ -289,6 +297,7 @@ double vpref_bench(double fs, int B, int nBlocks, int S, const float* voice, con
         procs[s].reset(new VocoderAudioProcessor());
         set_params(*procs[s], *q);
         procs[s]->prepareToPlay(fs, B);
+        if (g_window == 1) procs[s]->vocoderProcess.setWindows("hann");
     }
     std::atomic<int> next(0);
     auto work = [&]() {

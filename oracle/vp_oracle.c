@@ -29,7 +29,7 @@ typedef struct {
     vpo_params prm;
     int ub;
     /* vocoder (VocoderProcess.h:36-107) */
-    double *wV, *eV, *eS, *oV;
+    double *wV, *wS, *eV, *eS, *oV; /* analysis / synthesis window of the vocoder (the same for "sine") */
     double rV[ORDER_MAX + 1], aV[ORDER_MAX + 1], apV[ORDER_MAX + 1];
     double rS[ORDER_MAX + 1], aS[ORDER_MAX + 1], apS[ORDER_MAX + 1];
     double HV[10], HS[10], EeV, EeS, g;
@@ -126,6 +126,8 @@ static void levinson(const double* r, double* a, double* ap, int order) {
  * 1: every such site takes the bounds-correct reading of what the code says it wants -- the same rules as the engine's
  *    VP_MODE_DEFINED (include/vp_engine.h), so the two can be compared. vpo_defined_deviations() counts how often a
  *    defined-mode choice differed from what mode 0 would have done on the same state (0 => both modes agree exactly). */
+static int g_window = 0; /* 0 = "sine" (prepareToPlay), 1 = "hann" (VocoderProcess.cpp:116-124) */
+void vpo_set_window(int w) { g_window = w ? 1 : 0; }
 static int g_defined = 0;
 static long g_deviations = 0;
 void vpo_set_defined(int on) { g_defined = on ? 1 : 0; g_deviations = 0; }
@@ -212,7 +214,7 @@ static void voc_window(vpo_t* o, long u0, int block, int gated) {
         }
         float gv = db_to_gain_f(o->prm.gainVoc);
         for (int i = 0; i < o->wlenV; ++i) {
-            double v = gv * o->oV[i] * o->wV[i];
+            double v = gv * o->oV[i] * o->wS[i];
             o->out0[u0 + i] += v;
             o->out1[u0 + i] += v;
         }
@@ -596,6 +598,7 @@ int vpo_process_sched(double fs, int B, int nBlocks, const float* voice, const f
     o->out0 = (double*)calloc(outLen, sizeof(double));
     o->out1 = (double*)calloc(outLen, sizeof(double));
     o->wV = (double*)calloc((size_t)o->wlenV, sizeof(double));
+    o->wS = (double*)calloc((size_t)o->wlenV, sizeof(double));
     o->eV = (double*)calloc((size_t)o->wlenV, sizeof(double));
     o->eS = (double*)calloc((size_t)o->wlenV, sizeof(double));
     o->oV = (double*)calloc((size_t)o->wlenV, sizeof(double));
@@ -614,7 +617,15 @@ int vpo_process_sched(double fs, int B, int nBlocks, const float* voice, const f
         double overlap = (double)(o->wlenV - o->hopV) / (double)o->wlenV;
         double factor = 1.0;
         if (fabs(overlap - 0.75) < pow(10, -10)) factor = 1.0 / sqrt(2);
-        for (int i = 0; i < o->wlenV; ++i) o->wV[i] = factor * sin((i + 0.5) * VPO_PI_VOC / (double)o->wlenV);
+        for (int i = 0; i < o->wlenV; ++i) {
+            if (g_window == 1) { /* "hann" (:116-124): juce hann table (not normalised) x factor for synthesis, no analysis window */
+                o->wS[i] = (0.5 - 0.5 * cos((double)(2 * i) * VPO_PI / (double)(o->wlenV - 1))) * factor;
+                o->wV[i] = 1.0;
+            } else {
+                o->wV[i] = factor * sin((i + 0.5) * VPO_PI_VOC / (double)o->wlenV);
+                o->wS[i] = o->wV[i];
+            }
+        }
         o->g = 0.0; o->EeS = 1.0; o->EeV = 0.0;
         for (int i = 0; i <= ORDER_MAX; ++i) { o->rV[i] = o->aV[i] = o->apV[i] = 1.0; o->rS[i] = o->aS[i] = o->apS[i] = 1.0; }
     }
@@ -697,7 +708,7 @@ int vpo_process_sched(double fs, int B, int nBlocks, const float* voice, const f
     if (nP) *nP = o->nP;
     if (nV) *nV = o->nV;
     if (ubFlags) *ubFlags = o->ub;
-    free(o->out0); free(o->out1); free(o->wV); free(o->eV); free(o->eS); free(o->oV); free(o->yin);
+    free(o->out0); free(o->out1); free(o->wV); free(o->wS); free(o->eV); free(o->eS); free(o->oV); free(o->yin);
     free(o->eFrame); free(o->outE); free(o->yF); free(o->stW); free(o->psW); free(o->perS); free(o->xI);
     free(o);
     return 0;

@@ -61,6 +61,9 @@ typedef struct {
 /* Defined-behaviour mode (process-global, not thread-safe: set it before the runs it should apply to). 0 = the reference as
  * it runs (default), 1 = every undefined-behaviour site takes its bounds-correct reading (the engine's VP_MODE_DEFINED).
  * vpo_defined_deviations: how often, since vpo_set_defined, a defined-mode choice differed from the mode-0 one. */
+/* Vocoder window type of the runs that follow (process-global): 0 = "sine" (what prepareToPlay passes), 1 = "hann"
+ * (VocoderProcess.cpp:116-124: rectangular analysis, Hann synthesis). */
+void vpo_set_window(int hann);
 void vpo_set_defined(int on);
 long vpo_defined_deviations(void);
 

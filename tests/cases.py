@@ -45,10 +45,16 @@ CASES = {
                                            (263, dict(pitchBool=1)), (266, dict(vocBool=1, lpcVoice=48, lpcSynth=8)),
                                            (400, dict(pitchBool=0)), (407, dict(pitchBool=1, lpcVoice=40, lpcSynth=5)),
                                            (500, dict(vocBool=0, gainVoice=-10.0)), (520, dict(vocBool=1)), (600, dict(vocBool=0)), (601, dict(vocBool=1))]),
-    # 48 kHz, block 1024: whole blocks of vocoder / pitch corrector switched off
+    # 48 kHz, block 1024: whole blocks of vocoder / pitch corrector switched off; and the dry side-chain switched ON mid-stream
+    # (gainSynth off -> on: the first `latency` samples it adds come from the right channel's ring of the blocks before,
+    # which is filled whatever gainSynth is, MyBuffer.cpp:69-92) and off / on again
     "chain48_b1024_toggles": dict(fs=48000.0, B=1024, seconds=2.5, input=("synth", 0, 9), params=dict(),
-                                  schedule=[(20, dict(vocBool=0)), (22, dict(vocBool=1)), (40, dict(pitchBool=0)), (41, dict(pitchBool=1)),
-                                            (60, dict(vocBool=0, pitchBool=0)), (63, dict(vocBool=1, pitchBool=1)), (90, dict(pitchBool=0))]),
+                                  schedule=[(20, dict(vocBool=0)), (22, dict(vocBool=1)), (30, dict(gainSynth=-12.0)), (40, dict(pitchBool=0)),
+                                            (41, dict(pitchBool=1)), (60, dict(vocBool=0, pitchBool=0)), (63, dict(vocBool=1, pitchBool=1)),
+                                            (70, dict(gainSynth=-60.0)), (80, dict(gainSynth=-6.0)), (90, dict(pitchBool=0))]),
+    # the "hann" window type of VocoderProcess::setWindows (VocoderProcess.cpp:116-124: rectangular analysis, Hann synthesis),
+    # which prepareToPlay never selects: the harness calls the reference's own setWindows("hann") after prepareToPlay
+    "chain44_hann": dict(fs=44100.0, B=1024, seconds=2.0, input=("synth", 0, 10), params=dict(keyPitch=3), window="hann"),
     # leading silence -> gates (vocoder + pitch) then voiced onset; KAT-style inputs delayed by 0.5 s
     "gate_onset": dict(fs=44100.0, B=1024, seconds=2.0, input=("kat_delayed", 22050), params=dict(keyPitch=3)),
 }

@@ -37,7 +37,9 @@ def main():
         voice, sl, sr = case_inputs(vp, case)
         prm = refbind.default_params(**case["params"])
         sched = [(b, refbind.default_params(**d)) for b, d in case_schedule(case)]
+        refbind.set_window(case.get("window") == "hann")
         r = refbind.run(case["fs"], case["B"], voice, sl, synthR=sr, params=prm, log=True, kind="strict", schedule=sched)
+        refbind.set_window(False)
         rows = oracle_decisions(r["pitch"])
         mm = max([len(x["an"]) for x in rows] + [len(x["st"]) for x in rows] + [1])
         an = np.full((len(rows), mm), -1, np.int32)

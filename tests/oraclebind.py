@@ -45,6 +45,8 @@ def load():
     lib.vpo_notes.restype = C.c_int
     lib.vpo_notes.argtypes = [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int,
                               C.POINTER(C.c_double)]
+    lib.vpo_set_window.restype = None
+    lib.vpo_set_window.argtypes = [C.c_int]
     lib.vpo_set_defined.restype = None
     lib.vpo_set_defined.argtypes = [C.c_int]
     lib.vpo_defined_deviations.restype = C.c_long
@@ -84,6 +86,11 @@ def run(fs, B, voice, synthL, synthR=None, params=None, log=False, schedule=None
         res["pitch"] = [plog[i] for i in range(min(nP.value, pcap))]
         res["voc"] = [vlog[i] for i in range(min(nV.value, vcap))]
     return res
+
+
+def set_window(hann):
+    """Vocoder window of the runs that follow: False = "sine", True = "hann" (process-global)."""
+    load().vpo_set_window(1 if hann else 0)
 
 
 def set_defined(on):

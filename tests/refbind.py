@@ -76,6 +76,8 @@ def load(kind="strict"):
     lib.vpref_notes.restype = C.c_int
     lib.vpref_notes.argtypes = [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int,
                                 C.POINTER(C.c_double)]
+    lib.vpref_set_window.restype = None
+    lib.vpref_set_window.argtypes = [C.c_int]
     lib.vpref_closest_freq.restype = C.c_double
     lib.vpref_closest_freq.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
     _libs[kind] = lib
@@ -130,6 +132,11 @@ def run(fs, B, voice, synthL, synthR=None, params=None, log=False, kind="strict"
         res["pitch"] = [plog[i] for i in range(min(nP.value, pcap))]
         res["voc"] = [vlog[i] for i in range(min(nV.value, vcap))]
     return res
+
+
+def set_window(hann, kind="strict"):
+    """Vocoder window of the instances created from now on: False = "sine" (prepareToPlay's), True = "hann"."""
+    load(kind).vpref_set_window(1 if hann else 0)
 
 
 def bench(fs, B, voice, synthL, synthR=None, params=None, threads=1, kind="fast", want_out=False):

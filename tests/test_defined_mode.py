@@ -44,7 +44,11 @@ def test_defined_mode_equals_the_reference_where_no_site_decides_differently(vp,
     g = golden_load(name)
     voice, sl, sr = case_inputs(vp, case)
     sched = [(b, refbind.default_params(**d)) for b, d in case_schedule(case)]
-    r = defined.run(case["fs"], case["B"], voice, sl, synthR=sr, params=refbind.default_params(**case["params"]), log=True, schedule=sched)
+    defined.set_window(case.get("window") == "hann")
+    try:
+        r = defined.run(case["fs"], case["B"], voice, sl, synthR=sr, params=refbind.default_params(**case["params"]), log=True, schedule=sched)
+    finally:
+        defined.set_window(False)
     dev = defined.defined_deviations()
     assert r["ub"] == 0
     assert np.isfinite(r["outL"]).all()

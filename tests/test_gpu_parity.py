@@ -65,7 +65,7 @@ def run_engine_scheduled(vp, case, voice, sl, sr, extra_cuts=()):
     sched = dict(case_schedule(case))
     cuts = sorted(set([0, nb]) | set(sched) | set(extra_cuts))
     eng = vp.Engine(fs, B, 1, max(b - a for a, b in zip(cuts, cuts[1:])), params=vp.default_params(**case["params"]),
-                    reserve_orders=case.get("reserve"))
+                    reserve_orders=case.get("reserve"), window=vp.VP_WINDOW_HANN if case.get("window") == "hann" else vp.VP_WINDOW_SINE)
     try:
         outL, outR, pf = [], [], []
         vf = {"gated": [], "EeVoice": [], "EeSynth": [], "g": []}
@@ -92,7 +92,8 @@ def test_engine_matches_reference_golden(vp, name):
         l, r, eng = run_engine_scheduled(vp, case, voice, sl, sr)
         outL, outR = l[None], r[None]
     else:
-        outL, outR, eng = run_engine(vp, case["fs"], case["B"], voice[None], sl[None], sr[None], case["params"])
+        outL, outR, eng = run_engine(vp, case["fs"], case["B"], voice[None], sl[None], sr[None], case["params"],
+                                     window=vp.VP_WINDOW_HANN if case.get("window") == "hann" else vp.VP_WINDOW_SINE)
     try:
         assert_audio(g["outL"], outL[0], name + " L")
         assert_audio(g["outR"] if len(g["outR"]) else g["outL"], outR[0], name + " R")

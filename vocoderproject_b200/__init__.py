@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libvp_engine.so")
 VP_OK, VP_E_ARG, VP_E_STATE, VP_E_CUDA, VP_E_NOMEM, VP_E_RANGE = 0, -1, -2, -3, -4, -5
 VP_MAX_MARKS = 24
 VP_MODE_PARITY, VP_MODE_DEFINED = 0, 1
+VP_WINDOW_SINE, VP_WINDOW_HANN = 0, 1
 VP_NSTAGES = 16
 PF_GATED, PF_VOICED, PF_HAS_MARKS = 1, 2, 4
 PF_NEAR_GATE, PF_NEAR_YIN, PF_UB, PF_YIN_RECHECKED = 16, 32, 64, 128
@@ -29,7 +30,7 @@ ABI_SYMBOLS = [
     "vp_host_alloc", "vp_host_free", "vp_device_alloc", "vp_device_free", "vp_memcpy_h2d", "vp_memcpy_d2h",
     "vp_synth_host", "vp_synth_device", "vp_measure_peaks", "vp_engine_timing_reset", "vp_engine_timer_record",
     "vp_engine_timer_elapsed_ms", "vp_engine_last_timing_counts", "vp_measure_peaks2", "vp_engine_reset", "vp_engine_stream_buffers", "vp_engine_stream_block",
-    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan", "vp_engine_set_mode", "vp_engine_process_host_pcm16",
+    "vp_engine_stream_stats", "vp_engine_get_info", "vp_engine_reserve_orders", "vp_grid_plan", "vp_engine_set_mode", "vp_engine_process_host_pcm16", "vp_engine_set_window",
 ]
 
 
@@ -94,6 +95,7 @@ def load_library(path=None):
         "vp_engine_get_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]),
         "vp_engine_reserve_orders": (i, [vp, i, i]),
         "vp_engine_set_mode": (i, [vp, i]),
+        "vp_engine_set_window": (i, [vp, i]),
         "vp_grid_plan": (i, [dbl, i, i, C.POINTER(i), C.POINTER(Params), C.POINTER(CallPlan)]),
         "vp_engine_process_device": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
         "vp_engine_process_host": (i, [vp, i, fp, fp, fp, fp, fp, sz]),
@@ -218,7 +220,8 @@ class Engine:
     Engine(...) ~ construct + set parameters + prepareToPlay(sampleRate, samplesPerBlock);
     process(...) ~ nBlocks consecutive processBlock calls per stream."""
 
-    def __init__(self, sample_rate, block, n_streams, max_blocks, params=None, device=0, workspace_bytes=0, reserve_orders=None):
+    def __init__(self, sample_rate, block, n_streams, max_blocks, params=None, device=0, workspace_bytes=0, reserve_orders=None,
+                 window=VP_WINDOW_SINE):
         self.lib = load_library()
         self.h = C.c_void_p()
         rc = self.lib.vp_engine_create(C.byref(self.h), int(device))
@@ -227,6 +230,8 @@ class Engine:
             raise EngineError(rc, "vp_engine_create failed (no usable CUDA device %d; there is no CPU fallback)" % device)
         self.sample_rate, self.block, self.n_streams, self.max_blocks = float(sample_rate), int(block), int(n_streams), int(max_blocks)
         self.params = params or default_params()
+        if window != VP_WINDOW_SINE:
+            self._check(self.lib.vp_engine_set_window(self.h, int(window)))
         if reserve_orders:  # (maxLpcVoice, maxLpcSynth) that set_params may be given while the streams run
             self._check(self.lib.vp_engine_reserve_orders(self.h, int(reserve_orders[0]), int(reserve_orders[1])))
         self._check(self.lib.vp_engine_set_params(self.h, C.byref(self.params)))

@@ -169,7 +169,8 @@ inline cudaError_t vp_take_launch_error() {
 
 // ---- kernel launchers (one per .cu file) -------------------------------------
 struct VPTables {
-    const double* wV;        // vocoder sine window [wlenV]            VocoderProcess.cpp:125-130
+    const double* wV;        // vocoder analysis window [wlenV]        VocoderProcess.cpp:116-130 ("sine": the sine window; "hann": ones)
+    const double* wS;        // vocoder synthesis window [wlenV]       ("sine": the same table; "hann": Hann x overlap factor)
     const double* stP;       // pitch synthesis window [L]             PitchProcess.cpp:889-905
     const double* hann;      // PSOLA Hann tables, all T               PitchProcess.cpp:878-882
     const int* hannOff;      // offset of table T in hann[], [tauMax+1]

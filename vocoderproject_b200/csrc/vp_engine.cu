@@ -58,7 +58,10 @@ struct vp_engine {
     cudaStream_t st = nullptr, stIn = nullptr, stOut = nullptr;
     cudaStream_t st2 = nullptr;   // the sequential pitch-mark chain runs here, under the vocoder kernels of the same pass
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    std::vector<cudaEvent_t> evSide;  // (start, end) pairs of the side-stream kernel when stage timing is on
+    cudaEvent_t evYin[2] = {nullptr}, evMarks[2] = {nullptr}, evSideDone[2] = {nullptr}, evMix[2] = {nullptr};  // pass phases, by pass parity
+    bool sidePending = false, mixPending = false;  // an earlier pass of this call recorded evMarks / evMix
+    std::vector<cudaEvent_t> evSide;  // (start, end) pairs of the side-stream kernels when stage timing is on
+    std::vector<int> evSideStage;
     size_t evSideUsed = 0;
     bool overlapMarks = true;
     std::string err;
@@ -70,6 +73,8 @@ struct vp_engine {
     size_t workspace = 0;
     VPGeom geom;
     // tables (device)
+    double *dWS = nullptr;  // synthesis window when it differs from the analysis window ("hann")
+    int window = VP_WINDOW_SINE;
     double *dWV = nullptr, *dStP = nullptr, *dHann = nullptr, *dLutBeta = nullptr;
     int *dHannOff = nullptr, *dLutPeriodNew = nullptr, *dLutNote = nullptr;
     int lutKey = -1;
@@ -245,12 +250,21 @@ static int build_note_lut(vp_engine* e) {
 
 static int build_tables(vp_engine* e) {
     const vp_sizes& z = e->sz;
-    std::vector<double> wV(z.wlenV), stP(z.frameLenP, 1.0);
+    std::vector<double> wV(z.wlenV), wS, stP(z.frameLenP, 1.0);
     {
         const double overlap = (double)(z.wlenV - z.hopV) / (double)z.wlenV;
         double factor = 1.0;
         if (fabs(overlap - 0.75) < pow(10, -10)) factor = 1.0 / sqrt(2);
-        for (int i = 0; i < z.wlenV; ++i) wV[i] = factor * sin((i + 0.5) * kPiVoc / (double)z.wlenV);
+        if (e->window == VP_WINDOW_HANN) {
+            // VocoderProcess.cpp:116-124: juce hann table (normalise = false) x overlapFactor for synthesis, no analysis window
+            wS.resize(z.wlenV);
+            for (int i = 0; i < z.wlenV; ++i) {
+                wS[i] = (0.5 - 0.5 * cos((double)(2 * i) * kPi / (double)(z.wlenV - 1))) * factor;
+                wV[i] = 1.0;
+            }
+        } else {
+            for (int i = 0; i < z.wlenV; ++i) wV[i] = factor * sin((i + 0.5) * kPiVoc / (double)z.wlenV);
+        }
     }
     {
         const double overlap = ((double)(z.frameLenP - z.hopP)) / ((double)z.frameLenP);
@@ -272,6 +286,8 @@ static int build_tables(vp_engine* e) {
     }
     int rc;
     if ((rc = upload(e, &e->dWV, wV))) return rc;
+    if (e->dWS) { cudaFree(e->dWS); e->dWS = nullptr; }
+    if (!wS.empty() && (rc = upload(e, &e->dWS, wS))) return rc;
     if ((rc = upload(e, &e->dStP, stP))) return rc;
     if ((rc = upload(e, &e->dHann, hann))) return rc;
     if ((rc = upload(e, &e->dHannOff, off))) return rc;
@@ -332,6 +348,12 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
         cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming);
     }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&e->evTimer[i]);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&e->evYin[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evMarks[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evSideDone[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->evMix[i], cudaEventDisableTiming);
+    }
     { const char* ov = getenv("VP_OVERLAP"); e->overlapMarks = !(ov && ov[0] == '0'); }
     { const char* yp = getenv("VP_YIN_PHASES"); e->yinTwoPhase = !(yp && yp[0] == '1'); }
     const char* pt = getenv("VP_STAGE_TIMING");
@@ -345,7 +367,7 @@ extern "C" void vp_engine_destroy(vp_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     free_workspace(e);
-    void** t[] = {(void**)&e->dWV, (void**)&e->dStP, (void**)&e->dHann, (void**)&e->dHannOff, (void**)&e->dLutBeta,
+    void** t[] = {(void**)&e->dWS, (void**)&e->dWV, (void**)&e->dStP, (void**)&e->dHann, (void**)&e->dHannOff, (void**)&e->dLutBeta,
                   (void**)&e->dLutPeriodNew, (void**)&e->dLutNote};
     for (void** p : t) if (*p) cudaFree(*p);
     for (auto ev : e->ev) cudaEventDestroy(ev);
@@ -354,6 +376,7 @@ extern "C" void vp_engine_destroy(vp_engine* e) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(e->evTimer[i]);
     for (auto ev : e->evSide) cudaEventDestroy(ev);
     cudaEventDestroy(e->evFork); cudaEventDestroy(e->evJoin);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->evYin[i]); cudaEventDestroy(e->evMarks[i]); cudaEventDestroy(e->evSideDone[i]); cudaEventDestroy(e->evMix[i]); }
     cudaStreamDestroy(e->st); cudaStreamDestroy(e->stIn); cudaStreamDestroy(e->stOut); cudaStreamDestroy(e->st2);
     delete e;
 }
@@ -367,6 +390,17 @@ static int check_params(const vp_params* p) {
     if (p->keyPitch < 0 || p->keyPitch > 12) return VP_E_RANGE;
     const float gs[4] = {p->gainPitch, p->gainVoice, p->gainSynth, p->gainVoc};
     for (float g : gs) if (!(g >= -60.0f && g <= 6.0f)) return VP_E_RANGE;
+    return VP_OK;
+}
+
+extern "C" int vp_engine_set_window(vp_engine* e, int window) {
+    if (!e) return VP_E_ARG;
+    if (window != VP_WINDOW_SINE && window != VP_WINDOW_HANN) return vp_err(e, VP_E_ARG, "unknown window type");
+    if (window != e->window) {
+        if (e->prepared && e->gs.blocksDone > 0) return vp_err(e, VP_E_STATE, "the window type is an argument of prepare (VocoderProcess.cpp:35-71): vp_engine_reset first");
+        e->window = window;
+        e->prepared = false;  // the tables are built by vp_engine_prepare
+    }
     return VP_OK;
 }
 
@@ -608,13 +642,15 @@ static void stage_mark(vp_engine* e, int stage) {
     cudaEventRecord(e->ev[e->evUsed++], e->st);
 }
 
-static void side_mark(vp_engine* e) {
+static void side_mark(vp_engine* e, int stage = ST_MARKS) {
     if (!e->stageTiming) return;
     if (e->evSideUsed >= e->evSide.size()) {
         cudaEvent_t ev;
         cudaEventCreate(&ev);
         e->evSide.push_back(ev);
+        e->evSideStage.push_back(stage);
     }
+    e->evSideStage[e->evSideUsed] = stage;
     cudaEventRecord(e->evSide[e->evSideUsed++], e->st2);
 }
 
@@ -641,120 +677,205 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
     return VP_OK;
 }
 
-// One pass over Sc' <= Sc streams whose I/O rows start at the given pointers. streamBase = index of the pass's first
-// stream in the engine's batch (selects its carried state).
-static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, const float* voice, const float* synthL,
-                    const float* synthR, float* outL, float* outR) {
-    cudaStream_t st = e->st;
-    VPTables tb = {e->dWV, e->dStP, e->dHann, e->dHannOff, e->dLutBeta, e->dLutPeriodNew, e->dLutNote};
-    VPGeom g = gIO;
+// ---------------------------------------------------------------------------
+// One pass = Sc' <= Sc streams whose I/O rows start at the given pointers; streamBase = index of the pass's first stream in
+// the engine's batch (selects its carried state). Phases:
+//   A (main)  gate, YIN correlation + decision + FP64 re-decision                       -> evYin
+//   S (side)  pitch-mark chain (sequential per stream: one warp per stream)             -> evSideDone   (needs evYin)
+//   V (main)  vocoder: autocorrelation, Levinson, gain, synthesis
+//   P (main)  pitch LPC, PSOLA, all-pole resynthesis + overlap-add                      (needs evSideDone)
+//   M (main)  mix + egress, carried state, decisions kept for the getters
+// The mark chain has one warp per stream and cannot fill the GPU, so it runs on the side stream next to the vocoder
+// kernels. Measured and NOT adopted (profiles/README.md, round 2): the whole pitch synthesis on the side stream, and passes
+// software-pipelined across each other so that it has more to hide under -- the step time did not move (556.1 vs 555.6 ms):
+// the kernels slow each other down by what they overlap, the step is bound by instruction issue as a whole
+// (roofline.mix), not by latency.
+// ---------------------------------------------------------------------------
+struct PassCtx {
+    VPGeom g;
+    VPTables tb;
+    int Sp = 0;
+    size_t sb = 0;
+    const float *voice = nullptr, *synthL = nullptr, *synthR = nullptr;
+    float *outL = nullptr, *outR = nullptr;
+    int* listCount = nullptr;
+    int slot = 0;        // event set (pass parity)
+    bool sideUsed = false;
+};
+
+static void pass_init(vp_engine* e, PassCtx& c, const VPGeom& gIO, int Sp, int streamBase, const float* voice, const float* synthL,
+                      const float* synthR, float* outL, float* outR) {
+    c.g = gIO;
+    c.tb = VPTables{e->dWV, e->dWS ? e->dWS : e->dWV, e->dStP, e->dHann, e->dHannOff, e->dLutBeta, e->dLutPeriodNew, e->dLutNote};
+    c.Sp = Sp;
+    c.sb = (size_t)streamBase;
     const int hc = e->histCur;
-    const size_t sb = (size_t)streamBase;
-    g.histV = e->cHist[hc][0] + sb * e->H;
-    g.histS = e->cHist[hc][1] + sb * e->H;
-    g.histR = e->cHist[hc][2] + sb * e->H;
-    float* vDst = e->dOutV;
-    float* pDst = e->dOutP;
-    int* listCount = e->dListCount + (e->passCount % 1024);
+    c.g.histV = e->cHist[hc][0] + c.sb * e->H;
+    c.g.histS = e->cHist[hc][1] + c.sb * e->H;
+    c.g.histR = e->cHist[hc][2] + c.sb * e->H;
+    c.voice = voice; c.synthL = synthL; c.synthR = synthR; c.outL = outL; c.outR = outR;
+    c.listCount = e->dListCount + (e->passCount % 1024);
+    c.slot = e->passCount & 1;
     e->passCount++;
-    const size_t fP = (size_t)Sp * g.nFramesP;
-    const int synV1 = g.synV + 1, synS1 = g.synS + 1, capV1 = e->capV + 1, capS1 = e->capS + 1;
-    const long long rowsV = g.nFramesV + VP_VC, rowsP = g.nFramesP + VP_PC, rowsG = g.nBlocks + e->gateCarry;
+    c.sideUsed = false;
+}
+
+// phase A (main stream)
+static int pass_A(vp_engine* e, PassCtx& c) {
+    cudaStream_t st = e->st;
+    const VPGeom& g = c.g;
+    const int Sp = c.Sp;
+    const size_t sb = c.sb;
+    const long long rowsG = g.nBlocks + e->gateCarry;
     stage_mark(e, ST_OTHER);
-    // ---- carried rows of the previous call in front of this call's rows (coefficient rows: from the store's width to the
-    // call's row width; rows of narrower orders are zero padded)
+    // the previous pass's mark chain reads the gate flags and the YIN decisions this phase is about to overwrite
+    if (e->sidePending) VP_CUDA_OK(cudaStreamWaitEvent(st, e->evMarks[c.slot ^ 1], 0));
     vp_launch_carry_in(st, e->dGatePart, e->cGate + sb * e->gateCarry * 4, Sp, 32, 32, e->gateCarry, rowsG);
+    vp_launch_gate(st, g, Sp, c.voice, c.synthL, e->dGate, e->dGatePart, (int)rowsG);
+    vp_launch_carry_out(st, e->cGate + sb * e->gateCarry * 4, e->dGatePart, Sp, 32, 32, e->gateCarry, g.nBlocks, rowsG);
+    if (e->keepDecisions) VP_CUDA_OK(cudaMemcpyAsync(e->dGateAll + sb * g.nBlocks, e->dGate, (size_t)Sp * g.nBlocks, cudaMemcpyDeviceToDevice, st));
+    e->launches += 2;
+    stage_mark(e, ST_GATE);
+    if (g.pitchMix) {
+        VP_CUDA_OK(cudaMemsetAsync(c.listCount, 0, sizeof(int), st));
+        stage_mark(e, ST_CLEAR);
+    }
+    if (g.pitchOn && g.nFramesP > 0) {
+        if (e->yinDirect) {
+            vp_launch_yin(st, g, Sp, c.voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, c.listCount, e->maxList);
+            stage_mark(e, ST_YIN);
+        } else {
+            // (batch calls only: a streaming block has at most one pitch frame per stream and pays per launch)
+            const int k1 = (e->yinTwoPhase && g.nFramesP >= 16) ? vp_yin_phase_split(g) : 0;
+            if (k1 > 0) {
+                // two lag phases: the decision of most voiced frames ends below k1, and the lags above it are then
+                // never correlated for their chunks (exact: see k_yin_decide_reg)
+                const size_t nT = (size_t)Sp * (size_t)vp_yin_corr_tiles(g);
+                int* tCount = e->dYinTiles;
+                int* tFlag = e->dYinTiles + 4;
+                int* tList = tFlag + (size_t)e->Sc * e->yinTilesPerStreamCap;
+                VP_CUDA_OK(cudaMemsetAsync(e->dYinTiles, 0, (4 + nT) * sizeof(int), st));
+                vp_launch_yin_corr(st, g, Sp, c.voice, e->dYinP, e->dYinE, 0, k1, nullptr, nullptr);
+                stage_mark(e, ST_YIN);
+                vp_launch_yin_decide(st, g, Sp, c.voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, c.listCount,
+                                     e->maxList, k1, 1, e->dYinPending, tCount + 1, tFlag, tList, tCount);
+                stage_mark(e, ST_YIN_DECIDE);
+                vp_launch_yin_corr(st, g, Sp, c.voice, e->dYinP, e->dYinE, k1, 0, tList, tCount);
+                stage_mark(e, ST_YIN);
+                vp_launch_yin_decide(st, g, Sp, c.voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, c.listCount,
+                                     e->maxList, 0, 2, e->dYinPending, tCount + 1, tFlag, tList, tCount);
+                stage_mark(e, ST_YIN_DECIDE);
+                e->launches += 3;
+            } else {
+                vp_launch_yin_corr(st, g, Sp, c.voice, e->dYinP, e->dYinE, 0, 0, nullptr, nullptr);
+                stage_mark(e, ST_YIN);
+                vp_launch_yin_decide(st, g, Sp, c.voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, c.listCount,
+                                     e->maxList, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+                stage_mark(e, ST_YIN_DECIDE);
+                e->launches++;
+            }
+        }
+        vp_launch_yin_recheck(st, g, Sp, c.voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, c.listCount, e->maxList);
+        stage_mark(e, ST_YIN64);
+        e->launches += 2;
+    }
+    VP_CUDA_OK(cudaEventRecord(e->evYin[c.slot], st));
+    return VP_OK;
+}
+
+// phase S: everything of the pitch corrector after the YIN decision. On the side stream when the vocoder runs in this pass
+// (it then hides under the vocoder kernels), else on the main stream.
+static int pass_S(vp_engine* e, PassCtx& c) {
+    const VPGeom& g = c.g;
+    const int Sp = c.Sp;
+    const size_t sb = c.sb;
+    const long long rowsP = g.nFramesP + VP_PC;
+    const bool side = e->overlapMarks && g.vocOn && g.pitchOn && g.nFramesP > 0;
+    cudaStream_t q = side ? e->st2 : e->st;
+    c.sideUsed = side;
+    auto mark = [&](int stage) { if (side) side_mark(e, stage); else stage_mark(e, stage); };
+    if (side) {
+        VP_CUDA_OK(cudaStreamWaitEvent(q, e->evYin[c.slot], 0));
+        // the pitch workspace (frame records, LPC rows, PSOLA output, pitch plane) is single: the previous pass's phase M
+        // must have read it (mix, carried records, kept decisions)
+        if (e->mixPending) VP_CUDA_OK(cudaStreamWaitEvent(q, e->evMix[c.slot ^ 1], 0));
+    }
+    if (!g.pitchOn) {
+        // pitchBool off for these blocks: PitchProcess::silence() (PluginProcessor.cpp:218-221)
+        vp_launch_marks_silence(q, e->cMarks + sb, Sp);
+        e->launches++;
+    }
+    if (g.pitchMix) {
+        if (side) side_mark(e, ST_CLEAR);
+        vp_launch_carry_in(q, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), q));
+        mark(ST_CLEAR);
+    }
+    if (g.pitchOn && g.nFramesP > 0) {
+        if (side) side_mark(e, ST_MARKS);
+        vp_launch_marks(q, g, c.tb, Sp, c.voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames, e->cMarks + sb);
+        mark(ST_MARKS);
+        e->launches++;
+    }
+    if (side) {
+        VP_CUDA_OK(cudaEventRecord(e->evMarks[c.slot], q));
+        VP_CUDA_OK(cudaEventRecord(e->evSideDone[c.slot], q));
+        e->sidePending = true;
+    }
+    return VP_OK;
+}
+
+// phase P (main stream): pitch synthesis
+static int pass_P(vp_engine* e, PassCtx& c) {
+    cudaStream_t st = e->st;
+    const VPGeom& g = c.g;
+    const int Sp = c.Sp;
+    if (c.sideUsed) {
+        VP_CUDA_OK(cudaStreamWaitEvent(st, e->evSideDone[c.slot], 0));
+        stage_mark(e, ST_OTHER);  // whatever of the mark chain was not hidden under the vocoder kernels
+    }
+    if (g.pitchMix) {
+        vp_launch_pitch_lpc(st, g, Sp, c.voice, e->dFrames, e->dRP, e->dAP);
+        stage_mark(e, ST_PLPC);
+        vp_launch_pitch_psola(st, g, c.tb, Sp, c.voice, e->dFrames, e->dAP, e->dOutE);
+        stage_mark(e, ST_PFRAME);
+        vp_launch_pitch_iir(st, g, c.tb, Sp, e->dFrames, e->dAP, e->dOutE, e->dOutP);
+        stage_mark(e, ST_PIIR);
+        e->launches += 4;
+        e->yinFrames += (size_t)Sp * g.nFramesP;
+    }
+    return VP_OK;
+}
+
+// phase V (main stream): the vocoder
+static int pass_V(vp_engine* e, PassCtx& c) {
+    cudaStream_t st = e->st;
+    const VPGeom& g = c.g;
+    const int Sp = c.Sp;
+    const size_t sb = c.sb;
+    const int synV1 = g.synV + 1, synS1 = g.synS + 1, capV1 = e->capV + 1, capS1 = e->capS + 1;
+    const long long rowsV = g.nFramesV + VP_VC;
+    float* vDst = e->dOutV;
     if (g.vocOn) {
+        // carried rows of the previous call in front of this call's rows (coefficient rows: from the store's width to the
+        // call's row width; rows of narrower orders are zero padded)
         vp_launch_carry_in(st, e->dAV, e->cAV + sb * VP_VC * capV1, Sp, 8 * synV1, 8 * capV1, VP_VC, rowsV);
         vp_launch_carry_in(st, e->dAS, e->cAS + sb * VP_VC * capS1, Sp, 8 * synS1, 8 * capS1, VP_VC, rowsV);
         vp_launch_carry_in(st, e->dEeS, e->cEeS + sb * VP_VC, Sp, 8, 8, VP_VC, rowsV);
         vp_launch_carry_in(st, e->dGs, e->cG + sb * VP_VC, Sp, 8, 8, VP_VC, rowsV);
-    }
-    if (g.pitchMix) vp_launch_carry_in(st, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
-    vp_launch_gate(st, g, Sp, voice, synthL, e->dGate, e->dGatePart, (int)rowsG);
-    e->launches += 2;
-    stage_mark(e, ST_GATE);
-    // Order: YIN -> [side stream: pitch-mark chain, sequential per stream, latency-bound, few warps] running UNDER
-    // [main stream: the vocoder kernels, which do not depend on it] -> join -> pitch synthesis -> mix.
-    bool forked = false;
-    if (g.pitchMix) {
-        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), st));
-        VP_CUDA_OK(cudaMemsetAsync(listCount, 0, sizeof(int), st));
-        stage_mark(e, ST_CLEAR);
-    }
-    if (!g.pitchOn) {
-        // pitchBool off for these blocks: PitchProcess::silence() (PluginProcessor.cpp:218-221)
-        vp_launch_marks_silence(st, e->cMarks + sb, Sp);
-        e->launches++;
-    }
-    if (g.pitchOn) {
-        if (g.nFramesP > 0) {
-            if (e->yinDirect) {
-                vp_launch_yin(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-                stage_mark(e, ST_YIN);
-            } else {
-                // (batch calls only: a streaming block has at most one pitch frame per stream and pays per launch)
-                const int k1 = (e->yinTwoPhase && g.nFramesP >= 16) ? vp_yin_phase_split(g) : 0;
-                if (k1 > 0) {
-                    // two lag phases: the decision of most voiced frames ends below k1, and the lags above it are then
-                    // never correlated for their chunks (exact: see k_yin_decide_reg)
-                    const size_t nT = (size_t)Sp * (size_t)vp_yin_corr_tiles(g);
-                    int* tCount = e->dYinTiles;
-                    int* tFlag = e->dYinTiles + 4;
-                    int* tList = tFlag + (size_t)e->Sc * e->yinTilesPerStreamCap;
-                    VP_CUDA_OK(cudaMemsetAsync(e->dYinTiles, 0, (4 + nT) * sizeof(int), st));
-                    vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, 0, k1, nullptr, nullptr);
-                    stage_mark(e, ST_YIN);
-                    vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
-                                         e->maxList, k1, 1, e->dYinPending, tCount + 1, tFlag, tList, tCount);
-                    stage_mark(e, ST_YIN_DECIDE);
-                    vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, k1, 0, tList, tCount);
-                    stage_mark(e, ST_YIN);
-                    vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
-                                         e->maxList, 0, 2, e->dYinPending, tCount + 1, tFlag, tList, tCount);
-                    stage_mark(e, ST_YIN_DECIDE);
-                    e->launches += 3;
-                } else {
-                    vp_launch_yin_corr(st, g, Sp, voice, e->dYinP, e->dYinE, 0, 0, nullptr, nullptr);
-                    stage_mark(e, ST_YIN);
-                    vp_launch_yin_decide(st, g, Sp, voice, e->dGate, e->dYinP, e->dYinE, e->dPeriod, e->dYFlags, e->dList, listCount,
-                                         e->maxList, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-                    stage_mark(e, ST_YIN_DECIDE);
-                    e->launches++;
-                }
-            }
-            vp_launch_yin_recheck(st, g, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dList, listCount, e->maxList);
-            stage_mark(e, ST_YIN64);
-            e->launches += 2;
-            if (e->overlapMarks && g.vocOn) {
-                VP_CUDA_OK(cudaEventRecord(e->evFork, st));
-                VP_CUDA_OK(cudaStreamWaitEvent(e->st2, e->evFork, 0));
-                side_mark(e);
-                vp_launch_marks(e->st2, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames, e->cMarks + sb);
-                side_mark(e);
-                VP_CUDA_OK(cudaEventRecord(e->evJoin, e->st2));
-                forked = true;
-            } else {
-                vp_launch_marks(st, g, tb, Sp, voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames, e->cMarks + sb);
-                stage_mark(e, ST_MARKS);
-            }
-            e->launches++;
-        }
-    }
-    if (g.vocOn) {
         if (vp_voc_synth_needs_clear(g)) {
             VP_CUDA_OK(cudaMemsetAsync(e->dOutV, 0, (size_t)Sp * g.wstride * sizeof(float), st));
             stage_mark(e, ST_CLEAR);
         }
         if (g.nFramesV > 0) {
-            vp_launch_voc_autocorr(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS);
+            vp_launch_voc_autocorr(st, g, c.tb, Sp, c.voice, c.synthL, e->dGate, e->dRV, e->dRS);
             stage_mark(e, ST_VOC_AC);
-            vp_launch_voc_levinson(st, g, tb, Sp, voice, synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
+            vp_launch_voc_levinson(st, g, c.tb, Sp, c.voice, c.synthL, e->dGate, e->dRV, e->dRS, e->dAV, e->dAS, e->dEeV, e->dEeS);
             vp_launch_voc_gain(st, g, Sp, e->dEeV, e->dEeS, e->dG, e->dGs, e->cGainHist + sb * 20);
             stage_mark(e, ST_VOC_LEV);
             e->launches += 3;
         }
-        vp_launch_voc_synth(st, g, tb, Sp, synthL, e->dAV, e->dAS, e->dEeS, e->dGs, vDst);
+        vp_launch_voc_synth(st, g, c.tb, Sp, c.synthL, e->dAV, e->dAS, e->dEeS, e->dGs, vDst);
         stage_mark(e, ST_VOC_SYN);
         e->launches += 1;
     } else if (g.vocMix) {
@@ -765,50 +886,18 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         bool any = false;
         for (int j = 0; j < VP_ORPH; ++j) any = any || g.orphPos[j] != VP_NOFRAME;
         if (any) {  // frames of earlier calls that a vocBool-off stretch left off this call's grid
-            vp_launch_voc_orphans(st, g, tb, Sp, synthL, e->oAV + sb * VP_ORPH * capV1, e->oAS + sb * VP_ORPH * capS1, e->oEeS + sb * VP_ORPH,
+            vp_launch_voc_orphans(st, g, c.tb, Sp, c.synthL, e->oAV + sb * VP_ORPH * capV1, e->oAS + sb * VP_ORPH * capS1, e->oEeS + sb * VP_ORPH,
                                   e->oG + sb * VP_ORPH, vDst, e->capV, e->capS);
             stage_mark(e, ST_VOC_SYN);
             e->launches += 1;
         }
     }
-    if (g.pitchMix) {
-        if (forked) {
-            VP_CUDA_OK(cudaStreamWaitEvent(st, e->evJoin, 0));
-            stage_mark(e, ST_OTHER);  // whatever of the mark chain was not hidden under the vocoder kernels
-        }
-        vp_launch_pitch_lpc(st, g, Sp, voice, e->dFrames, e->dRP, e->dAP);
-        stage_mark(e, ST_PLPC);
-        vp_launch_pitch_psola(st, g, tb, Sp, voice, e->dFrames, e->dAP, e->dOutE);
-        stage_mark(e, ST_PFRAME);
-        vp_launch_pitch_iir(st, g, tb, Sp, e->dFrames, e->dAP, e->dOutE, pDst);
-        stage_mark(e, ST_PIIR);
-        e->launches += 4;
-        e->yinFrames += fP;
-    }
-    vp_launch_mix(st, g, Sp, voice, synthL, synthR, e->dOutV, e->dOutP, outL, outR);
-    e->launches++;
-    stage_mark(e, ST_MIX);
-    // ---- state for the next call: last rows of (carry ++ new), and the last H input samples
-    vp_launch_carry_out(st, e->cGate + sb * e->gateCarry * 4, e->dGatePart, Sp, 32, 32, e->gateCarry, g.nBlocks, rowsG);
-    if (g.vocOn) {
+    if (g.vocOn) {  // the vocoder's carried state: last rows of (carry ++ new); kept decisions
         vp_launch_carry_out(st, e->cAV + sb * VP_VC * capV1, e->dAV, Sp, 8 * synV1, 8 * capV1, VP_VC, g.nFramesV, rowsV);
         vp_launch_carry_out(st, e->cAS + sb * VP_VC * capS1, e->dAS, Sp, 8 * synS1, 8 * capS1, VP_VC, g.nFramesV, rowsV);
         vp_launch_carry_out(st, e->cEeS + sb * VP_VC, e->dEeS, Sp, 8, 8, VP_VC, g.nFramesV, rowsV);
         vp_launch_carry_out(st, e->cG + sb * VP_VC, e->dGs, Sp, 8, 8, VP_VC, g.nFramesV, rowsV);
-    }
-    if (g.pitchMix) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
-    vp_launch_hist_update(st, e->cHist[hc ^ 1][0] + sb * e->H, g.histV, voice, Sp, e->H, g.n, g.stride);
-    vp_launch_hist_update(st, e->cHist[hc ^ 1][1] + sb * e->H, g.histS, synthL, Sp, e->H, g.n, g.stride);
-    // channel 1 of the side-chain ring is filled on every block whatever gainSynth is (MyBuffer.cpp:69-92): the history
-    // follows the caller's right channel when there is one, else channel 0 (R == L), so that gainSynth can be automated on
-    vp_launch_hist_update(st, e->cHist[hc ^ 1][2] + sb * e->H, g.histR, synthR ? synthR : synthL, Sp, e->H, g.n, g.stride);
-    if (e->keepDecisions && streamBase >= 0) {
-        if (g.pitchOn && g.nFramesP > 0)
-            VP_CUDA_OK(cudaMemcpy2DAsync(e->dFramesAll + sb * g.nFramesP, (size_t)g.nFramesP * sizeof(vp_pitch_frame),
-                                         e->dFrames + VP_PC, (size_t)rowsP * sizeof(vp_pitch_frame),
-                                         (size_t)g.nFramesP * sizeof(vp_pitch_frame), Sp, cudaMemcpyDeviceToDevice, st));
-        VP_CUDA_OK(cudaMemcpyAsync(e->dGateAll + sb * g.nBlocks, e->dGate, (size_t)Sp * g.nBlocks, cudaMemcpyDeviceToDevice, st));
-        if (g.vocOn && g.nFramesV > 0) {
+        if (e->keepDecisions && g.nFramesV > 0) {
             const size_t w = (size_t)g.nFramesV * 8, sp = (size_t)rowsV * 8;
             VP_CUDA_OK(cudaMemcpy2DAsync(e->dEeVAll + sb * g.nFramesV, w, e->dEeV + VP_VC, sp, w, Sp, cudaMemcpyDeviceToDevice, st));
             VP_CUDA_OK(cudaMemcpy2DAsync(e->dEeSAll + sb * g.nFramesV, w, e->dEeS + VP_VC, sp, w, Sp, cudaMemcpyDeviceToDevice, st));
@@ -816,9 +905,49 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
         }
         stage_mark(e, ST_OTHER);
     }
+    return VP_OK;
+}
+
+// phase M (main stream): mix + egress and what the next call needs
+static int pass_M(vp_engine* e, PassCtx& c) {
+    cudaStream_t st = e->st;
+    const VPGeom& g = c.g;
+    const int Sp = c.Sp;
+    const size_t sb = c.sb;
+    const int hc = e->histCur;
+    const long long rowsP = g.nFramesP + VP_PC;
+    vp_launch_mix(st, g, Sp, c.voice, c.synthL, c.synthR, e->dOutV, e->dOutP, c.outL, c.outR);
+    e->launches++;
+    stage_mark(e, ST_MIX);
+    if (g.pitchMix) vp_launch_carry_out(st, e->cFrames + sb * VP_PC, e->dFrames, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, g.nFramesP, rowsP);
+    vp_launch_hist_update(st, e->cHist[hc ^ 1][0] + sb * e->H, g.histV, c.voice, Sp, e->H, g.n, g.stride);
+    vp_launch_hist_update(st, e->cHist[hc ^ 1][1] + sb * e->H, g.histS, c.synthL, Sp, e->H, g.n, g.stride);
+    // channel 1 of the side-chain ring is filled on every block whatever gainSynth is (MyBuffer.cpp:69-92): the history
+    // follows the caller's right channel when there is one, else channel 0 (R == L), so that gainSynth can be automated on
+    vp_launch_hist_update(st, e->cHist[hc ^ 1][2] + sb * e->H, g.histR, c.synthR ? c.synthR : c.synthL, Sp, e->H, g.n, g.stride);
+    if (e->keepDecisions && g.pitchOn && g.nFramesP > 0)
+        VP_CUDA_OK(cudaMemcpy2DAsync(e->dFramesAll + sb * g.nFramesP, (size_t)g.nFramesP * sizeof(vp_pitch_frame),
+                                     e->dFrames + VP_PC, (size_t)rowsP * sizeof(vp_pitch_frame),
+                                     (size_t)g.nFramesP * sizeof(vp_pitch_frame), Sp, cudaMemcpyDeviceToDevice, st));
+    stage_mark(e, ST_OTHER);
+    VP_CUDA_OK(cudaEventRecord(e->evMix[c.slot], st));
+    e->mixPending = true;
     VP_CUDA_OK(vp_take_launch_error());
     VP_CUDA_OK(cudaGetLastError());
     return VP_OK;
+}
+
+// the phases of one pass
+static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, const float* voice, const float* synthL,
+                    const float* synthR, float* outL, float* outR) {
+    PassCtx c;
+    pass_init(e, c, gIO, Sp, streamBase, voice, synthL, synthR, outL, outR);
+    int rc;
+    if ((rc = pass_A(e, c))) return rc;
+    if ((rc = pass_S(e, c))) return rc;
+    if ((rc = pass_V(e, c))) return rc;
+    if ((rc = pass_P(e, c))) return rc;
+    return pass_M(e, c);
 }
 
 // Before the first pass of a call: what a block with vocBool / pitchBool off does to the state every stream shares.
@@ -1035,11 +1164,11 @@ extern "C" int vp_engine_process_device(vp_engine* e, int nBlocks, const float* 
     e->lastG = g;
     e->passCount = 0;
     if (!e->timingOpen) { e->evUsed = 0; e->evSideUsed = 0; VP_CUDA_OK(cudaEventRecord(e->evT0, e->st)); e->timingOpen = e->timingAccumulate; }
+    e->sidePending = e->mixPending = false;
     for (int s0 = 0; s0 < e->S; s0 += e->Sc) {
         const int Sp = std::min(e->Sc, e->S - s0);
         const size_t off = (size_t)s0 * stride;
-        rc = run_pass(e, g, Sp, s0, voice + off, synthL + off, synthR ? synthR + off : nullptr, outL + off,
-                      outR ? outR + off : nullptr);
+        rc = run_pass(e, g, Sp, s0, voice + off, synthL + off, synthR ? synthR + off : nullptr, outL + off, outR ? outR + off : nullptr);
         if (rc) { e->failed = true; return rc; }  // some streams' carried state has advanced, others' has not
     }
     finish_call(e, g);
@@ -1118,6 +1247,7 @@ static int process_host_impl(vp_engine* e, int nBlocks, const void* voiceV, cons
         }
     }
     begin_call(e);
+    e->sidePending = e->mixPending = false;
     VPGeom g;
     make_geom(e, nBlocks, (size_t)n, &g);  // staged rows are dense
     e->lastBlocks = nBlocks;
@@ -1228,6 +1358,7 @@ extern "C" int vp_engine_stream_block(vp_engine* e) {
     if (e->prm.gainSynth > -59.0f) return vp_err(e, VP_E_ARG, "streaming mode carries side-chain channel 0 only: gainSynth must be off");
     VP_CUDA_OK(cudaSetDevice(e->device));
     begin_call(e);
+    e->sidePending = e->mixPending = false;
     VPGeom g;
     make_geom(e, 1, (size_t)e->B, &g);
     e->lastBlocks = 1;
@@ -1351,7 +1482,7 @@ extern "C" int vp_engine_last_timing_counts(vp_engine* e, int* stageCount) {
     if (!e || !stageCount) return VP_E_ARG;
     for (int i = 0; i < VP_NSTAGES; ++i) stageCount[i] = 0;
     for (size_t i = 1; i < e->evUsed; ++i) stageCount[e->evStage[i]]++;
-    stageCount[ST_MARKS] += (int)(e->evSideUsed / 2);
+    for (size_t i = 1; i < e->evSideUsed; i += 2) stageCount[e->evSideStage[i]]++;
     return VP_OK;
 }
 
@@ -1395,7 +1526,7 @@ extern "C" int vp_engine_last_timing(vp_engine* e, float* totalMs, float* stageM
         for (size_t i = 1; i < e->evSideUsed; i += 2) {
             float ms = 0.f;
             cudaEventSynchronize(e->evSide[i]);
-            if (cudaEventElapsedTime(&ms, e->evSide[i - 1], e->evSide[i]) == cudaSuccess) stageMs[ST_MARKS] += ms;
+            if (cudaEventElapsedTime(&ms, e->evSide[i - 1], e->evSide[i]) == cudaSuccess) stageMs[e->evSideStage[i]] += ms;
         }
     }
     return VP_OK;

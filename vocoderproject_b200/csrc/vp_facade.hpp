@@ -113,6 +113,7 @@ public:
     void setParams(const vp_params& p) { params = p; engine.check(vp_engine_set_params(engine.h, &params)); }
     // largest lpcVoice / lpcSynth that may be set while the streams run (before prepare; VocoderProcess.cpp:50-57 sizes its
     // vectors for the ends of the parameter ranges: 100 / 30)
+    void setWindow(bool hann) { engine.check(vp_engine_set_window(engine.h, hann ? VP_WINDOW_HANN : VP_WINDOW_SINE)); }
     void reserveOrders(int maxLpcVoice, int maxLpcSynth) { engine.check(vp_engine_reserve_orders(engine.h, maxLpcVoice, maxLpcSynth)); }
     // prepareToPlay on a running instance: back to the freshly prepared state first
     void restart() { if (B > 0) engine.check(vp_engine_reset(engine.h)); }
@@ -158,12 +159,14 @@ private:
 class VocoderProcess {
 public:
     void prepare(int wlenIn, int hopIn, std::string windowType, double silenceThresholdDbIn) {
-        if (windowType != "sine") throw Error(VP_E_ARG, "only the \"sine\" window of prepareToPlay is on the path (VocoderProcess.cpp:125-130)");
+        if (windowType != "sine" && windowType != "hann") throw Error(VP_E_ARG, "unknown window type (VocoderProcess.cpp:131-134)");
+        hann = windowType == "hann";
         if (wlenIn != 4 * hopIn) throw Error(VP_E_ARG, "overlap must be 0.75 (VocoderProcess.cpp:110-114)");
         if (silenceThresholdDbIn != -60.0) throw Error(VP_E_ARG, "the gate threshold is the plug-in's -60 dB (PluginProcessor.cpp:148)");
         wlen = wlenIn; hop = hopIn;
     }
     int getLatency(int /*samplesPerBlock*/) const { return wlen; }  // VocoderProcess.cpp:86
+    bool isHann() const { return hann; }
     void process(MyBuffer& myBuffer) {
         if (myBuffer.sizes.wlenV != wlen || myBuffer.sizes.hopV != hop) throw Error(VP_E_ARG, "wlen / hop differ from prepareToPlay's derivation");
         myBuffer.vocRequested = true;
@@ -171,6 +174,7 @@ public:
 
 private:
     int wlen = 0, hop = 0;
+    bool hann = false;
 };
 
 // Source/PitchProcess.h:40-48
@@ -216,7 +220,8 @@ public:
         myBuffer.reserveOrders(maxLpcVoice, maxLpcSynth);
         myBuffer.setParams(params);
         pitchProcess.prepare(sampleRate, 100.0, 800.0, frameLenPitch, hopPitch, samplesPerBlock, silenceDb);   // :172
-        vocoderProcess.prepare(wlenVoc, hopVoc, "sine", silenceDb);                                             // :173
+        vocoderProcess.prepare(wlenVoc, hopVoc, windowType, silenceDb);                                         // :173
+        myBuffer.setWindow(vocoderProcess.isHann());
         latency = std::max(pitchProcess.getLatency(samplesPerBlock), vocoderProcess.getLatency(samplesPerBlock));  // :175
         myBuffer.prepare(samplesPerBlock, frameLenPitch, latency, sampleRate, 1, 2, 2, nStreams, maxBlocksPerCall);  // :176-179
         pitchProcess.prepare2(myBuffer);                                   // :181
@@ -238,6 +243,7 @@ public:
     }
 
     vp_params params;   // the ten plug-in parameters (PluginProcessor.cpp:37-73)
+    std::string windowType = "sine";  // the literal prepareToPlay passes to VocoderProcess::prepare (:173); "hann" = the class's other branch
     MyBuffer myBuffer;
     VocoderProcess vocoderProcess;
     PitchProcess pitchProcess;

@@ -47,8 +47,55 @@ __global__ void __launch_bounds__(256) k_mix(VPGeom g, const float* __restrict__
     }
 }
 
+// The common case -- no dry paths, rows 16-byte aligned -- as 128-bit accesses with 32-bit indexing inside a row: 4 output
+// samples per thread and iteration for 2 loads, 4 adds and 1 (2) stores; the general kernel above spends ~57 instructions
+// per sample on 64-bit index arithmetic (ncu, profiles/ncu_mix_r02e.json), 2.9 % of the whole step's instruction issue.
+template <bool VOC, bool PITCH>
+__global__ void __launch_bounds__(256) k_mix4(const float4* __restrict__ outV, const float4* __restrict__ outP, float4* __restrict__ outL,
+                                              float4* __restrict__ outR, int n4, int stride4, int wstride4) {
+    const int s = blockIdx.y;
+    const float4* a = outV + (size_t)s * wstride4;
+    const float4* b = outP + (size_t)s * wstride4;
+    float4* l = outL + (size_t)s * stride4;
+    float4* r = outR ? outR + (size_t)s * stride4 : nullptr;
+    const int step = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * step) {
+        const int i2 = i + step;
+        const bool two = i2 < n4;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, p0 = v0, p1 = v0;
+        if (VOC) { v0 = __ldg(a + i); if (two) v1 = __ldg(a + i2); }
+        if (PITCH) { p0 = __ldg(b + i); if (two) p1 = __ldg(b + i2); }
+        // (0 + voc) + pitch, the order of the general kernel: bit-identical
+        const float4 o0 = make_float4((0.0f + v0.x) + p0.x, (0.0f + v0.y) + p0.y, (0.0f + v0.z) + p0.z, (0.0f + v0.w) + p0.w);
+        l[i] = o0;
+        if (r) r[i] = o0;
+        if (two) {
+            const float4 o1 = make_float4((0.0f + v1.x) + p1.x, (0.0f + v1.y) + p1.y, (0.0f + v1.z) + p1.z, (0.0f + v1.w) + p1.w);
+            l[i2] = o1;
+            if (r) r[i2] = o1;
+        }
+    }
+}
+
 void vp_launch_mix(cudaStream_t st, const VPGeom& g, int S, const float* voice, const float* synthL,
                    const float* synthR, const float* outV, const float* outP, float* outL, float* outR) {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!g.dryOn && !g.synthOn && (g.n & 3) == 0 && (g.stride & 3) == 0 && (g.wstride & 3) == 0 && g.n / 4 < (1LL << 30) && al16(outV) &&
+        al16(outP) && al16(outL) && al16(outR)) {
+        const int n4 = (int)(g.n / 4);
+        int bx = (n4 + 2 * 256 - 1) / (2 * 256);
+        if (bx > 2048) bx = 2048;
+        if (bx < 1) bx = 1;
+        dim3 grid((unsigned)bx, S);
+        const float4 *a = reinterpret_cast<const float4*>(outV), *b = reinterpret_cast<const float4*>(outP);
+        float4 *l = reinterpret_cast<float4*>(outL), *r = reinterpret_cast<float4*>(outR);
+        const int s4 = (int)(g.stride / 4), w4 = (int)(g.wstride / 4);
+        if (g.vocMix && g.pitchMix) VP_LAUNCH(k_mix4<true, true><<<grid, 256, 0, st>>>(a, b, l, r, n4, s4, w4));
+        else if (g.vocMix) VP_LAUNCH(k_mix4<true, false><<<grid, 256, 0, st>>>(a, b, l, r, n4, s4, w4));
+        else if (g.pitchMix) VP_LAUNCH(k_mix4<false, true><<<grid, 256, 0, st>>>(a, b, l, r, n4, s4, w4));
+        else VP_LAUNCH(k_mix4<false, false><<<grid, 256, 0, st>>>(a, b, l, r, n4, s4, w4));
+        return;
+    }
     long long bx = (g.n + 4 * 256 - 1) / (4 * 256);
     if (bx > 4096) bx = 4096;
     if (bx < 1) bx = 1;

@@ -787,8 +787,12 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
                                                const uint8_t* __restrict__ gate, const int* __restrict__ periodArr,
                                                const uint32_t* __restrict__ yflags, vp_pitch_frame* __restrict__ frames,
                                                VPMarkState* __restrict__ carry, int S) {
-    extern __shared__ float smarks[];  // [warps][L] the current frame's samples (argExt searches hit shared memory)
-    float* fsm = smarks + (size_t)(threadIdx.x >> 5) * g.L;
+    // [warps][2][L + 8] floats: the current frame's samples (argExt searches hit shared memory) and the NEXT frame's, which
+    // arrive by cp.async while this frame's marks are placed -- the chain is sequential per stream and latency-bound, and
+    // half of its time used to be the wait for a frame's samples (ncu: 51 % of the stall samples on the staging lines)
+    extern __shared__ __align__(16) float smarks[];
+    const int LB = (g.L + 8 + 3) & ~3;
+    float* fbuf = smarks + (size_t)(threadIdx.x >> 5) * 2 * LB;
     const int lane = threadIdx.x & 31;
     const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     if (s >= S) return;
@@ -813,10 +817,33 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
         if (nSt >= cap) ub = true;                     \
         if (nSt < VP_SLOTS - 1) { if (lane == nSt) st = (val); ++nSt; } \
     } while (0)
+    // asynchronous copy of frame f's samples into buffer f & 1; returns the offset of the frame's first sample in the buffer
+    // (16-byte copies start at the aligned address at or below it). Frames that reach into the carried history or past the
+    // call's input are staged synchronously when they are needed (shift -1).
+    auto issue = [&](int f) -> int {
+        if (f >= g.nFramesP) return 0;
+        const long long t0 = (long long)f * hop + g.offP - g.lat;
+        int m = -1;
+        if (t0 >= 4 && t0 + L + 4 <= g.n) {
+            m = (int)((reinterpret_cast<uintptr_t>(v.x + t0) >> 2) & 3);
+            const float4* s4 = reinterpret_cast<const float4*>(v.x + t0 - m);
+            float4* d4 = reinterpret_cast<float4*>(fbuf + (f & 1) * LB);
+            const int n4 = (m + L + 3) >> 2;
+            for (int j = lane; j < n4; j += 32) __pipeline_memcpy_async(d4 + j, s4 + j, 16);
+        }
+        __pipeline_commit();
+        return m;
+    };
+    int shiftNext = issue(0);
     for (int f = 0; f < g.nFramesP; ++f) {
         const long long p = (long long)f * hop + g.offP;
         const int b = (int)(p / g.B);
         const size_t fidx = (size_t)s * g.nFramesP + f;
+        __pipeline_wait_prior(0);
+        __syncwarp();  // frame f has landed; every lane is done with frame f - 1's buffer
+        const int shift = shiftNext;
+        float* fsm = fbuf + (f & 1) * LB + (shift > 0 ? shift : 0);
+        shiftNext = issue(f + 1);
         vp_pitch_frame* rec = frames + vp_prow(g, s, f);
         unsigned flags = 0;
         bool ub = false;
@@ -834,7 +861,7 @@ __global__ void __launch_bounds__(128) k_marks(VPGeom g, VPTables tb, const floa
             if (voiced) prevVoicedPeriod = period;
             period = periodArr[fidx];
             voiced = period > 0;
-            if (voiced) {  // only voiced frames search the waveform
+            if (voiced && shift < 0) {  // (only voiced frames search the waveform) edge frame: not prefetched
                 __syncwarp();
                 vp_stage<12>(fsm, v, p, L, g, lane, 32);
                 __syncwarp();
@@ -1009,7 +1036,7 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
     const int threads = 128;
     const long long tot = (long long)S * 32;
     cudaFuncSetAttribute(k_marks, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  // 4 frames of L floats: > 48 KB above 132 kHz
-    VP_LAUNCH(k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * g.L * sizeof(float), st>>>(
+    VP_LAUNCH(k_marks<<<(unsigned)((tot + threads - 1) / threads), threads, (size_t)(threads / 32) * 2 * ((g.L + 8 + 3) & ~3) * sizeof(float), st>>>(
         g, tb, voice, gate, period, yflags, frames, carry, S));
 }
 

@@ -596,251 +596,17 @@ void vp_launch_voc_gain(cudaStream_t st, const VPGeom& g, int S, const double* E
 }
 
 // ---------------------------------------------------------------------------
-// Streaming form of the same stage (default for the plug-in's orders). wlen = 4 hop, so exactly four frames overlap
-// any output position. A group of 4 lanes owns one stream, lane phase phi runs the frames k = phi (mod 4) back to
-// back, and all four lanes step through the SAME output position t in lock step:
-//   * the side-chain sample x[t] is one (broadcast) load for the group -- no staging buffer,
-//   * the overlap-add out[t] = sum of the four lanes' windowed outputs is two xor-shuffles -- no accumulator buffer,
-//     no atomics, no pre-zeroed output, every position written exactly once,
-//   * coefficients are (re)loaded once per frame, states restart at zero (VocoderProcess.cpp:243-247, :280-285).
+// Lock-step streaming synthesis (default for row orders 40 / 5). wlen = 4 hop, so exactly four frames overlap any output
+// position. A group of 4 lanes owns one stream, lane phase phi runs the frames k = phi (mod 4) back to back, and all four
+// lanes step through the SAME output position t in lock step:
+//   * the overlap-add out[t] = sum of the four lanes' windowed outputs is a transpose-reduce of three shuffles per four
+//     positions -- no accumulator buffer, no atomics, no pre-zeroed output, every position written exactly once,
+//   * coefficients are (re)loaded once per frame, states restart at zero (VocoderProcess.cpp:243-247, :280-285); the
+//     recursion is in transposed direct form II: P independent DFMAs per sample, states and coefficients in registers.
 // A warp = 8 streams x one segment of frames; a segment starts 3 rows early (the 3 frames that still overlap its first
-// position) and only emits its own positions. No shared memory except the window table; registers hold a[], the
-// transposed-form states and the FIR taps, so several warps per scheduler stay resident.
-// ---------------------------------------------------------------------------
-#define VT_WARPS 2
-
-// four consecutive side-chain samples at delayed positions t .. t+3 (history before the call, zero beyond its input)
-__device__ __forceinline__ void vt_load4(const VPRow& row, long long t, const VPGeom& g, float* x) {
-    const long long i0 = t - g.lat;
-    if (i0 >= 0 && i0 + 4 <= g.n) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = __ldg(row.x + i0 + j);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = vp_x(row, t + j, g);
-    }
-}
-
-template <int P, int PS>
-__global__ void __launch_bounds__(32 * VT_WARPS) k_voc_synth_stream(VPGeom g, VPTables tb, const float* __restrict__ synth,
-                                                                    const double* __restrict__ aV, const double* __restrict__ aS,
-                                                                    const double* __restrict__ EeS, const double* __restrict__ G,
-                                                                    float* __restrict__ outV, int S,
-                                                                    int nSeg, int segFrames, int rowPad) {
-    extern __shared__ double wv[];  // window rows: wv[r * rowPad + i] = w[r * hop + i] (row stride odd: 4 phases, 4 banks)
-    const int hop = g.hopV;
-    for (int i = threadIdx.x; i < 4 * hop; i += blockDim.x) wv[(i / hop) * rowPad + (i % hop)] = tb.wV[i];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-lane landing zone of the NEXT frame's parameters, filled by cp.async one hop-row ahead of its use:
-    // [0, P] aV row, [P+1, P+PS+1] aS row, then the frame's gain and its EeSynth (< 0 marks a gated frame)
-    constexpr int CF_AS = P + 1, CF_G = P + PS + 2, CF_ES = CF_G + 1, CF_N = CF_ES + 1;
-    constexpr int CF_STRIDE = CF_N | 1;  // odd stride: the 64-bit reads of 32 lanes hit distinct banks
-    double* cf = wv + 4 * rowPad + ((size_t)warp * 32 + lane) * CF_STRIDE;
-    const long long wid = (long long)blockIdx.x * VT_WARPS + warp;
-    const int groups = (S + 7) / 8;
-    if (wid >= (long long)groups * nSeg) return;
-    const int grp = (int)(wid / nSeg), seg = (int)(wid - (long long)grp * nSeg);
-    const int phi = lane & 3;
-    int s = grp * 8 + (lane >> 2);
-    const bool sOk = s < S;
-    if (!sOk) s = S - 1;  // idle group: runs along on a valid stream, stores are masked
-    // Rows: row rho = the hop positions [rho hop + offV, (rho + 1) hop + offV) (call-local); frame rho starts at its row.
-    // Rows < 0 belong to frames of the previous call (carry rows of the workspace) that still reach into this one.
-    const int kS = seg * segFrames;
-    const int nRowsAll = (int)((g.n - g.offV + hop - 1) / hop);  // rows that start before the end of the call
-    if (seg > 0 && kS >= nRowsAll) return;
-    const bool lastSeg = (seg == nSeg - 1) || (kS + segFrames >= nRowsAll);
-    const int kE = lastSeg ? nRowsAll : kS + segFrames;
-    const long long emit0 = (seg == 0) ? 0 : (long long)kS * hop + g.offV;
-    const long long emit1 = lastSeg ? g.n : (long long)kE * hop + g.offV;
-    const int rho0 = (seg == 0) ? -VP_VC : kS - 3;  // a position is covered by 4 frames; 4 carry rows when offV > 0
-    const VPRow y = vp_row(synth, g.histS, s, g);
-    float* o = outV + (size_t)s * g.vstride;
-    double a[P + 1], as[PS + 1], st[P + 1], t[PS + 1];
-#pragma unroll
-    for (int j = 0; j <= P; ++j) { a[j] = 0.0; st[j] = 0.0; }
-#pragma unroll
-    for (int j = 0; j <= PS; ++j) { as[j] = 0.0; t[j] = 0.0; }
-    int wrow = 0;  // window row of this lane's current frame in the current hop-row
-    float xA[4] = {0.f, 0.f, 0.f, 0.f}, xB[4] = {0.f, 0.f, 0.f, 0.f};  // side-chain samples of the next block / the one after
-    bool primed = false;
-    auto frameOk = [&](int k) { return k + g.kV0 >= 0 && k < g.nFramesV; };  // frame exists (global index >= 0, starts inside)
-    auto prefetch = [&](int k) {  // asynchronous copy of frame k's parameters into this lane's landing zone
-        if (frameOk(k) && ((k + 4 * VP_VC) & 3) == phi) {
-            const size_t row = vp_vrow(g, s, k);
-            const double* ap = aV + row * (P + 1);
-#pragma unroll
-            for (int j = 0; j <= P; ++j) __pipeline_memcpy_async(cf + j, ap + j, 8);
-            const double* sp = aS + row * (PS + 1);
-#pragma unroll
-            for (int j = 0; j <= PS; ++j) __pipeline_memcpy_async(cf + CF_AS + j, sp + j, 8);
-            __pipeline_memcpy_async(cf + CF_G, G + row, 8);
-            __pipeline_memcpy_async(cf + CF_ES, EeS + row, 8);
-        }
-        __pipeline_commit();
-    };
-    prefetch(rho0);
-    for (int rho = rho0; rho < kE; ++rho) {
-        __pipeline_wait_prior(0);
-        // ---- frame start for the phase that begins at this row
-        if (((rho + 4 * VP_VC) & 3) == phi) {
-#pragma unroll
-            for (int j = 0; j <= P; ++j) st[j] = 0.0;
-#pragma unroll
-            for (int j = 0; j <= PS; ++j) t[j] = 0.0;
-            // a gated frame carries EeSynth < 0 (written by the Levinson kernel; VocoderProcess.cpp:199-204)
-            const bool active = frameOk(rho) && cf[CF_ES] >= 0.0;
-            if (active) {
-                const double gain = cf[CF_G];
-#pragma unroll
-                for (int j = 1; j <= P; ++j) a[j] = cf[j];
-#pragma unroll
-                for (int j = 0; j <= PS; ++j) as[j] = gain * cf[CF_AS + j];  // gain folded into the FIR taps
-            } else {
-#pragma unroll
-                for (int j = 1; j <= P; ++j) a[j] = 0.0;
-#pragma unroll
-                for (int j = 0; j <= PS; ++j) as[j] = 0.0;
-            }
-            wrow = 0;
-        }
-        prefetch(rho + 1);
-        const double* wr = wv + wrow * rowPad;
-        const long long tBase = (long long)rho * hop + g.offV;
-        const bool emitRow = sOk;
-        // Software pipeline inside a row (blocks of 4 positions): while block b runs its 4 x P dependent-on-one-value
-        // DFMA batches, the whitening FIR of block b+1 and the overlap-add shuffles + store of block b-1 are issued
-        // from the same straight-line code, so their latencies hide under the FP64 pipe. Samples are fetched two
-        // blocks ahead. The pipeline drains at the end of a row (a new frame may start at the next one).
-        const int nblk = (hop + 3) >> 2;
-        // side-chain loads of this row (offsets reach at most hop + 7 past its start): when all of them fall inside this
-        // call's input they are plain loads off one row pointer, no per-block range test or 64-bit address arithmetic
-        const long long rowIn = tBase - g.lat;
-        const bool rowFast = rowIn >= 0 && rowIn + hop + 8 <= g.n;
-        const float* rowPtr = y.x + rowIn;
-        auto load4 = [&](int off, float* x) {
-            if (rowFast) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = __ldg(rowPtr + off + j);
-            } else vt_load4(y, tBase + off, g, x);
-        };
-        if (!primed) {
-            load4(0, xA);
-            load4((4 < hop) ? 4 : hop, xB);
-            primed = true;
-        }
-        double eN[4];
-        {   // FIR of block 0 (not overlapped: once per row)
-            const int nb0 = min(4, hop);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                eN[j] = 0.0;
-                if (j < nb0) {
-                    const double x = (double)xA[j] * wr[j];
-                    eN[j] = fma(as[0], x, t[0]);
-#pragma unroll
-                    for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) xA[j] = xB[j];
-            // samples of block 2 of this row, or of the first block(s) of the next row
-            load4((8 < hop) ? 8 : ((4 < hop) ? hop : hop + 4), xB);
-        }
-        float cP[4] = {0.f, 0.f, 0.f, 0.f};
-        int iP = 0, nbP = 0;  // offset in the row and size of the block whose overlap-add is pending
-        // the whole row lies inside this segment's emission range: stores go off one row pointer, no range test
-        const bool rowEmit = emitRow && tBase >= emit0 && tBase + hop <= emit1;
-        float* orow = o + tBase;
-        auto emit = [&](float tot) {
-            if (rowEmit) {
-                if (phi < nbP) orow[iP + phi] = tot;
-            } else {
-                const long long tp = tBase + iP + phi;
-                if (emitRow && phi < nbP && tp >= emit0 && tp < emit1) o[tp] = tot;
-            }
-        };
-        // FULL: block b and block b+1 are both complete blocks of this row -> no guards, one basic block
-        auto blockStep = [&](auto fullTag, int b) {
-            constexpr bool FULL = decltype(fullTag)::value;
-            const int i0 = b << 2;
-            const int nb = FULL ? 4 : min(4, hop - i0);
-            double e[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = eN[j];
-            // ---- FIR of block b+1 (same row only)
-            if (FULL || b + 1 < nblk) {
-                const int i1 = i0 + 4, nb1 = FULL ? 4 : min(4, hop - i1);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    eN[j] = 0.0;
-                    if (FULL || j < nb1) {
-                        const double x = (double)xA[j] * wr[i1 + j];
-                        eN[j] = fma(as[0], x, t[0]);
-#pragma unroll
-                        for (int qq = 0; qq < PS; ++qq) t[qq] = fma(as[qq + 1], x, t[qq + 1]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xA[j] = xB[j];
-                // start of the block three ahead in the global block sequence (rows are contiguous in position)
-                const int i3 = i0 + 12;
-                int on;
-                if (i3 < hop) on = i3;
-                else if (i0 + 8 < hop) on = hop;          // block b+2 is the row's last: b+3 = next row, block 0
-                else on = hop + 4;                        // block b+1 is the row's last: b+3 = next row, block 1
-                load4(on, xB);
-            }
-            // ---- all-pole recursion of block b
-            float c[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (FULL || j < nb) {
-                    const double ov = e[j] + st[0];
-#pragma unroll
-                    for (int kk = 0; kk < P; ++kk) st[kk] = fma(-a[kk + 1], ov, st[kk + 1]);
-                    c[j] = (float)(ov * wr[i0 + j]);  // window re-read from shared memory: cheaper than 8 live registers
-                } else c[j] = 0.0f;
-            }
-            // ---- overlap-add of the 4 phase lanes for the 4 positions of block b-1: transpose-reduce, 3 shuffles;
-            // lane phi ends with the sum over the group of cP[phi] (block -1 of a row: zeros, nbP = 0 -> no store)
-            {
-                const bool hi = (phi & 2) != 0, od = (phi & 1) != 0;
-                const float s0 = hi ? cP[0] : cP[2], s1 = hi ? cP[1] : cP[3];   // send the pair the partner (xor 2) owns
-                const float k0 = hi ? cP[2] : cP[0], k1 = hi ? cP[3] : cP[1];   // keep the own pair
-                const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
-                const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-                const float snd = od ? r0 : r1, kp = od ? r1 : r0;
-                const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
-                emit(tot);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cP[j] = c[j];
-            iP = i0;
-            nbP = nb;
-        };
-        const int nFullPairs = (hop >> 2) - 1;  // blocks b with b and b+1 both full: b < hop/4 - 1
-        int b = 0;
-        for (; b < nFullPairs; ++b) blockStep(std::true_type{}, b);
-        for (; b < nblk; ++b) blockStep(std::false_type{}, b);
-        {   // drain: the row's last block
-            const bool hi = (phi & 2) != 0, od = (phi & 1) != 0;
-            const float s0 = hi ? cP[0] : cP[2], s1 = hi ? cP[1] : cP[3];
-            const float k0 = hi ? cP[2] : cP[0], k1 = hi ? cP[3] : cP[1];
-            const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
-            const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-            const float snd = od ? r0 : r1, kp = od ? r1 : r0;
-            const float tot = kp + __shfl_xor_sync(0xffffffffu, snd, 1);
-            emit(tot);
-        }
-        ++wrow;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Row-staged form of the streaming synthesis (default). Same lock-step scheme and the same arithmetic as
-// k_voc_synth_stream (FIR32 = false: bit-identical output), rebuilt around what the pipe microbenchmark
+// position) and only emits its own positions.
+// Round 2 rebuilt the step (round 1: k_voc_synth_stream, same arithmetic -- FIR32 = false is bit-identical to it; 146.7 ->
+// 103 ms per step of the default workload) around what the pipe microbenchmark
 // (tools/ubench_mix.cu, profiles/ubench_mix_r02a.txt) measured on the B200: next to DFMAs NO other instruction issues for
 // free -- an FFMA, an integer op or a load each cost their own issue cycle, an F2F about 2.7 -- so the step is trimmed to
 // its 40 + 6 DFMAs plus the fewest possible other instructions:
@@ -868,7 +634,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_voc_synth_rows(VPGeom g, VPTa
                                                                   const double* __restrict__ aV, const double* __restrict__ aS,
                                                                   const double* __restrict__ EeS, const double* __restrict__ G,
                                                                   float* __restrict__ outV, int S, int nSeg, int segFrames,
-                                                                  int wPad, int xPad) {
+                                                                  int wPad, int xPad, int wsOff) {
     using WT = typename std::conditional<FIR32, float, double>::type;  // window / FIR arithmetic type
     extern __shared__ __align__(16) unsigned char vr_smem[];
     constexpr int CF_AS = P + 1, CF_G = P + PS + 2, CF_ES = CF_G + 1, CF_N = CF_ES + 1;
@@ -876,11 +642,14 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_voc_synth_rows(VPGeom g, VPTa
     const int hop = g.hopV;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* xsAll = reinterpret_cast<float*>(vr_smem);                         // [VR_WARPS][2][8][xPad] side-chain rows
-    WT* wv = reinterpret_cast<WT*>(xsAll + (size_t)VR_WARPS * 2 * 8 * xPad);  // [4][wPad] window rows
-    double* cfAll = reinterpret_cast<double*>(wv + (size_t)4 * wPad);         // [VR_WARPS][8][CF_STRIDE] frame parameters
+    // [4][wPad] analysis-window rows, then -- wsOff != 0: the "hann" window type, whose synthesis window differs
+    // (VocoderProcess.cpp:116-124) -- [4][wPad] synthesis-window rows; for "sine" both are the same table
+    WT* wv = reinterpret_cast<WT*>(xsAll + (size_t)VR_WARPS * 2 * 8 * xPad);
+    double* cfAll = reinterpret_cast<double*>(wv + (size_t)4 * wPad + wsOff);  // [VR_WARPS][8][CF_STRIDE] frame parameters
     for (int i = threadIdx.x; i < 4 * wPad; i += blockDim.x) {
         const int r = i / wPad, c = i - r * wPad;
         wv[i] = (c < hop) ? (WT)tb.wV[r * hop + c] : (WT)0;
+        if (wsOff) wv[wsOff + i] = (c < hop) ? (WT)tb.wS[r * hop + c] : (WT)0;
     }
     __syncthreads();
     const long long wid = (long long)blockIdx.x * VR_WARPS + warp;
@@ -971,6 +740,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_voc_synth_rows(VPGeom g, VPTa
         if (rho + 1 < kE) stage(rho + 1, cur ^ 1);
         const float* xr = xs0 + cur * xbuf;
         const WT* wr = wv + wrow * wPad;
+        const WT* wo = wr + wsOff;  // synthesis-window row
         const long long tBase = (long long)rho * hop + g.offV;
         const bool rowEmit = sOk && tBase >= emit0 && tBase + hop <= emit1;  // whole row inside the emission range
         const int nblk = (hop + 3) >> 2;
@@ -1011,10 +781,10 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_voc_synth_rows(VPGeom g, VPTa
                 constexpr bool FULL = decltype(fullTag)::value;
                 WT w4[4];
                 if (FIR32) {
-                    const float4 q = *reinterpret_cast<const float4*>(wr + i0);
+                    const float4 q = *reinterpret_cast<const float4*>(wo + i0);
                     w4[0] = (WT)q.x; w4[1] = (WT)q.y; w4[2] = (WT)q.z; w4[3] = (WT)q.w;
                 } else {
-                    const double2 q0 = *reinterpret_cast<const double2*>(wr + i0), q1 = *reinterpret_cast<const double2*>(wr + i0 + 2);
+                    const double2 q0 = *reinterpret_cast<const double2*>(wo + i0), q1 = *reinterpret_cast<const double2*>(wo + i0 + 2);
                     w4[0] = (WT)q0.x; w4[1] = (WT)q0.y; w4[2] = (WT)q1.x; w4[3] = (WT)q1.y;
                 }
 #pragma unroll
@@ -1128,7 +898,7 @@ __global__ void __launch_bounds__(32 * VS_WARPS) k_voc_synth_generic(VPGeom g, V
     double h[VP_ORDER_MAX];
     for (int j = 0; j < P; ++j) h[j] = 0.0;
     for (int i = 0; i < wlen; ++i) {
-        const double w = tb.wV[i];
+        const double w = tb.wS[i];
         double o = 0.0;
         if (active) {
             double e = 0.0;
@@ -1187,8 +957,8 @@ __global__ void __launch_bounds__(64) k_voc_orphans(VPGeom g, VPTables tb, const
         for (int i = 0; i < g.wlenV; ++i) {
             const long long u = (long long)pos + i;
             if (u >= g.n) break;
-            const double w = tb.wV[i];
-            const double x = (double)vp_x(y, u, g) * w;
+            const double x = (double)vp_x(y, u, g) * tb.wV[i];
+            const double w = tb.wS[i];
             const double e = fma(gain * as[0], x, t[0]);
             for (int q = 0; q < PS; ++q) t[q] = fma(gain * as[q + 1], x, t[q + 1]);
             const double ov = e + st[0];
@@ -1230,7 +1000,8 @@ static void launch_synth_rows(cudaStream_t st, const VPGeom& g, const VPTables& 
     if (FIR32) wPad = vr_pad4odd(g.hopV);
     else { wPad = 4 * nblk; if (((wPad >> 1) & 1) == 0) wPad += 2; }     // doubles: 16-byte rows, row stride / 16 B odd
     const int cfStride = (40 + 1 + 5 + 1 + 2) | 1;
-    const size_t smem = (size_t)VR_WARPS * 2 * 8 * xPad * sizeof(float) + (size_t)4 * wPad * (FIR32 ? sizeof(float) : sizeof(double)) +
+    const int wsOff = (tb.wS != tb.wV) ? 4 * wPad : 0;  // "hann": a second table for the synthesis window
+    const size_t smem = (size_t)VR_WARPS * 2 * 8 * xPad * sizeof(float) + (size_t)(4 * wPad + wsOff) * (FIR32 ? sizeof(float) : sizeof(double)) +
                         (size_t)VR_WARPS * 8 * cfStride * sizeof(double);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int perSM = 4, dev = 0, nSM = 148;
@@ -1242,15 +1013,16 @@ static void launch_synth_rows(cudaStream_t st, const VPGeom& g, const VPTables& 
     const int nSeg = vs_segments(g, groups, nSM * perSM * VR_WARPS, &segFrames);
     const long long warps = (long long)groups * nSeg;
     VP_LAUNCH(kern<<<(unsigned)((warps + VR_WARPS - 1) / VR_WARPS), 32 * VR_WARPS, smem, st>>>(
-        g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, wPad, xPad));
+        g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, wPad, xPad, wsOff));
 }
 
-// VP_SYNTH = rows (default) | rows32 (FP32 whitening FIR + window) | stream (round-1 kernel)
+// VP_SYNTH = rows (default) | rows32 (FP32 whitening FIR + window multiplies: 102.5 vs 109.3 ms per step at 2 waves, worst
+// stream 124 dB instead of 146 dB against the reference) | generic (the any-order kernel, for A/B)
 static int vs_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VP_SYNTH");
-        v = (e && strcmp(e, "stream") == 0) ? 2 : (e && strcmp(e, "rows32") == 0) ? 1 : 0;
+        v = (e && strcmp(e, "generic") == 0) ? 2 : (e && strcmp(e, "rows32") == 0) ? 1 : 0;
     }
     return v;
 }
@@ -1260,24 +1032,6 @@ void vp_launch_voc_synth(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
     if (g.synV == 40 && g.synS == 5 && vs_variant() != 2 && g.hopV >= 8) {
         if (vs_variant() == 1) launch_synth_rows<true>(st, g, tb, S, synth, aV, aS, EeS, G, outV);
         else launch_synth_rows<false>(st, g, tb, S, synth, aV, aS, EeS, G, outV);
-        return;
-    }
-    if (g.synV == 40 && g.synS == 5) {
-        const int groups = (S + 7) / 8;
-        int perSM = 4, dev = 0, nSM = 148;
-        const int rowPad = g.hopV | 1;
-        const int cfStride = (40 + 1 + 5 + 1 + 2) | 1;
-        const size_t smem = ((size_t)4 * rowPad + (size_t)VT_WARPS * 32 * cfStride) * sizeof(double);
-        cudaFuncSetAttribute(k_voc_synth_stream<40, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_voc_synth_stream<40, 5>, 32 * VT_WARPS, smem);
-        if (perSM < 1) perSM = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
-        int segFrames = 0;
-        const int nSeg = vs_segments(g, groups, nSM * perSM * VT_WARPS, &segFrames);
-        const long long warps = (long long)groups * nSeg;
-        VP_LAUNCH(k_voc_synth_stream<40, 5><<<(unsigned)((warps + VT_WARPS - 1) / VT_WARPS), 32 * VT_WARPS, smem, st>>>(
-            g, tb, synth, aV, aS, EeS, G, outV, S, nSeg, segFrames, rowPad));
         return;
     }
     const int tilesPerStream = (g.nFramesV + VP_VC + 31) / 32;
