@@ -1221,8 +1221,8 @@ template <int P>
 __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTables tb, const float* __restrict__ voice,
                                                             vp_pitch_frame* __restrict__ frames,
                                                             const double* __restrict__ aP, float* __restrict__ outE,
-                                                            int xLen, int eLen) {
-    extern __shared__ double smd[];
+                                                            int xLen, int eLen, int eAlloc) {
+    extern __shared__ __align__(16) double smd[];
     const int f = (int)blockIdx.x - VP_PC, s = blockIdx.y;  // f = -1: the previous call's last frame
     const size_t fidx = vp_prow(g, s, f);
     vp_pitch_frame* rec = frames + fidx;
@@ -1230,8 +1230,10 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     if (!pf_live(g, rec, f)) return;
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
-    double* e = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smd) + 15) & ~(uintptr_t)15);  // [eLen + pad] residual, e[j] <-> frame-relative idx j - tauMax
-    float* xfBase = (float*)(e + ((eLen + PF_XPAD + 1) & ~1));  // 16-byte aligned; [xLen + pad] floats; dead after the residual -> oE [L] doubles
+    double* e = smd;  // [eLen + pad] residual, e[j] <-> frame-relative idx j - tauMax (16-byte aligned: the shared-memory window is)
+    // (eAlloc <= eLen doubles are allocated: grain samples end at clAn + T + tauMax <= L + 2 tauMax, the 3-chunk look-ahead of
+    // the reference's eFrame beyond that is never read)
+    float* xfBase = (float*)(e + ((eAlloc + PF_XPAD + 1) & ~1));  // 16-byte aligned; [xLen + pad] floats; dead after the residual -> oE [L] doubles + Hann table
     double* oE = (double*)xfBase;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
     const VPRow v = vp_row(voice, g.histV, s, g);
@@ -1260,8 +1262,8 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     }
     const float* xf = xfBase + m;  // the PF_XPAD floats after xf[xLen - 1] only feed residual samples nobody reads
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
-    __shared__ int sELo, sEHi;
-    if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; }
+    __shared__ int sELo, sEHi, sUb;
+    if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; sUb = 0; }
     const double* ap = aP + fidx * (size_t)(ord + 1);
     const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
     // Hann table of this frame's period (PitchProcess.cpp:878-882): read in place (one table per period, shared by every
@@ -1273,7 +1275,11 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     // chunk n at which the reference handles it (the first n with stMark - T < (n + 1) c), the look-ahead and residual
     // extent visible at that chunk, the closest complete analysis mark, the output range -- so that the element loop
     // below carries no per-grain scalar work.
-    __shared__ int gSt[VP_MAX_MARKS], gCl[VP_MAX_MARKS], gI0[VP_MAX_MARKS], gI1[VP_MAX_MARKS], gEv[VP_MAX_MARKS], gFl[VP_MAX_MARKS];
+    // per synthesis mark: flags, mark, output range [gI0, gI1), e index of grain sample 0, number of grain samples that exist
+    // in the residual filtered so far, and the range [gW0, gW1) of grain samples the Hann window applies to (all of them for
+    // an inner mark, the second half for the first mark, the first half for the last: PitchProcess.cpp:697-731)
+    __shared__ int gSt[VP_MAX_MARKS], gI0[VP_MAX_MARKS], gI1[VP_MAX_MARKS], gFl[VP_MAX_MARKS], gEb[VP_MAX_MARKS], gJl[VP_MAX_MARKS],
+        gW0[VP_MAX_MARKS], gW1[VP_MAX_MARKS];
     const double beta = rec->beta;
     const bool okT = T > 0 && T < tauMax;
     if (tid < VP_MAX_MARKS) {
@@ -1317,18 +1323,26 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
                 const double xEnd = dSt + (double)(T) / beta;
                 if (!g.defined && x0 >= 0.0 && x0 == floor(x0)) fl |= 8;  // U5
                 gSt[tid] = stMark;
-                gCl[tid] = clAn;
                 // output indices i with x0 <= i <= xEnd (interp(), PitchProcess.cpp:850-852), i >= nc (chunk already
                 // filtered, App. A.4 #6), i < L: as integer bounds -- i >= x0 <=> i >= ceil(x0), and i < ceil(xEnd)
                 // already implies i <= xEnd -- so that the element loop compares integers only
                 gI0[tid] = max(max((int)ceil(x0), 0), nc);
                 gI1[tid] = min((int)ceil(xEnd), L);
-                gEv[tid] = L + nc;                            // residual filtered so far
+                {
+                    const int eValid = L + nc;                  // residual filtered so far
+                    const int eBase = clAn - T + tauMax;        // e index of grain sample j = 0
+                    gEb[tid] = eBase;
+                    gJl[tid] = min(min(eLen, eAlloc) - eBase, eValid - (clAn - T));  // grain samples j < jLim exist in the residual so far
+                    const bool first = tid == 0, last = tid == nSt - 1;
+                    gW0[tid] = first ? T : 0;
+                    gW1[tid] = (!first && last) ? T : 2 * T + 1;
+                }
                 atomicMin(&sELo, max(clAn - T + tauMax - 1, 0));          // grain samples j = 0 .. 2T (and j - 1)
-                atomicMax(&sEHi, min(clAn + T + tauMax + 1, eLen));
+                atomicMax(&sEHi, min(clAn + T + tauMax + 1, min(eLen, eAlloc)));
                 fl |= 1 | (tid == 0 ? 2 : 0) | (tid == nSt - 1 ? 4 : 0);
             }
         }
+        if (fl & 8) atomicOr(&sUb, 1);
         gFl[tid] = fl;
     }
     __pipeline_wait_prior(0);
@@ -1369,43 +1383,47 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
         }
     }
     __syncthreads();
-    for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;  // own indices only (i mod PF_THREADS == tid): no barrier needed
+    // ---- PSOLA proper. The frame's Hann table (PitchProcess.cpp:878-882, one per period) is copied into the dead sample
+    // region first (behind the accumulator), so the two window values of a contribution are shared-memory reads -- they were
+    // dependent global loads, 21 % of this kernel's stall samples in the round-1 profile. Per synthesis mark everything that
+    // does not depend on the output index comes from the grain table; thread <-> output index i is fixed (i mod PF_THREADS)
+    // so that successive grains accumulate into oE[i] in mark order without synchronisation.
     bool ub = !okT;
+    for (int i = tid; i < L; i += PF_THREADS) oE[i] = 0.0;  // own indices only: no barrier needed for the accumulator
     if (okT) {
+        // first half of the table only (T + 1 values, behind the accumulator in the sample region): the window is symmetric,
+        // hann[j] and hann[2 T - j] differ by an ulp of the cosine at most (1e-16 of a contribution)
+        double* hsm = oE + L;
+        for (int j = tid; j <= T; j += PF_THREADS) hsm[j] = __ldg(hs + j);
+        __syncthreads();
+        const double dT = (double)T;
         for (int m = 0; m < nSt; ++m) {
-            const int fl = gFl[m];
-            if (fl & 8) ub = true;
-            if (!(fl & 1)) continue;
-            const bool first = (fl & 2) != 0, last = (fl & 4) != 0, inner = !first && !last;
-            const int clAn = gCl[m], eValid = gEv[m], startIdx = gI0[m], stopIdx = gI1[m];
+            if (!(gFl[m] & 1)) continue;
+            const int eb = gEb[m], jl = gJl[m], w0 = gW0[m], w1 = gW1[m], startIdx = gI0[m], stopIdx = gI1[m];
+            // first own index >= startIdx
+            int i = startIdx + ((tid - startIdx) & (PF_THREADS - 1));
+            // interp() (PitchProcess.cpp:842-870): lower_bound j over x[j] = stMark + (j - T) / beta, then linear interpolation
+            // between grain samples j-1 and j. In grain coordinates tg = T + (i - stMark) beta the bound is j = ceil(tg) and the
+            // weight (i - x[j-1]) / (x[j] - x[j-1]) = tg - (j - 1). The interpolant is continuous in tg, so a lower_bound that
+            // differs from the reference's when tg is within rounding of an integer changes the value by O(1e-13) only.
             const double dSt = (double)gSt[m];
-            const int eBase = clAn - T + tauMax;  // e index of grain sample j = 0
-            const int jLim = min(eLen - eBase, eValid - (clAn - T));  // grain samples j < jLim exist in the residual so far
-            // thread <-> output index i is fixed (i mod PF_THREADS) so that successive grains
-            // accumulate into oE[i] in mark order without synchronisation
-            for (int i = (startIdx / PF_THREADS) * PF_THREADS + tid; i < stopIdx; i += PF_THREADS) {
-                if (i < startIdx) continue;
-                const double di = (double)i;
-                // interp() (PitchProcess.cpp:842-870): lower_bound j over x[j] = stMark + (j - T) / beta, then linear
-                // interpolation between grain samples j-1 and j. In grain coordinates tg = T + (i - stMark) beta the
-                // bound is j = ceil(tg) and the weight (i - x[j-1]) / (x[j] - x[j-1]) = tg - (j - 1). The interpolant
-                // is continuous in tg, so a lower_bound that differs from the reference's when tg is within rounding of
-                // an integer changes the value by O(1e-13) only.
-                const double tg = fma(di - dSt, beta, (double)T);
+            for (; i < stopIdx; i += PF_THREADS) {
+                const double tg = fma((double)i - dSt, beta, dT);
                 int j = (int)ceil(tg);
                 j = max(0, min(j, 2 * T));
-                const int ej = eBase + j;
-                double y1 = (ej >= 0 && j < jLim) ? e[ej] : 0.0;
-                if (inner || (first ? (j >= T) : (j < T))) y1 *= __ldg(hs + j);
+                const int ej = eb + j;
+                double y1 = (ej >= 0 && j < jl) ? e[ej] : 0.0;
+                if (j >= w0 && j < w1) y1 *= hsm[min(j, 2 * T - j)];
                 double val = y1;
                 if (j > 0) {
-                    double y0 = (ej >= 1 && j - 1 < jLim) ? e[ej - 1] : 0.0;
-                    if (inner || (first ? (j - 1 >= T) : (j - 1 < T))) y0 *= __ldg(hs + j - 1);
+                    double y0 = (ej >= 1 && j - 1 < jl) ? e[ej - 1] : 0.0;
+                    if (j - 1 >= w0 && j - 1 < w1) y0 *= hsm[min(j - 1, 2 * T - j + 1)];
                     val = fma(y1 - y0, tg - (double)(j - 1), y0);
                 }
                 oE[i] += val;
             }
         }
+        if (sUb) ub = true;
     }
     float* dst = outE + fidx * (size_t)L;
     for (int i = tid; i < L; i += PF_THREADS) dst[i] = (float)oE[i];  // own indices again
@@ -1429,17 +1447,18 @@ void vp_launch_pitch_lpc(cudaStream_t st, const VPGeom& g, int S, const float* v
 void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S, const float* voice,
                            vp_pitch_frame* frames, const double* aP, float* outE) {
     const int eLen = g.tauMax + g.L + 3 * g.c;
+    const int eAlloc = std::min(eLen, g.L + 2 * g.tauMax + 2);
     int xLen = g.tauMax + g.ordP + g.L + 3 * g.c;  // frame-relative [-tauMax - ord, L + 3c)
-    xLen = std::max(xLen, 2 * g.L);                // the region is reused as outE [L] doubles
+    xLen = std::max(xLen, 2 * g.L + 2 * (g.tauMax + 1));  // the region is reused as outE [L] doubles + half a Hann table [tauMax] doubles
     xLen = (xLen + 3) & ~3;
-    const size_t smem = (size_t)((eLen + PF_XPAD + 1) & ~1) * sizeof(double) + (size_t)(xLen + PF_XPAD + 4) * sizeof(float) + 16;
+    const size_t smem = (size_t)((eAlloc + PF_XPAD + 1) & ~1) * sizeof(double) + (size_t)(xLen + PF_XPAD + 4) * sizeof(float) + 16;
     dim3 grid(g.nFramesP + VP_PC, S);
     if (g.ordP == 15) {
         cudaFuncSetAttribute(k_pitch_psola<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        VP_LAUNCH(k_pitch_psola<15><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen));
+        VP_LAUNCH(k_pitch_psola<15><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen, eAlloc));
     } else {
         cudaFuncSetAttribute(k_pitch_psola<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        VP_LAUNCH(k_pitch_psola<0><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen));
+        VP_LAUNCH(k_pitch_psola<0><<<grid, PF_THREADS, smem, st>>>(g, tb, voice, frames, aP, outE, xLen, eLen, eAlloc));
     }
 }
 
