@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    extra = os.environ.get("VP_NVCC_EXTRA", "").split()  # developer A/B builds (e.g. -DAV_STAGE_UNROLL=6)
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

@@ -203,6 +203,10 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 // ---------------------------------------------------------------------------
 #define AV_WARPS 10  // 10 x 10.3 KB + window: two CTAs per SM = 20 warps (registers capped at 102 by the launch bounds)
 #define AV_BATCH 32  // consecutive frames per warp (cache locality of the 4x overlapping frame reads)
+#ifndef AV_STAGE_UNROLL
+#define AV_STAGE_UNROLL 6  // measured: 6 -> 149.6 ms, 9 -> 155.0, 18 -> 180.9 (autocorrelation stage of the default workload, marks alongside)
+#endif
+constexpr int kStageUnroll = AV_STAGE_UNROLL;
 
 // A warp walks AV_BATCH consecutive frames of one stream and builds each frame's windowed FP64 copies straight from global
 // memory (a sample is read by the 4 frames that overlap it, back to back by the same warp: L1 / L2 hits). An earlier
@@ -251,7 +255,8 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
             if (t0 >= 0 && t0 + wlen <= g.n) {
                 const float* pv = v.x + t0;
                 const float* ps = y.x + t0;
-#pragma unroll 6
+                // all of a batch's loads are issued before its first use: AV_STAGE_UNROLL iterations = 2 x that many loads in flight
+#pragma unroll kStageUnroll
                 for (int j = lane; j < wlen; j += 32) {
                     const double w = wv[j];
                     xw[j] = (double)__ldg(pv + j) * w;
