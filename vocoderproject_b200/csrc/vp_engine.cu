@@ -64,6 +64,7 @@ struct vp_engine {
     std::vector<int> evSideStage;
     size_t evSideUsed = 0;
     bool overlapMarks = true;
+    bool forkEarly = false;   // VP_OVERLAP=y (developer A/B): fork the mark chain before the autocorrelation instead of after it
     std::string err;
     vp_params prm;
     vp_sizes sz;
@@ -354,7 +355,7 @@ extern "C" int vp_engine_create(vp_engine** out, int device) {
         cudaEventCreateWithFlags(&e->evSideDone[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->evMix[i], cudaEventDisableTiming);
     }
-    { const char* ov = getenv("VP_OVERLAP"); e->overlapMarks = !(ov && ov[0] == '0'); }
+    { const char* ov = getenv("VP_OVERLAP"); e->overlapMarks = !(ov && ov[0] == '0'); e->forkEarly = ov && ov[0] == 'y'; }
     { const char* yp = getenv("VP_YIN_PHASES"); e->yinTwoPhase = !(yp && yp[0] == '1'); }
     const char* pt = getenv("VP_STAGE_TIMING");
     e->stageTiming = pt && pt[0] == '1';
@@ -681,7 +682,8 @@ static int make_geom(vp_engine* e, int nBlocks, size_t stride, VPGeom* g) {
 // One pass = Sc' <= Sc streams whose I/O rows start at the given pointers; streamBase = index of the pass's first stream in
 // the engine's batch (selects its carried state). Phases:
 //   A (main)  gate, YIN correlation + decision + FP64 re-decision                       -> evYin
-//   S (side)  pitch-mark chain (sequential per stream: one warp per stream)             -> evSideDone   (needs evYin)
+//   S (side)  pitch-mark chain (sequential per stream: one warp per stream)             -> evSideDone   (needs evYin, re-recorded
+//             behind the autocorrelation: the chain runs next to the Levinson and synthesis kernels)
 //   V (main)  vocoder: autocorrelation | Levinson, gain, synthesis (S is forked between the two parts)
 //   P (main)  pitch LPC, PSOLA, all-pole resynthesis + overlap-add                      (needs evSideDone)
 //   M (main)  mix + egress, carried state, decisions kept for the getters
@@ -953,9 +955,15 @@ static int run_pass(vp_engine* e, const VPGeom& gIO, int Sp, int streamBase, con
     // enough to hide it), and the autocorrelation -- the step's largest kernel, the one the roofline line is about -- is
     // timed without a co-runner. The step time is the same wherever the chain overlaps (it costs its ~25 ms of issue slots).
     if ((rc = pass_A(e, c))) return rc;
-    if ((rc = pass_V(e, c, 1))) return rc;
-    if ((rc = pass_S(e, c))) return rc;
-    if ((rc = pass_V(e, c, 2))) return rc;
+    if (e->forkEarly) {  // developer A/B (VP_OVERLAP=y): chain forked right after YIN, next to the autocorrelation
+        if ((rc = pass_S(e, c))) return rc;
+        if ((rc = pass_V(e, c, 0))) return rc;
+    } else {
+        if ((rc = pass_V(e, c, 1))) return rc;
+        VP_CUDA_OK(cudaEventRecord(e->evYin[c.slot], e->st));  // the fork point of phase S: now behind the autocorrelation
+        if ((rc = pass_S(e, c))) return rc;
+        if ((rc = pass_V(e, c, 2))) return rc;
+    }
     if ((rc = pass_P(e, c))) return rc;
     return pass_M(e, c);
 }

@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
                 }
 #pragma unroll
                 for (int u = 0; u < YC_R; ++u) {  // tail: fewer than YC_R samples left
-                    const float a = (n + u < c) ? xa[n + u] : 0.0f;
+                    if (n + u >= c) break;        // warp-uniform
+                    const float a = xa[n + u];
 #pragma unroll
                     for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a, W[(u + r) % YC_R], acc[r]);
                     W[u % YC_R] = xw[n + u + YC_R];

@@ -122,11 +122,13 @@ __device__ __forceinline__ void ac_task(const double* __restrict__ xw, int n0, i
         W[(R - 1) % R] = pw[R];  // element for u = 0 of the next round
     }
     const int rem = segLen - full * R;
-    if (rem > 0) {  // last, partial round (the window reads beyond it stay inside the zero padding)
+    if (rem > 0) {  // last, partial round: `rem` steps (a 10 ms frame is 4 full rounds + 6 steps per segment; running the
+                    // round out with a = 0 would be 11 % of the kernel's DFMAs). The window reads stay inside the zero padding.
 #pragma unroll
         for (int u = 0; u < R; ++u) {
+            if (u >= rem) break;  // warp-uniform
             if (u > 0) W[(u + R - 1) % R] = pw[u];
-            const double a = (u < rem) ? p[u] : 0.0;
+            const double a = p[u];
 #pragma unroll
             for (int j = 0; j < R; ++j) acc[j] = fma(a, W[(u + j) % R], acc[j]);
         }
@@ -201,12 +203,20 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 // runs lane = (segment of 8) x (lag group of 4: voice lags 0-13, 14-27, 28-41, side-chain lags 0-13) with the same
 // register-window task as above. Only warp-level synchronisation.
 // ---------------------------------------------------------------------------
+#ifndef AV_WARPS
 #define AV_WARPS 10  // 10 x 10.3 KB + window: two CTAs per SM = 20 warps (registers capped at 102 by the launch bounds)
+#endif
 #define AV_BATCH 32  // consecutive frames per warp (cache locality of the 4x overlapping frame reads)
 #ifndef AV_STAGE_UNROLL
-#define AV_STAGE_UNROLL 6  // measured: 6 -> 149.6 ms, 9 -> 155.0, 18 -> 180.9 (autocorrelation stage of the default workload, marks alongside)
+#define AV_STAGE_UNROLL 15  // raw samples per signal and lane loaded at once (15 x 32 = a 10 ms frame at 48 kHz); predicated, no remainder loop
 #endif
 constexpr int kStageUnroll = AV_STAGE_UNROLL;
+#ifndef AV_PREFETCH
+#define AV_PREFETCH 0  // 1: the loads of frame k + 1 are issued before the lag sums of frame k (registers held across them).
+                       // Measured [B200], default workload, autocorrelation timed alone: 0 -> 128.2 ms; 1 with 8 / 10 / 12 / 15
+                       // loads ahead -> 128.2 / 132.0 / 131.3 / 142.6 (spills): the load latency is already covered by the
+                       // other 19 warps of the SM, so the default keeps the simple form.
+#endif
 
 // A warp walks AV_BATCH consecutive frames of one stream and builds each frame's windowed FP64 copies straight from global
 // memory (a sample is read by the 4 frames that overlap it, back to back by the same warp: L1 / L2 hits). An earlier
@@ -244,33 +254,67 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
     const double* sig = isSynth ? sw : xw;
     const int m0 = (grp == 2) ? AC_R : (grp == 3) ? 2 * AC_R - 1 : 0;
     const int order = isSynth ? g.ordS : g.ordV;
+    // The raw samples of a frame are loaded into registers in one go (kStageUnroll loads per signal and lane = 32 kStageUnroll
+    // samples: whole frames up to 48 kHz, the head of longer ones; predicated, so 44.1 kHz frames of 441 samples take the same
+    // path), then windowed into the FP64 copies. Round 2 measured 6 loads at a time + remainder loop at 149.6 ms, this form at
+    // 140.5 ms (mark chain alongside in both). AV_PREFETCH = 1 issues them one frame ahead instead (no gain, see above).
+    float rv[kStageUnroll], rs[kStageUnroll];
+    auto frame_src = [&](int k, const float*& pv, const float*& ps) -> bool {
+        const long long t0 = (long long)k * hop + g.offV - g.lat;
+        pv = v.x + t0; ps = y.x + t0;
+        return k < g.nFramesV && t0 >= 0 && t0 + wlen <= g.n;   // the frame lies inside this call's input (else: history / zeros, slow path)
+    };
+    auto prefetch = [&](const float* pv, const float* ps) {
+#pragma unroll
+        for (int i = 0; i < kStageUnroll; ++i) {
+            const int j = lane + 32 * i;
+            rv[i] = (j < wlen) ? __ldg(pv + j) : 0.0f;
+            rs[i] = (j < wlen) ? __ldg(ps + j) : 0.0f;
+        }
+    };
+    const float *pv = nullptr, *ps = nullptr;
+    bool pre = false;
+#if AV_PREFETCH
+    pre = frame_src(k0, pv, ps);
+    if (pre) prefetch(pv, ps);
+#endif
     for (int fb = 0; fb < AV_BATCH; ++fb) {
         const int k = k0 + fb;
         if (k >= g.nFramesV) break;
         const long long u0 = (long long)k * hop + g.offV;
         __syncwarp();
-        // ---- windowed FP64 copies straight from global memory (L1 / L2: a sample is read by 4 consecutive frames)
-        {
-            const long long t0 = u0 - g.lat;
-            if (t0 >= 0 && t0 + wlen <= g.n) {
-                const float* pv = v.x + t0;
-                const float* ps = y.x + t0;
-                // all of a batch's loads are issued before its first use: AV_STAGE_UNROLL iterations = 2 x that many loads in flight
-#pragma unroll kStageUnroll
-                for (int j = lane; j < wlen; j += 32) {
+#if !AV_PREFETCH
+        pre = frame_src(k, pv, ps);
+        if (pre) prefetch(pv, ps);
+#endif
+        // ---- windowed FP64 copies of this frame
+        if (pre) {
+#pragma unroll
+            for (int i = 0; i < kStageUnroll; ++i) {
+                const int j = lane + 32 * i;
+                if (j < wlen) {
                     const double w = wv[j];
-                    xw[j] = (double)__ldg(pv + j) * w;
-                    sw[j] = (double)__ldg(ps + j) * w;
+                    xw[j] = (double)rv[i] * w;
+                    sw[j] = (double)rs[i] * w;
                 }
-            } else {
-                for (int j = lane; j < wlen; j += 32) {
-                    const double w = wv[j];
-                    xw[j] = (double)vp_x(v, u0 + j, g) * w;
-                    sw[j] = (double)vp_x(y, u0 + j, g) * w;
-                }
+            }
+            for (int j = lane + 32 * kStageUnroll; j < wlen; j += 32) {  // frames longer than the prefetch (above 48 kHz)
+                const double w = wv[j];
+                xw[j] = (double)__ldg(pv + j) * w;
+                sw[j] = (double)__ldg(ps + j) * w;
+            }
+        } else {
+            for (int j = lane; j < wlen; j += 32) {
+                const double w = wv[j];
+                xw[j] = (double)vp_x(v, u0 + j, g) * w;
+                sw[j] = (double)vp_x(y, u0 + j, g) * w;
             }
         }
         __syncwarp();
+#if AV_PREFETCH
+        pre = (fb + 1 < AV_BATCH) && frame_src(k + 1, pv, ps);
+        if (pre) prefetch(pv, ps);
+#endif
         double acc[AC_R];
         ac_task<AC_R>(sig, seg * segLen, segLen, m0, acc);
 #pragma unroll
