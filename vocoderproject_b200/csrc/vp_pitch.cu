@@ -235,6 +235,9 @@ void vp_launch_yin_recheck(cudaStream_t st, const VPGeom& g, int S, const float*
 #define YC_LAGS (32 * YC_R)  // lags per warp pass
 #define YC_CH 8              // chunks (= warps) per CTA
 
+#ifndef YC_PAIR_A
+#define YC_PAIR_A 1       // 64-bit loads of the broadcast sample in k_yin_corr (0: one 32-bit load per step)
+#endif
 #define YC_SUB (4 * YC_R)    // first-level accumulation length (two-level FP32 summation: tighter error bound)
 
 // Persistent CTAs: each loops over tiles (one stream x YC_CH chunks) with the samples of the NEXT tile arriving through
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
     int cur = 0;
     issue(tileOf(wi), xsAll);
     const int half = lane >> 4, lg = lane & 15;
+    const bool pairA = YC_PAIR_A && (c & 1) == 0 && (subPad & 1) == 0 && (spanPad & 1) == 0;  // every warp's chunk starts on an even float
     for (; wi < nWork; wi += gridDim.x) {
         const long long tile = tileOf(wi);
         const long long next = wi + gridDim.x;
@@ -316,6 +320,24 @@ __global__ void __launch_bounds__(32 * YC_CH, 4) k_yin_corr(VPGeom g, const floa
                 int n = 0;
                 while (n + YC_R <= c) {
                     const int nSub = min(n + YC_SUB, c);
+                    // a shared-memory load holds the scheduler for ~3 issue cycles next to FFMAs (tools/ubench_yin.cu: 22.6
+                    // cycles per 15 FFMA + 2 LDS step, 19.9 with the broadcast sample fetched for two steps at once): rounds
+                    // of 2 YC_R steps with 64-bit `a` loads while the chunk length keeps them aligned (n stays even: a single
+                    // YC_R round can only close the last, partial group), same order of additions as single rounds
+                    if (pairA) {
+                        for (; n + 2 * YC_R <= nSub; n += 2 * YC_R) {
+#pragma unroll
+                            for (int u = 0; u < 2 * YC_R; u += 2) {
+                                const float2 a2 = *reinterpret_cast<const float2*>(xa + n + u);
+#pragma unroll
+                                for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a2.x, W[(u + r) % YC_R], acc[r]);
+                                W[u % YC_R] = xw[n + u + YC_R];
+#pragma unroll
+                                for (int r = 0; r < YC_R; ++r) acc[r] = fmaf(a2.y, W[(u + 1 + r) % YC_R], acc[r]);
+                                W[(u + 1) % YC_R] = xw[n + u + 1 + YC_R];
+                            }
+                        }
+                    }
                     for (; n + YC_R <= nSub; n += YC_R) {
 #pragma unroll
                         for (int u = 0; u < YC_R; ++u) {

@@ -196,6 +196,51 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
     }
 }
 
+// The same task with 128-bit shared loads: two `a` samples per load at even steps, two window elements per load at odd
+// steps (tools/ubench_mix.cu: a shared load next to DFMAs holds the scheduler ~3 cycles whatever its width, so 14 loads per
+// round of 14 steps instead of 28). Needs xw 16-byte aligned and n0, m0, segLen even; the additions are the same, in the same
+// order. A 128-bit load is served per quarter-warp (the 8 segments of one lag group): segment stride = 4 (mod 8) words puts
+// the 8 lanes on 8 disjoint groups of 4 banks.
+template <int R>
+__device__ __forceinline__ void ac_task4(const double* __restrict__ xw, int n0, int segLen, int m0, double* acc) {
+    static_assert(R % 2 == 0, "pairs of steps");
+    double W[R];
+#pragma unroll
+    for (int j = 0; j < R; j += 2) {
+        const double2 w2 = *reinterpret_cast<const double2*>(xw + n0 + m0 + j);
+        acc[j] = 0.0; acc[j + 1] = 0.0; W[j] = w2.x; W[j + 1] = w2.y;
+    }
+    const double* p = xw + n0;            // a = x[n]
+    const double* pw = p + m0 + R - 1;    // newest window element of step u: pw[u]
+    const int full = segLen / R;
+    for (int r = 0; r < full; ++r, p += R, pw += R) {
+#pragma unroll
+        for (int u = 0; u < R; u += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(p + u);
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = fma(a.x, W[(u + j) % R], acc[j]);
+            const double2 w2 = *reinterpret_cast<const double2*>(pw + u + 1);   // newest elements of steps u + 1 and u + 2
+            W[u % R] = w2.x;
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = fma(a.y, W[(u + 1 + j) % R], acc[j]);
+            W[(u + 1) % R] = w2.y;
+        }
+    }
+    const int rem = segLen - full * R;  // even; the last, partial round runs only its own steps
+#pragma unroll
+    for (int u = 0; u < R; u += 2) {
+        if (u >= rem) break;  // warp-uniform
+        const double2 a = *reinterpret_cast<const double2*>(p + u);
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = fma(a.x, W[(u + j) % R], acc[j]);
+        const double2 w2 = *reinterpret_cast<const double2*>(pw + u + 1);
+        W[u % R] = w2.x;
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = fma(a.y, W[(u + 1 + j) % R], acc[j]);
+        W[(u + 1) % R] = w2.y;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // v2 (default): one WARP per frame, warps stream over batches of AB consecutive frames of one stream. The raw samples
 // of a batch (span (AB-1) hop + wlen, shared by its frames) are loaded once, coalesced, as floats; each frame then
@@ -211,6 +256,9 @@ __global__ void __launch_bounds__(32 * 12) k_voc_autocorr(VPGeom g, VPTables tb,
 #define AV_STAGE_UNROLL 15  // raw samples per signal and lane loaded at once (15 x 32 = a 10 ms frame at 48 kHz); predicated, no remainder loop
 #endif
 constexpr int kStageUnroll = AV_STAGE_UNROLL;
+#ifndef AV_V4
+#define AV_V4 0  // 1: 128-bit shared loads in the lag sums (ac_task4, half the load instructions). Measured [B200]: 129.7 ms against 128.2 for the 64-bit form -- the loop is not bound by its load issue
+#endif
 #ifndef AV_PREFETCH
 #define AV_PREFETCH 0  // 1: the loads of frame k + 1 are issued before the lag sums of frame k (registers held across them).
                        // Measured [B200], default workload, autocorrelation timed alone: 0 -> 128.2 ms; 1 with 8 / 10 / 12 / 15
@@ -227,7 +275,8 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
                                                                  const float* __restrict__ synth, double* __restrict__ rV,
                                                                  double* __restrict__ rS, int segLen, int FS, int ringLen,
                                                                  int batchesPerStream, int S) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double smA[];
+    double* sm = smA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hop = g.hopV, wlen = g.wlenV;
     double* wv = sm;  // [wlen] analysis window, shared by the CTA
@@ -252,7 +301,11 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
     const int seg = lane & (AC_SEGS - 1), grp = lane >> 3;
     const bool isSynth = grp == 1;
     const double* sig = isSynth ? sw : xw;
+#if AV_V4
+    const int m0 = (grp == 2) ? AC_R : (grp == 3) ? 2 * AC_R : 0;        // even offsets: 128-bit window loads (ac_task4)
+#else
     const int m0 = (grp == 2) ? AC_R : (grp == 3) ? 2 * AC_R - 1 : 0;
+#endif
     const int order = isSynth ? g.ordS : g.ordV;
     // The raw samples of a frame are loaded into registers in one go (kStageUnroll loads per signal and lane = 32 kStageUnroll
     // samples: whole frames up to 48 kHz, the head of longer ones; predicated, so 44.1 kHz frames of 441 samples take the same
@@ -316,7 +369,11 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
         if (pre) prefetch(pv, ps);
 #endif
         double acc[AC_R];
+#if AV_V4
+        ac_task4<AC_R>(sig, seg * segLen, segLen, m0, acc);
+#else
         ac_task<AC_R>(sig, seg * segLen, segLen, m0, acc);
+#endif
 #pragma unroll
         for (int j = 0; j < AC_R; ++j) {
             double a = acc[j];
@@ -354,7 +411,11 @@ void vp_launch_voc_autocorr(cudaStream_t st, const VPGeom& g, const VPTables& tb
     // (the streaming form always runs its three voice lag groups, whatever the order: pad for lag offsets up to 27 + 2 R)
     int FSv = AC_SEGS * segLen + 3 * AC_R + 2 * AC_R + 2;
     if (FSv < FS) FSv = FS;
+#if AV_V4
+    const int FS2 = (FSv + 1) & ~1;            // even: the voice and the side-chain copy both 16-byte aligned (ac_task4)
+#else
     const int FS2 = (FSv + 15) / 16 * 16 + 1;  // odd distance between the voice and the side-chain copy (see k_voc_autocorr2)
+#endif
     const int ringLen = 0;   // (no raw-sample ring any more: see k_voc_autocorr2)
     const size_t smem2 = ((size_t)((g.wlenV + 1) & ~1) + (size_t)AV_WARPS * (2 * FS2 + ringLen)) * sizeof(double);
     // the streaming form needs its seven warps' windows + rings in shared memory (fits up to 88.2 kHz frames)
