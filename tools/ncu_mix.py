@@ -60,7 +60,7 @@ def parse(path, samples):
         if (r[iid], r[ik]) not in seen:
             seen.add((r[iid], r[ik]))
             launches[r[ik].split("(")[0]] += 1
-    passes = max(launches.get("k_mix", 1), 1)
+    passes = max(sum(n for k, n in launches.items() if stage_of(k) == "mix"), 1)  # one mix kernel (k_mix / k_mix4<..>) per pass
     out = collections.OrderedDict()
     for st, d in stages.items():
         per = {k: v / passes / float(samples) for k, v in d.items()}

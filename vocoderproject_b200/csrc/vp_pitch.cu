@@ -1079,6 +1079,9 @@ void vp_launch_marks(cudaStream_t st, const VPGeom& g, const VPTables& tb, int S
 #define PA_WARPS 4
 #define PA_SEGS 16
 #define PA_R 8
+#ifndef PA_LOADS
+#define PA_LOADS 18  // frame loads in flight per lane in k_pitch_autocorr (measured: 8 -> 17.0 ms, 12 -> 15.3, 18 -> 14.9 for the LPC stage)
+#endif
 
 // Frame slots of the pitch synthesis kernels: slot index = f + VP_PC; f < 0 are the last frames of earlier calls (their
 // records are carried): the reference adds a chunk's samples into the output ring when the chunk is handled, also
@@ -1116,8 +1119,15 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
         const long long t0 = p - g.lat;
         if (t0 >= 0 && t0 + L <= g.n) {
             const float* src = v.x + t0;
-#pragma unroll 8
-            for (int j = lane; j < L; j += 32) xd[j] = (double)__ldg(src + j);
+            // batches of PA_LOADS predicated loads per lane, all issued before the first conversion, no remainder loop (the
+            // kernel waits on these loads more than on anything else: a 1112-sample frame is 3 round trips instead of 4 + 3)
+            for (int j0 = lane; j0 < L; j0 += 32 * PA_LOADS) {
+                float t[PA_LOADS];
+#pragma unroll
+                for (int i = 0; i < PA_LOADS; ++i) t[i] = (j0 + 32 * i < L) ? __ldg(src + j0 + 32 * i) : 0.0f;
+#pragma unroll
+                for (int i = 0; i < PA_LOADS; ++i) if (j0 + 32 * i < L) xd[j0 + 32 * i] = (double)t[i];
+            }
         } else {
             for (int j = lane; j < L; j += 32) xd[j] = (double)vp_x(v, p + j, g);
         }
@@ -1146,7 +1156,8 @@ __global__ void __launch_bounds__(32 * PA_WARPS) k_pitch_autocorr(VPGeom g, cons
         if (rem > 0) {
 #pragma unroll
             for (int u = 0; u < PA_R; ++u) {
-                const double a = (u < rem) ? pa[u] : 0.0;
+                if (u >= rem) break;  // warp-uniform
+                const double a = pa[u];
 #pragma unroll
                 for (int j = 0; j < PA_R; ++j) acc[j] = fma(a, W[(u + j) % PA_R], acc[j]);
                 W[u % PA_R] = pw[u];
@@ -1496,13 +1507,19 @@ void vp_launch_pitch_psola(cudaStream_t st, const VPGeom& g, const VPTables& tb,
 // atomics on a zeroed buffer).
 // ===========================================================================
 #define PI_WARPS 2
+#define PI_ROW 36  // floats per tile row: 32 samples + 4 spare (16-byte aligned rows, conflict-free 128-bit accesses)
 
 template <int P>
 __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTables tb, const vp_pitch_frame* __restrict__ frames,
                                                              const double* __restrict__ aP, const float* __restrict__ outE,
                                                              float* __restrict__ outP, long long nFramesTot) {
-    __shared__ float tin[PI_WARPS][2][32][33];
-    __shared__ float tout[PI_WARPS][32][33];
+    // Rows of 36 floats: 16-byte aligned (128-bit copies in, 128-bit reads / writes by the filter thread: a quarter-warp's 8
+    // rows start 4 banks apart), and the 4 spare floats of a tout row carry that frame's output range and position for the
+    // row-wise write-out. A shared-memory or shuffle instruction costs the scheduler ~3 cycles next to FP64 work
+    // (tools/ubench_mix.cu), so the slab moves count: per sample and lane this form issues 4.5 of them, the round-1 form
+    // (4-byte copies, 4 shuffles per output row) 10.
+    __shared__ __align__(16) float tin[PI_WARPS][2][32][PI_ROW];
+    __shared__ __align__(16) float tout[PI_WARPS][32][PI_ROW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long f0 = ((long long)blockIdx.x * PI_WARPS + warp) * 32;
     if (f0 >= nFramesTot) return;
@@ -1527,26 +1544,37 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
         const double* ap = aP + (size_t)fidx * (order + 1);
         for (int k = 0; k <= order; ++k) a[k] = ap[k];
     }
-    // per-lane metadata shared through shuffles for the cooperative slab moves
+    // frame-relative output range that lands inside this call (positions before 0 went out with an earlier call, beyond n go
+    // out with a later one) and the frame's offset in the output plane relative to the warp's first stream: lane fr's values
+    // go into the spare floats of tout row fr
     const long long myP = vp_ppos(g, f);
-    // frame-relative output range that lands inside this call: positions before 0 went out with an earlier call, beyond
-    // n go out with a later one; and the frame's base offset in the output plane
-    const int myLo = (int)max(0LL, -myP), myHi = (int)min((long long)nSteps, (long long)g.n - myP);
-    const long long myBase = (long long)s * (long long)g.pstride + myP;
+    const int s0 = (int)(f0 / (g.nFramesP + VP_PC));
+    const long long planeBase = (long long)s0 * (long long)g.pstride;
+    {
+        int4 meta;
+        meta.x = (int)max(0LL, -myP);
+        meta.y = (int)min((long long)nSteps, (long long)g.n - myP);
+        meta.z = (int)((long long)(s - s0) * (long long)g.pstride + myP);  // |.| < 2^31: checked by the launcher
+        meta.w = 0;
+        if (nSteps == 0) { meta.x = 0; meta.y = 0; meta.z = 0; }
+        *reinterpret_cast<int4*>(&tout[warp][lane][32]) = meta;
+    }
     const double gp = (double)g.gainPitchF;
     const int nSlabs = (L + 31) / 32;
     int maxSteps = nSteps;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xffffffffu, maxSteps, o));
-    // slab sl: row fr of the tile <- outE[frame f0+fr][32 sl .. 32 sl + 32), as asynchronous 4-byte copies (zero fill
-    // beyond the frame's steps) into one of two tiles: the next slab is in flight while this one is filtered
+    // slab sl: row fr of the tile <- outE[frame f0+fr][32 sl .. 32 sl + 32) as asynchronous 16-byte copies (rows of outE are
+    // L = 4 c floats: aligned; zero fill beyond the frame's steps) into one of two tiles: the next slab is in flight while
+    // this one is filtered
     auto issue = [&](int sl, int buf) {
         const int i0 = sl * 32;
-#pragma unroll 8
-        for (int fr = 0; fr < 32; ++fr) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int idx = it * 32 + lane, fr = idx >> 3, q4 = (idx & 7) * 4;
             const int steps = __shfl_sync(0xffffffffu, nSteps, fr);
-            const bool ok = i0 + lane < steps;
-            __pipeline_memcpy_async(&tin[warp][buf][fr][lane], outE + (ok ? (size_t)(f0 + fr) * L + i0 + lane : 0), 4, ok ? 0 : 4);
+            const int valid = min(max(steps - (i0 + q4), 0), 4);
+            __pipeline_memcpy_async(&tin[warp][buf][fr][q4], outE + (valid ? (size_t)(f0 + fr) * L + i0 + q4 : 0), 16, 16 - 4 * valid);
         }
         __pipeline_commit();
     };
@@ -1557,28 +1585,40 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
         if (sl + 1 < nSlabs && i0 + 32 < maxSteps) { issue(sl + 1, buf ^ 1); __pipeline_wait_prior(1); }
         else __pipeline_wait_prior(0);
         __syncwarp();
-        for (int j = 0; j < 32; ++j) {
-            const int i = i0 + j;
-            double acc = (double)tin[warp][buf][lane][j];
-            if (P > 0) {
-                // transposed direct form II: y = x + s_1; s_k <- s_{k+1} - a[k] y  (independent DFMAs, no history shift)
-                acc += h[0];
-#pragma unroll
-                for (int k = 0; k < PA; ++k) h[k] = fma(-a[k + 1], acc, h[k + 1]);
-            } else {
-                for (int k = 1; k <= order && k <= i; ++k) acc = fma(-a[k], h[(i - k) % order], acc);
-                h[i % order] = acc;
+#pragma unroll 2
+        for (int q4 = 0; q4 < 32; q4 += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(&tin[warp][buf][lane][q4]);
+            const float xin[4] = {x4.x, x4.y, x4.z, x4.w};
+            float yo[4];
+            double wv[4] = {0.0, 0.0, 0.0, 0.0};
+            if (i0 + q4 < L) {  // L is a multiple of 4: a group of 4 lies inside the synthesis window or beyond it
+                const double2 w01 = *reinterpret_cast<const double2*>(tb.stP + i0 + q4);
+                const double2 w23 = *reinterpret_cast<const double2*>(tb.stP + i0 + q4 + 2);
+                wv[0] = w01.x; wv[1] = w01.y; wv[2] = w23.x; wv[3] = w23.y;
             }
-            const double w = (i < L) ? tb.stP[i] : 0.0;
-            tout[warp][lane][j] = (float)(acc * w * gp);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int i = i0 + q4 + jj;
+                double acc = (double)xin[jj];
+                if (P > 0) {
+                    // transposed direct form II: y = x + s_1; s_k <- s_{k+1} - a[k] y  (independent DFMAs, no history shift)
+                    acc += h[0];
+#pragma unroll
+                    for (int k = 0; k < PA; ++k) h[k] = fma(-a[k + 1], acc, h[k + 1]);
+                } else {
+                    for (int k = 1; k <= order && k <= i; ++k) acc = fma(-a[k], h[(i - k) % order], acc);
+                    h[i % order] = acc;
+                }
+                yo[jj] = (float)(acc * wv[jj] * gp);
+            }
+            *reinterpret_cast<float4*>(&tout[warp][lane][q4]) = make_float4(yo[0], yo[1], yo[2], yo[3]);
         }
         __syncwarp();
         for (int fr = 0; fr < 32; ++fr) {
-            const int lo = __shfl_sync(0xffffffffu, myLo, fr), hi = __shfl_sync(0xffffffffu, myHi, fr);
-            const long long ob = __shfl_sync(0xffffffffu, myBase, fr);
+            const int4 meta = *reinterpret_cast<const int4*>(&tout[warp][fr][32]);  // {lo, hi, plane offset}: one broadcast load
             const int i = i0 + lane;
-            if (i >= lo && i < hi) {
-                float* o = outP + ob + i;
+            if (i >= meta.x && i < meta.y) {
+                float* o = outP + planeBase + meta.z + i;
                 const float val = tout[warp][fr][lane];
                 if (i < c || i >= 3 * c) atomicAdd(o, val);   // cross-fade chunks: two frames contribute
                 else *o = val;
@@ -1592,6 +1632,12 @@ void vp_launch_pitch_iir(cudaStream_t st, const VPGeom& g, const VPTables& tb, i
                          const double* aP, const float* outE, float* outP) {
     const long long tot = (long long)S * (g.nFramesP + VP_PC);
     const unsigned grid = (unsigned)((tot + 32 * PI_WARPS - 1) / (32 * PI_WARPS));
+    // a warp's 32 frame slots span at most 32 / (nFramesP + VP_PC) + 1 streams: their plane offsets relative to the first
+    // one are kept in 32 bits
+    if (((long long)(32 / (g.nFramesP + VP_PC)) + 2) * (long long)g.pstride >= (1LL << 31)) {
+        if (g_vpLaunchError == cudaSuccess) g_vpLaunchError = cudaErrorInvalidValue;
+        return;
+    }
     if (g.ordP == 15) VP_LAUNCH(k_pitch_iir<15><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot));
     else VP_LAUNCH(k_pitch_iir<0><<<grid, 32 * PI_WARPS, 0, st>>>(g, tb, frames, aP, outE, outP, tot));
 }

@@ -253,7 +253,7 @@ __device__ __forceinline__ void ac_task4(const double* __restrict__ xw, int n0, 
 #endif
 #define AV_BATCH 32  // consecutive frames per warp (cache locality of the 4x overlapping frame reads)
 #ifndef AV_STAGE_UNROLL
-#define AV_STAGE_UNROLL 15  // raw samples per signal and lane loaded at once (15 x 32 = a 10 ms frame at 48 kHz); predicated, no remainder loop
+#define AV_STAGE_UNROLL 9  // raw samples per signal and lane loaded at once, predicated batches (a 556-sample frame at 48 kHz = 2 x 9 x 32)
 #endif
 constexpr int kStageUnroll = AV_STAGE_UNROLL;
 #ifndef AV_V4
@@ -317,19 +317,30 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
         pv = v.x + t0; ps = y.x + t0;
         return k < g.nFramesV && t0 >= 0 && t0 + wlen <= g.n;   // the frame lies inside this call's input (else: history / zeros, slow path)
     };
-    auto prefetch = [&](const float* pv, const float* ps) {
+    auto prefetch = [&](const float* pv, const float* ps, int j0) {
 #pragma unroll
         for (int i = 0; i < kStageUnroll; ++i) {
-            const int j = lane + 32 * i;
+            const int j = j0 + lane + 32 * i;
             rv[i] = (j < wlen) ? __ldg(pv + j) : 0.0f;
             rs[i] = (j < wlen) ? __ldg(ps + j) : 0.0f;
+        }
+    };
+    auto convert = [&](int j0) {
+#pragma unroll
+        for (int i = 0; i < kStageUnroll; ++i) {
+            const int j = j0 + lane + 32 * i;
+            if (j < wlen) {
+                const double w = wv[j];
+                xw[j] = (double)rv[i] * w;
+                sw[j] = (double)rs[i] * w;
+            }
         }
     };
     const float *pv = nullptr, *ps = nullptr;
     bool pre = false;
 #if AV_PREFETCH
     pre = frame_src(k0, pv, ps);
-    if (pre) prefetch(pv, ps);
+    if (pre) prefetch(pv, ps, 0);
 #endif
     for (int fb = 0; fb < AV_BATCH; ++fb) {
         const int k = k0 + fb;
@@ -338,23 +349,14 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
         __syncwarp();
 #if !AV_PREFETCH
         pre = frame_src(k, pv, ps);
-        if (pre) prefetch(pv, ps);
+        if (pre) prefetch(pv, ps, 0);
 #endif
         // ---- windowed FP64 copies of this frame
         if (pre) {
-#pragma unroll
-            for (int i = 0; i < kStageUnroll; ++i) {
-                const int j = lane + 32 * i;
-                if (j < wlen) {
-                    const double w = wv[j];
-                    xw[j] = (double)rv[i] * w;
-                    sw[j] = (double)rs[i] * w;
-                }
-            }
-            for (int j = lane + 32 * kStageUnroll; j < wlen; j += 32) {  // frames longer than the prefetch (above 48 kHz)
-                const double w = wv[j];
-                xw[j] = (double)__ldg(pv + j) * w;
-                sw[j] = (double)__ldg(ps + j) * w;
+            convert(0);
+            for (int j0 = 32 * kStageUnroll; j0 < wlen; j0 += 32 * kStageUnroll) {  // further batches of a frame longer than one
+                prefetch(pv, ps, j0);
+                convert(j0);
             }
         } else {
             for (int j = lane; j < wlen; j += 32) {
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
         __syncwarp();
 #if AV_PREFETCH
         pre = (fb + 1 < AV_BATCH) && frame_src(k + 1, pv, ps);
-        if (pre) prefetch(pv, ps);
+        if (pre) prefetch(pv, ps, 0);
 #endif
         double acc[AC_R];
 #if AV_V4
