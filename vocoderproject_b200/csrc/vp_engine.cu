@@ -807,17 +807,19 @@ static int pass_S(vp_engine* e, PassCtx& c) {
         vp_launch_marks_silence(q, e->cMarks + sb, Sp);
         e->launches++;
     }
-    if (g.pitchMix) {
-        if (side) side_mark(e, ST_CLEAR);
-        vp_launch_carry_in(q, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
-        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), q));
-        mark(ST_CLEAR);
-    }
+    // (the chain first: it is the long, latency-bound part of this phase and starts the moment the fork allows; the carried
+    // records occupy the rows in front of the ones it writes, and the cleared plane is only needed by phase P)
     if (g.pitchOn && g.nFramesP > 0) {
         if (side) side_mark(e, ST_MARKS);
         vp_launch_marks(q, g, c.tb, Sp, c.voice, e->dGate, e->dPeriod, e->dYFlags, e->dFrames, e->cMarks + sb);
         mark(ST_MARKS);
         e->launches++;
+    }
+    if (g.pitchMix) {
+        if (side) side_mark(e, ST_CLEAR);
+        vp_launch_carry_in(q, e->dFrames, e->cFrames + sb * VP_PC, Sp, (int)sizeof(vp_pitch_frame), (int)sizeof(vp_pitch_frame), VP_PC, rowsP);
+        VP_CUDA_OK(cudaMemsetAsync(e->dOutP, 0, (size_t)Sp * g.wstride * sizeof(float), q));
+        mark(ST_CLEAR);
     }
     if (side) {
         VP_CUDA_OK(cudaEventRecord(e->evMarks[c.slot], q));
