@@ -1260,8 +1260,6 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     const int f = (int)blockIdx.x - VP_PC, s = blockIdx.y;  // f = -1: the previous call's last frame
     const size_t fidx = vp_prow(g, s, f);
     vp_pitch_frame* rec = frames + fidx;
-    const unsigned flags = rec->flags;
-    if (!pf_live(g, rec, f)) return;
     const int L = g.L, c = g.c, ord = (P > 0) ? P : g.ordP, tauMax = g.tauMax;
     const int X0 = tauMax + ord;        // xf[X0 + idx] = voice at frame-relative idx, idx in [-tauMax - ord, L + 3c)
     double* e = smd;  // [eLen + pad] residual, e[j] <-> frame-relative idx j - tauMax (16-byte aligned: the shared-memory window is)
@@ -1270,6 +1268,7 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     float* xfBase = (float*)(e + ((eAlloc + PF_XPAD + 1) & ~1));  // 16-byte aligned; [xLen + pad] floats; dead after the residual -> oE [L] doubles + Hann table
     double* oE = (double*)xfBase;
     __shared__ int sAn[VP_MAX_MARKS + 1], sSt[VP_MAX_MARKS];
+    __shared__ __align__(16) double sAr[(P > 0 ? P : 1) + 1];  // the frame's LPC row (P > 0), staged with the samples
     const VPRow v = vp_row(voice, g.histV, s, g);
     const long long p = vp_ppos(g, f);
     const int chunkLim = vp_plim(g, f);
@@ -1278,6 +1277,9 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     // ---- frame samples global -> shared without a register round trip. Common case (the whole span lies inside this
     // call's input): 16-byte copies from the 16-byte aligned address at or below the first sample, the frame then starts
     // m floats into the buffer. Otherwise (history before the call / end of the input): 4-byte copies with zero fill.
+    // Issued before the frame's record is looked at: the copies, the record and the marks are then ONE round trip to memory
+    // instead of three in a row (the ncu source view had 30 % of this kernel's stall samples on those dependent loads); a
+    // frame without marks waits for its copies and leaves.
     const long long t0 = p - X0 - g.lat;
     int m = (int)((reinterpret_cast<uintptr_t>(v.x + t0) >> 2) & 3);
     if (t0 - m >= 0 && t0 + xLen + 4 <= g.n) {
@@ -1295,15 +1297,19 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
         }
     }
     const float* xf = xfBase + m;  // the PF_XPAD floats after xf[xLen - 1] only feed residual samples nobody reads
+    const double* ap = aP + fidx * (size_t)(ord + 1);
+    if (P > 0 && tid < (P + 1) / 2) __pipeline_memcpy_async(sAr + 2 * tid, ap + 2 * tid, 16);  // rows of P + 1 = 16 doubles: 16-byte aligned
+    __pipeline_commit();
+    const unsigned flags = rec->flags;
+    const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
+    const double beta = rec->beta;
     if (tid < VP_MAX_MARKS) { sAn[tid] = rec->anMarks[tid]; sSt[tid] = rec->stMarks[tid]; }
+    if (!pf_live(g, rec, f)) { __pipeline_wait_prior(0); return; }
     __shared__ int sELo, sEHi, sUb;
     if (tid == 0) { sAn[VP_MAX_MARKS] = 0; sELo = eLen; sEHi = 0; sUb = 0; }
-    const double* ap = aP + fidx * (size_t)(ord + 1);
-    const int T = rec->periodPsola, nSt = rec->nSt, nAn = rec->nAn, nAnOv = rec->nAnOv;
     // Hann table of this frame's period (PitchProcess.cpp:878-882): read in place (one table per period, shared by every
     // frame with that period: cache resident) -- a private shared copy would cost a CTA slot per SM
     const double* __restrict__ hs = tb.hann + ((T > 0 && T < tauMax) ? tb.hannOff[T] : 0);
-    __pipeline_commit();
     __syncthreads();  // marks visible; the staging copies are still in flight under the grain table
     // ---- PSOLA (PitchProcess.cpp:665-741, :788-870). Grain table first: thread m prepares synthesis mark m -- the
     // chunk n at which the reference handles it (the first n with stMark - T < (n + 1) c), the look-ahead and residual
@@ -1314,7 +1320,6 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
     // an inner mark, the second half for the first mark, the first half for the last: PitchProcess.cpp:697-731)
     __shared__ int gSt[VP_MAX_MARKS], gI0[VP_MAX_MARKS], gI1[VP_MAX_MARKS], gFl[VP_MAX_MARKS], gEb[VP_MAX_MARKS], gJl[VP_MAX_MARKS],
         gW0[VP_MAX_MARKS], gW1[VP_MAX_MARKS];
-    const double beta = rec->beta;
     const bool okT = T > 0 && T < tauMax;
     if (tid < VP_MAX_MARKS) {
         int fl = 0;  // 1 = process, 2 = first mark, 4 = last mark, 8 = UB in the reference
@@ -1388,7 +1393,7 @@ __global__ void __launch_bounds__(PF_THREADS, 7) k_pitch_psola(VPGeom g, VPTable
         constexpr int PP = (P > 0) ? P : 1;
         double ar[PP + 1];
 #pragma unroll
-        for (int k = 0; k <= PP; ++k) ar[k] = ap[k];
+        for (int k = 0; k <= PP; ++k) ar[k] = sAr[k];
         // Scatter form: every input sample is loaded and converted once and feeds the (up to PP + 1) outputs of this
         // thread it belongs to -- PF_RJ accumulators instead of a PF_RJ + PP window in registers, no bounds predicates
         // (xf and e are padded). Inputs run newest to oldest so that each output still sums its taps k = 0 .. PP in order.
