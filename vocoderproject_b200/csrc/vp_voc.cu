@@ -534,16 +534,9 @@ __device__ __forceinline__ double lev_energy_static(const double* __restrict__ r
         a[1] = r[1] / r[0];
 #pragma unroll
         for (int p = 2; p <= P; ++p) {
-            // the two dot products as two partial sums each (odd / even i): four independent DFMA chains instead of two. The
-            // thread is alone with its recursion (226 registers: 2 warps per scheduler), and a chain of p dependent DFMAs
-            // per order is what the kernel waited on (ncu: stall "wait" 2.4 of 2.9 warps)
-            double rho = 0.0, ra = 0.0, rho1 = 0.0, ra1 = 0.0;
+            double rho = 0.0, ra = 0.0;
 #pragma unroll
-            for (int i = 1; i < p; ++i) {
-                if (i & 1) { rho = fma(r[p - i], a[i], rho); ra = fma(r[i], a[i], ra); }
-                else { rho1 = fma(r[p - i], a[i], rho1); ra1 = fma(r[i], a[i], ra1); }
-            }
-            rho += rho1; ra += ra1;
+            for (int i = 1; i < p; ++i) { rho = fma(r[p - i], a[i], rho); ra = fma(r[i], a[i], ra); }
             const double k = (r[p] - rho) / (r[0] - ra);
 #pragma unroll
             for (int i = 1; 2 * i <= p; ++i) {
