@@ -499,15 +499,20 @@ __global__ void __launch_bounds__(32 * YD_WARPS) k_yin_decide(VPGeom g, const fl
     }
 }
 
+#ifndef YD9_CTAS
+#define YD9_CTAS 3  // resident CTAs per SM the phase-1 kernel (PER = 9) is compiled for (80 registers, 24 warps: 37.6 -> 33.2 ms; 4: 33.8)
+#endif
 // Register-resident decision kernel for tauMax <= 32 * PER: lane owns lags [lane PER, (lane + 1) PER), no shared memory.
 template <int PER>
-__global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* __restrict__ voice, const uint8_t* __restrict__ gate,
+__global__ void __launch_bounds__(256, (PER <= 9) ? YD9_CTAS : 2) k_yin_decide_reg(VPGeom g, const float* __restrict__ voice, const uint8_t* __restrict__ gate,
                                                         const float* __restrict__ P, const double* __restrict__ Ech, int nChunks,
                                                         int lagPad, int S, int* __restrict__ period, uint32_t* __restrict__ yflags,
                                                         int* __restrict__ list, int* __restrict__ listCount, int maxList,
                                                         int kLimit, int phase, int* __restrict__ pendList, int* __restrict__ pendCount,
                                                         int* __restrict__ tileFlag, int* __restrict__ tileList,
-                                                        int* __restrict__ tileCount, int tilesPerStream) {
+                                                        int* __restrict__ tileCount, int tilesPerStream, int rs) {
+    // rs = row stride of the warp's shared rows in floats (>= 32 PER, multiple of 4): lagPad, or less when only the lags
+    // below kLimit are staged (phase 1) -- the kernel waits on its staging copies, so resident warps are what it needs
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     // phase 2 runs over the list of frames phase 1 left pending (persistent warps); phases 0 / 1 over every frame
@@ -541,21 +546,21 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
     // copies for the aligned P rows), and each lane then reads its own lags from shared memory (stride PER floats, PER
     // odd: conflict-free).
     extern __shared__ float ydsm[];
-    float* sb = ydsm + (size_t)warp * 6 * lagPad;  // rows 0..3: P chunks 3f..3f+3; row 4: x[q + L + k]; row 5: x[q + k]
+    float* sb = ydsm + (size_t)warp * 6 * rs;  // rows 0..3: P chunks 3f..3f+3; row 4: x[q + L + k]; row 5: x[q + k]
     {
         const float4* src = reinterpret_cast<const float4*>(P + ((size_t)s * nChunks + (size_t)3 * f) * (size_t)lagPad);
         float4* dst = reinterpret_cast<float4*>(sb);
         if (!partial) {
-            for (int j = lane; j < lagPad; j += 32) __pipeline_memcpy_async(dst + j, src + j, 16);  // 4 rows x lagPad / 4
+            for (int j = lane; j < lagPad; j += 32) __pipeline_memcpy_async(dst + j, src + j, 16);  // 4 rows x lagPad / 4 (rs == lagPad)
         } else {
-            const int q4 = (kEnd + 3) >> 2, r4 = lagPad >> 2;  // 16-byte pieces per row that hold lags < kEnd
-            for (int j = lane; j < 4 * q4; j += 32) {
+            const int q4 = (kEnd + 3) >> 2, r4 = lagPad >> 2, d4 = rs >> 2;  // 16-byte pieces per row that hold lags < kEnd
+            for (int j = lane; j < 4 * q4; j += 32) {  // (the division is cheaper than it looks: two forms without it measured 37 ms against 31)
                 const int row = j / q4, col = j - row * q4;
-                __pipeline_memcpy_async(dst + row * r4 + col, src + row * r4 + col, 16);
+                __pipeline_memcpy_async(dst + row * d4 + col, src + row * r4 + col, 16);
             }
         }
-        float* sh = sb + 4 * lagPad;
-        float* sl = sb + 5 * lagPad;
+        float* sh = sb + 4 * rs;
+        float* sl = sb + 5 * rs;
         if (inside) {
             const float* ph = v.x + tq + L;
             const float* pl = v.x + tq;
@@ -578,12 +583,12 @@ __global__ void __launch_bounds__(256) k_yin_decide_reg(VPGeom g, const float* _
         const int k = kA + j;
         double dl = 0.0;
         if (k < kEnd) {
-            const double h = (double)sb[4 * lagPad + k], l = (double)sb[5 * lagPad + k];
+            const double h = (double)sb[4 * rs + k], l = (double)sb[5 * rs + k];
             dl = h * h - l * l;
         }
         en[j] = dl;  // delta for now
         locDelta += dl;
-        dn[j] = ((double)P0[j] + (double)P0[lagPad + j]) + ((double)P0[2 * lagPad + j] + (double)P0[3 * lagPad + j]);
+        dn[j] = ((double)P0[j] + (double)P0[rs + j]) + ((double)P0[2 * rs + j] + (double)P0[3 * rs + j]);
     }
     double inc = locDelta;
 #pragma unroll
@@ -751,13 +756,14 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
     const long long tot = (long long)S * g.nFramesP;
     if (g.tauMax <= 32 * 15) {
         const size_t smemReg = (size_t)8 * 6 * lagPad * sizeof(float);
+        const int rs9 = std::min(lagPad, 32 * 9);  // phase 1: 9 lags per lane, rows of 288 floats instead of lagPad
         cudaFuncSetAttribute(k_yin_decide_reg<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (phase == 1 && kLimit <= 32 * 9) {
             // phase 1 reads lags < kLimit only: 9 lags per lane (odd: conflict-free) instead of 15 -> 0.6 x the instructions
             cudaFuncSetAttribute(k_yin_decide_reg<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            VP_LAUNCH(k_yin_decide_reg<9><<<(unsigned)((tot + 7) / 8), 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
-                                                                           recheckList, recheckCount, maxList, kLimit, phase, pendList, pendCount,
-                                                                           tileFlag, tileList, tileCount, vp_yin_corr_tiles(g)));
+            VP_LAUNCH(k_yin_decide_reg<9><<<(unsigned)((tot + 7) / 8), 256, (size_t)8 * 6 * rs9 * sizeof(float), st>>>(
+                g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags, recheckList, recheckCount, maxList, kLimit, phase, pendList,
+                pendCount, tileFlag, tileList, tileCount, vp_yin_corr_tiles(g), rs9));
             return;
         }
         long long grid = (tot + 7) / 8;
@@ -769,7 +775,7 @@ void vp_launch_yin_decide(cudaStream_t st, const VPGeom& g, int S, const float* 
         }
         VP_LAUNCH(k_yin_decide_reg<15><<<(unsigned)grid, 256, smemReg, st>>>(g, voice, gate, P, Ech, nChunks, lagPad, S, period, yflags,
                                                              recheckList, recheckCount, maxList, kLimit, phase, pendList, pendCount,
-                                                             tileFlag, tileList, tileCount, vp_yin_corr_tiles(g)));
+                                                             tileFlag, tileList, tileCount, vp_yin_corr_tiles(g), lagPad));
         return;
     }
     const int tauPad = (g.tauMax + 3) & ~3;
@@ -1561,7 +1567,7 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
         meta.y = (int)min((long long)nSteps, (long long)g.n - myP);
         meta.z = (int)((long long)(s - s0) * (long long)g.pstride + myP);  // |.| < 2^31: checked by the launcher
         meta.w = 0;
-        if (nSteps == 0) { meta.x = 0; meta.y = 0; meta.z = 0; }
+        if (nSteps == 0 || meta.y < meta.x) { meta.x = 0; meta.y = 0; meta.z = 0; }  // empty range: hi == lo (the write-out tests i - lo < hi - lo unsigned)
         *reinterpret_cast<int4*>(&tout[warp][lane][32]) = meta;
     }
     const double gp = (double)g.gainPitchF;
@@ -1572,13 +1578,17 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
     // slab sl: row fr of the tile <- outE[frame f0+fr][32 sl .. 32 sl + 32) as asynchronous 16-byte copies (rows of outE are
     // L = 4 c floats: aligned; zero fill beyond the frame's steps) into one of two tiles: the next slab is in flight while
     // this one is filtered
+    // (the steps of the 8 frames whose rows this lane copies: fetched once, not once per slab -- the wait for these shuffles
+    // was 18 % of the kernel's stall samples)
+    int stepsOf[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) stepsOf[it] = __shfl_sync(0xffffffffu, nSteps, it * 4 + (lane >> 3));
     auto issue = [&](int sl, int buf) {
         const int i0 = sl * 32;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int idx = it * 32 + lane, fr = idx >> 3, q4 = (idx & 7) * 4;
-            const int steps = __shfl_sync(0xffffffffu, nSteps, fr);
-            const int valid = min(max(steps - (i0 + q4), 0), 4);
+            const int valid = min(max(stepsOf[it] - (i0 + q4), 0), 4);
             __pipeline_memcpy_async(&tin[warp][buf][fr][q4], outE + (valid ? (size_t)(f0 + fr) * L + i0 + q4 : 0), 16, 16 - 4 * valid);
         }
         __pipeline_commit();
@@ -1619,14 +1629,19 @@ __global__ void __launch_bounds__(32 * PI_WARPS, 8) k_pitch_iir(VPGeom g, VPTabl
             *reinterpret_cast<float4*>(&tout[warp][lane][q4]) = make_float4(yo[0], yo[1], yo[2], yo[3]);
         }
         __syncwarp();
-        for (int fr = 0; fr < 32; ++fr) {
-            const int4 meta = *reinterpret_cast<const int4*>(&tout[warp][fr][32]);  // {lo, hi, plane offset}: one broadcast load
+        {
             const int i = i0 + lane;
-            if (i >= meta.x && i < meta.y) {
-                float* o = outP + planeBase + meta.z + i;
-                const float val = tout[warp][fr][lane];
-                if (i < c || i >= 3 * c) atomicAdd(o, val);   // cross-fade chunks: two frames contribute
-                else *o = val;
+            float* const oLane = outP + planeBase + i;         // per slab; a row then only adds its 32-bit plane offset
+            const bool shared2 = i < c || i >= 3 * c;          // cross-fade chunks: two frames contribute
+#pragma unroll 4
+            for (int fr = 0; fr < 32; ++fr) {
+                const int4 meta = *reinterpret_cast<const int4*>(&tout[warp][fr][32]);  // {lo, hi, plane offset}: one broadcast load
+                if ((unsigned)(i - meta.x) < (unsigned)(meta.y - meta.x)) {             // lo <= i < hi (an empty range has hi = lo = 0)
+                    float* o = oLane + meta.z;
+                    const float val = tout[warp][fr][lane];
+                    if (shared2) atomicAdd(o, val);
+                    else *o = val;
+                }
             }
         }
         __syncwarp();

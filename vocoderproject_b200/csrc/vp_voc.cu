@@ -40,10 +40,17 @@ __global__ void __launch_bounds__(128) k_gate_partial(VPGeom g, const float* __r
         for (int k = 0; k < GU; ++k) {
             const int t = t0 + k * (int)blockDim.x;
             const double a = (double)av[k], c = (double)cv[k];
+            // the square of a float is exact in double, so fma(a, a, s) rounds exactly what s + a * a rounds: one FP64
+            // instruction per sample and signal instead of two, same sums, same order (zeros beyond the block add nothing)
+#ifndef GATE_MULADD
+            sv = fma(a, a, sv);
+            ss = fma(c, c, ss);
+            if (t >= tail0) { tv = fma(a, a, tv); ts = fma(c, c, ts); }
+#else
             const double a2 = a * a, c2 = c * c;
-            sv += a2;   // zeros beyond the block add nothing: same sums, same order
-            ss += c2;
+            sv += a2; ss += c2;
             if (t >= tail0) { tv += a2; ts += c2; }
+#endif
         }
     }
     sv = vp_warp_sum(sv); ss = vp_warp_sum(ss); tv = vp_warp_sum(tv); ts = vp_warp_sum(ts);
