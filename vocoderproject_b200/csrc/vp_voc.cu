@@ -249,14 +249,13 @@ __device__ __forceinline__ void ac_task4(const double* __restrict__ xw, int n0, 
 }
 
 // ---------------------------------------------------------------------------
-// v2 (default): one WARP per frame, warps stream over batches of AB consecutive frames of one stream. The raw samples
-// of a batch (span (AB-1) hop + wlen, shared by its frames) are loaded once, coalesced, as floats; each frame then
-// builds its windowed FP64 copies from shared memory (no global latency, no integer division in the staging loop) and
-// runs lane = (segment of 8) x (lag group of 4: voice lags 0-13, 14-27, 28-41, side-chain lags 0-13) with the same
-// register-window task as above. Only warp-level synchronisation.
+// v2 (default): one WARP per frame; a warp walks AV_BATCH consecutive frames of one stream. Each frame's raw samples are
+// loaded coalesced in predicated batches, windowed into two FP64 copies in shared memory (voice, side-chain), and the warp
+// runs lane = (segment of 8) x (lag group of 4: voice lags 0-13, side-chain lags 0-13, voice lags 14-27, 27-40) with the
+// same register-window task as above. Only warp-level synchronisation.
 // ---------------------------------------------------------------------------
 #ifndef AV_WARPS
-#define AV_WARPS 10  // 10 x 10.3 KB + window: two CTAs per SM = 20 warps (registers capped at 102 by the launch bounds)
+#define AV_WARPS 10  // 10 x 10.3 KB + window: two CTAs per SM = 20 warps (registers capped at 96 by the launch bounds)
 #endif
 #define AV_BATCH 32  // consecutive frames per warp (cache locality of the 4x overlapping frame reads)
 #ifndef AV_STAGE_UNROLL
