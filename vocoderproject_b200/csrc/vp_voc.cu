@@ -262,6 +262,9 @@ __device__ __forceinline__ void ac_task4(const double* __restrict__ xw, int n0, 
 #define AV_STAGE_UNROLL 9  // raw samples per signal and lane loaded at once, predicated batches (a 556-sample frame at 48 kHz = 2 x 9 x 32)
 #endif
 constexpr int kStageUnroll = AV_STAGE_UNROLL;
+#ifndef AV_TREDUCE
+#define AV_TREDUCE 1  // transposed reduction over the segments (0: butterfly on every accumulator)
+#endif
 #ifndef AV_V4
 #define AV_V4 0  // 1: 128-bit shared loads in the lag sums (ac_task4, half the load instructions). Measured [B200]: 129.7 ms against 128.2 for the 64-bit form -- the loop is not bound by its load issue
 #endif
@@ -382,6 +385,41 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
 #else
         ac_task<AC_R>(sig, seg * segLen, segLen, m0, acc);
 #endif
+        double* rowV = rV + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordV);
+        double* rowS = rS + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordS);
+#if AV_TREDUCE
+        // Sum over the 8 segments, transposed: at each of the three exchange steps a lane keeps half of its values and trades
+        // the other half with its partner, so the 14 sums cost 13 exchanges (26 shuffles) instead of 42 (84) -- a shuffle
+        // holds the scheduler like a shared-memory load does. Same pairs added at every step as in the butterfly
+        // ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7)): bit-identical sums. Afterwards lane (b2 b1 b0) of a group
+        // holds the sums of lags m0 + 7 b0 + 4 b1 + 2 b2 + {0, 1} (index 7 of a half is padding).
+        {
+            static_assert(AC_R == 14, "the exchange pattern below is written for 14 lags per group");
+            const bool b0 = (seg & 1) != 0, b1 = (seg & 2) != 0, b2 = (seg & 4) != 0;
+            double t7[8];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const double keep = b0 ? acc[j + 7] : acc[j], send = b0 ? acc[j] : acc[j + 7];
+                t7[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            t7[7] = 0.0;
+            double t4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double keep = b1 ? t7[j + 4] : t7[j], send = b1 ? t7[j] : t7[j + 4];
+                t4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            double* r = isSynth ? rowS : rowV;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double keep = b2 ? t4[j + 2] : t4[j], send = b2 ? t4[j] : t4[j + 2];
+                const double sum = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                const int li = (b1 ? 4 : 0) + (b2 ? 2 : 0) + j;
+                const int m = m0 + (b0 ? 7 : 0) + li;
+                if (li < 7 && m <= order) r[m] = sum;  // raw sum; the Levinson kernel applies the 1/wlen of LPC.cpp:93-96
+            }
+        }
+#else
 #pragma unroll
         for (int j = 0; j < AC_R; ++j) {
             double a = acc[j];
@@ -390,8 +428,6 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
             a += __shfl_xor_sync(0xffffffffu, a, 4);
             acc[j] = a;
         }
-        double* rowV = rV + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordV);
-        double* rowS = rS + ((size_t)s * g.nFramesV + k) * (size_t)vp_rowlen(g.ordS);
         if (seg == 0) {
             double* r = isSynth ? rowS : rowV;
 #pragma unroll
@@ -400,6 +436,7 @@ __global__ void __launch_bounds__(32 * AV_WARPS, 2) k_voc_autocorr2(VPGeom g, VP
                 if (m <= order) r[m] = acc[j];  // raw sum; the Levinson kernel applies the 1/wlen of LPC.cpp:93-96
             }
         }
+#endif
         // the frame's last `order` windowed samples, appended to its row (coalesced)
         for (int t = lane; t < g.ordV; t += 32) rowV[g.ordV + 1 + t] = (wlen - g.ordV + t >= 0) ? xw[wlen - g.ordV + t] : 0.0;
         for (int t = lane; t < g.ordS; t += 32) rowS[g.ordS + 1 + t] = (wlen - g.ordS + t >= 0) ? sw[wlen - g.ordS + t] : 0.0;
