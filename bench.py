@@ -259,6 +259,80 @@ def link_ceiling(n_gpus):
     return best
 
 
+def live_link_probe(group, dev, h_src, h_dst, nbytes, reps=4):
+    """The same three rates measured on THIS box inside the run (tools/link_probe.cu's method through libcudart): every rank
+    copies `nbytes` of the pinned end-to-end buffers up / down / both ways on two streams, all ranks released together by a
+    barrier; rates are summed over the ranks. The committed probe logs describe the boxes they were taken on -- a 2-GPU box is
+    not the first two GPUs of an 8-GPU box. Returns None when the runtime library cannot be loaded or a call fails."""
+    try:
+        rt = None
+        for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                rt = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if rt is None:
+            return None
+        vpp, sz = C.c_void_p, C.c_size_t
+        rt.cudaMalloc.argtypes = [C.POINTER(vpp), sz]
+        rt.cudaFree.argtypes = [vpp]
+        rt.cudaStreamCreateWithFlags.argtypes = [C.POINTER(vpp), C.c_uint]
+        rt.cudaStreamDestroy.argtypes = [vpp]
+        rt.cudaEventCreate.argtypes = [C.POINTER(vpp)]
+        rt.cudaEventDestroy.argtypes = [vpp]
+        rt.cudaEventRecord.argtypes = [vpp, vpp]
+        rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), vpp, vpp]
+        rt.cudaMemcpyAsync.argtypes = [vpp, vpp, sz, C.c_int, vpp]
+        rt.cudaStreamSynchronize.argtypes = [vpp]
+
+        def ok(rc):
+            if rc != 0:
+                raise RuntimeError("cudart call failed: %d" % rc)
+
+        ok(rt.cudaSetDevice(C.c_int(dev)))
+        d_in, d_out, s_a, s_b = vpp(), vpp(), vpp(), vpp()
+        ok(rt.cudaMalloc(C.byref(d_in), nbytes))
+        ok(rt.cudaMalloc(C.byref(d_out), nbytes))
+        ok(rt.cudaStreamCreateWithFlags(C.byref(s_a), 1))
+        ok(rt.cudaStreamCreateWithFlags(C.byref(s_b), 1))
+        ev = [vpp() for _ in range(4)]
+        for e_ in ev:
+            ok(rt.cudaEventCreate(C.byref(e_)))
+
+        def run(up, down):
+            def issue():
+                if up:
+                    ok(rt.cudaMemcpyAsync(d_in, vpp(h_src), nbytes, 1, s_a))
+                if down:
+                    ok(rt.cudaMemcpyAsync(vpp(h_dst), d_out, nbytes, 2, s_b))
+            issue()
+            ok(rt.cudaStreamSynchronize(s_a)); ok(rt.cudaStreamSynchronize(s_b))
+            group.barrier()
+            ok(rt.cudaEventRecord(ev[0], s_a)); ok(rt.cudaEventRecord(ev[2], s_b))
+            for _ in range(reps):
+                issue()
+            ok(rt.cudaEventRecord(ev[1], s_a)); ok(rt.cudaEventRecord(ev[3], s_b))
+            ok(rt.cudaStreamSynchronize(s_a)); ok(rt.cudaStreamSynchronize(s_b))
+            rate = 0.0
+            for on, e0, e1 in ((up, ev[0], ev[1]), (down, ev[2], ev[3])):
+                if on:
+                    ms = C.c_float()
+                    ok(rt.cudaEventElapsedTime(C.byref(ms), e0, e1))
+                    rate += reps * nbytes / (ms.value * 1e-3) / 1e9
+            return group.sum(rate)
+
+        out = {"h2d": run(True, False), "d2h": run(False, True), "duplex": run(True, True), "file": None, "live_gib": nbytes / 2.0**30}
+        for e_ in ev:
+            rt.cudaEventDestroy(e_)
+        rt.cudaStreamDestroy(s_a); rt.cudaStreamDestroy(s_b)
+        rt.cudaFree(d_in); rt.cudaFree(d_out)
+        return out
+    except Exception as ex:  # the probe must never cost the run its result
+        sys.stderr.write("live link probe failed: %r\n" % (ex,))
+        return None
+
+
 def link_bound(link, h2d_bytes, d2h_bytes):
     """Time (s) the host link needs at least for a step's copies: each direction at its rate when it runs alone, and both
     together at the total rate measured with both directions busy (the host's memory system is shared: with 8 GPUs the
@@ -423,20 +497,23 @@ def run_engine(args, wl, group):
         if parity is not None:  # the host path must return what the device-resident path left in HBM, bit for bit
             same = all(np.array_equal(ho.array[s_], dev_rows[s_]) for s_ in picks if s_ < Se)
             parity["e2e_rows_equal_device_rows"] = bool(group.min(1.0 if same else 0.0) > 0.5)
-        link = link_ceiling(group.world)
+        e2e_checksum = float(np.abs(ho.array[:, ::4097]).sum())
+        # the host link's rates on this box, now (fallback: the committed probe log for this GPU count)
+        link = live_link_probe(group, dev, hv.ptr, ho.ptr, min(1 << 30, nb_e)) or link_ceiling(group.world)
         link_info = None
         if link:
             lb = link_bound(link, 2.0 * nb_e * group.world, 1.0 * nb_e * group.world)
             link_info = {"h2d_alone_gbs": link["h2d"], "d2h_alone_gbs": link["d2h"], "duplex_total_gbs": link["duplex"], "lower_bound_ms": 1e3 * lb,
                          "achieved_gbs": 3.0 * nb_e * group.world / (e_t / args.steps) / 1e9,
                          "model": "max(h2d bytes / h2d-alone rate, d2h bytes / d2h-alone rate, all bytes / both-directions total rate)",
-                         "source": os.path.relpath(link["file"], ROOT) + ": pinned 1-D copies, %d GPU(s) copying at once" % group.world}
+                         "source": (os.path.relpath(link["file"], ROOT) + ": pinned 1-D copies, %d GPU(s) copying at once" % group.world) if link.get("file")
+                                   else "measured in this run (tools/link_probe.cu's method): pinned 1-D copies of %.2f GiB, %d GPU(s) copying at once" % (link["live_gib"], group.world)}
         e2e = {"value": e_val, "unit": "audio-s/s", "h2d_bytes_per_step": 2 * nb_e * group.world, "d2h_bytes_per_step": nb_e * group.world,
                "streams_per_gpu": Se, "numa": numa, "link": link_info,
                "link_frac": (link_info["lower_bound_ms"] / (1e3 * e_t / args.steps)) if link_info else None,
                "ms_per_step": 1e3 * e_t / args.steps, "timer": "host wall clock around vp_engine_process_host, max over ranks",
                "note": "voice + side-chain ch0 uploaded (the path reads ch0 only, VocoderProcess.cpp:211,218); one output channel "
-                       "returned (L == R while gainSynth <= -59 dB)", "checksum": float(np.abs(ho.array[:, ::4097]).sum())}
+                       "returned (L == R while gainSynth <= -59 dB)", "checksum": e2e_checksum}
         if not args.no_pcm16:
             # the same batch as 16-bit PCM across the link (vp_engine_process_host_pcm16): the float rows are quantised in
             # place into the first half of their own pinned buffers (row s of the int16 view ends before row s of the floats)
