@@ -263,9 +263,19 @@ def live_link_probe(group, dev, h_src, h_dst, nbytes, reps=4):
     """The same three rates measured on THIS box inside the run (tools/link_probe.cu's method through libcudart): every rank
     copies `nbytes` of the pinned end-to-end buffers up / down / both ways on two streams, all ranks released together by a
     barrier; rates are summed over the ranks. The committed probe logs describe the boxes they were taken on -- a 2-GPU box is
-    not the first two GPUs of an 8-GPU box. Returns None when the runtime library cannot be loaded or a call fails."""
+    not the first two GPUs of an 8-GPU box. Returns None when the runtime library cannot be loaded or a call fails on any
+    rank; every rank makes the same collective calls whatever happens locally."""
+    vpp, sz = C.c_void_p, C.c_size_t
+    rt = None
+    d_in, d_out, s_a, s_b = vpp(), vpp(), vpp(), vpp()
+    ev = [vpp() for _ in range(4)]
+
+    def ok(rc):
+        if rc != 0:
+            raise RuntimeError("cudart call failed: %d" % rc)
+
+    good = True
     try:
-        rt = None
         for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
             try:
                 rt = C.CDLL(name)
@@ -273,8 +283,7 @@ def live_link_probe(group, dev, h_src, h_dst, nbytes, reps=4):
             except OSError:
                 continue
         if rt is None:
-            return None
-        vpp, sz = C.c_void_p, C.c_size_t
+            raise RuntimeError("libcudart not found")
         rt.cudaMalloc.argtypes = [C.POINTER(vpp), sz]
         rt.cudaFree.argtypes = [vpp]
         rt.cudaStreamCreateWithFlags.argtypes = [C.POINTER(vpp), C.c_uint]
@@ -285,52 +294,68 @@ def live_link_probe(group, dev, h_src, h_dst, nbytes, reps=4):
         rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), vpp, vpp]
         rt.cudaMemcpyAsync.argtypes = [vpp, vpp, sz, C.c_int, vpp]
         rt.cudaStreamSynchronize.argtypes = [vpp]
-
-        def ok(rc):
-            if rc != 0:
-                raise RuntimeError("cudart call failed: %d" % rc)
-
         ok(rt.cudaSetDevice(C.c_int(dev)))
-        d_in, d_out, s_a, s_b = vpp(), vpp(), vpp(), vpp()
         ok(rt.cudaMalloc(C.byref(d_in), nbytes))
         ok(rt.cudaMalloc(C.byref(d_out), nbytes))
         ok(rt.cudaStreamCreateWithFlags(C.byref(s_a), 1))
         ok(rt.cudaStreamCreateWithFlags(C.byref(s_b), 1))
-        ev = [vpp() for _ in range(4)]
         for e_ in ev:
             ok(rt.cudaEventCreate(C.byref(e_)))
+    except Exception as ex:
+        sys.stderr.write("live link probe: set-up failed: %r\n" % (ex,))
+        good = False
+    good = group.min(1.0 if good else 0.0) > 0.5   # all ranks or none
 
-        def run(up, down):
-            def issue():
-                if up:
-                    ok(rt.cudaMemcpyAsync(d_in, vpp(h_src), nbytes, 1, s_a))
-                if down:
-                    ok(rt.cudaMemcpyAsync(vpp(h_dst), d_out, nbytes, 2, s_b))
-            issue()
-            ok(rt.cudaStreamSynchronize(s_a)); ok(rt.cudaStreamSynchronize(s_b))
+    def issue(up, down):
+        if up:
+            ok(rt.cudaMemcpyAsync(d_in, vpp(h_src), nbytes, 1, s_a))
+        if down:
+            ok(rt.cudaMemcpyAsync(vpp(h_dst), d_out, nbytes, 2, s_b))
+
+    out = {"file": None, "live_gib": nbytes / 2.0**30}
+    if good:
+        for key, up, down in (("h2d", True, False), ("d2h", False, True), ("duplex", True, True)):
+            rate, failed = 0.0, False
+            try:
+                issue(up, down)
+                ok(rt.cudaStreamSynchronize(s_a)); ok(rt.cudaStreamSynchronize(s_b))
+            except Exception:
+                failed = True
             group.barrier()
-            ok(rt.cudaEventRecord(ev[0], s_a)); ok(rt.cudaEventRecord(ev[2], s_b))
-            for _ in range(reps):
-                issue()
-            ok(rt.cudaEventRecord(ev[1], s_a)); ok(rt.cudaEventRecord(ev[3], s_b))
-            ok(rt.cudaStreamSynchronize(s_a)); ok(rt.cudaStreamSynchronize(s_b))
-            rate = 0.0
-            for on, e0, e1 in ((up, ev[0], ev[1]), (down, ev[2], ev[3])):
-                if on:
-                    ms = C.c_float()
-                    ok(rt.cudaEventElapsedTime(C.byref(ms), e0, e1))
-                    rate += reps * nbytes / (ms.value * 1e-3) / 1e9
-            return group.sum(rate)
-
-        out = {"h2d": run(True, False), "d2h": run(False, True), "duplex": run(True, True), "file": None, "live_gib": nbytes / 2.0**30}
-        for e_ in ev:
-            rt.cudaEventDestroy(e_)
-        rt.cudaStreamDestroy(s_a); rt.cudaStreamDestroy(s_b)
-        rt.cudaFree(d_in); rt.cudaFree(d_out)
-        return out
-    except Exception as ex:  # the probe must never cost the run its result
-        sys.stderr.write("live link probe failed: %r\n" % (ex,))
-        return None
+            try:
+                if not failed:
+                    ok(rt.cudaEventRecord(ev[0], s_a)); ok(rt.cudaEventRecord(ev[2], s_b))
+                    for _ in range(reps):
+                        issue(up, down)
+                    ok(rt.cudaEventRecord(ev[1], s_a)); ok(rt.cudaEventRecord(ev[3], s_b))
+                    ok(rt.cudaStreamSynchronize(s_a)); ok(rt.cudaStreamSynchronize(s_b))
+                    for on, e0, e1 in ((up, ev[0], ev[1]), (down, ev[2], ev[3])):
+                        if on:
+                            ms = C.c_float()
+                            ok(rt.cudaEventElapsedTime(C.byref(ms), e0, e1))
+                            rate += reps * nbytes / (ms.value * 1e-3) / 1e9
+            except Exception as ex:
+                sys.stderr.write("live link probe: %s failed: %r\n" % (key, ex))
+                failed = True
+            out[key] = group.sum(rate)
+            if group.max(1.0 if failed else 0.0) > 0.5:
+                good = False
+    if rt is not None:
+        try:
+            for e_ in ev:
+                if e_.value:
+                    rt.cudaEventDestroy(e_)
+            if s_a.value:
+                rt.cudaStreamDestroy(s_a)
+            if s_b.value:
+                rt.cudaStreamDestroy(s_b)
+            if d_in.value:
+                rt.cudaFree(d_in)
+            if d_out.value:
+                rt.cudaFree(d_out)
+        except Exception:
+            pass
+    return out if good and all(out.get(k_, 0) > 0 for k_ in ("h2d", "d2h", "duplex")) else None
 
 
 def link_bound(link, h2d_bytes, d2h_bytes):

@@ -51,8 +51,11 @@ np.save(os.path.join(%(tmp)r, "shard%%d.npy" %% g.rank), np.stack(outs))
 g.barrier()
 secs = 1.0 + g.rank  # rank 1 is the slow one
 val, t, tot = aggregate_throughput(g, (hi - lo) * n / fs, secs)
+# bench.py's in-run host-link probe without a GPU: every rank fails its set-up, all agree (one collective) and return None
+import bench
+probe = bench.live_link_probe(g, 0, 0, 0, 1 << 20)
 if g.rank == 0:
-    print(json.dumps({"value": val, "t": t, "total": tot, "world": g.world, "range": [lo, hi]}))
+    print(json.dumps({"value": val, "t": t, "total": tot, "world": g.world, "range": [lo, hi], "probe": probe}))
 g.close()
 """
 
@@ -76,7 +79,7 @@ def test_two_rank_gloo_sharding(tmp_path, vp, oracle):
         assert p.returncode == 0, se.decode()[-2000:]
     line = json.loads(outs[0][0].decode().strip().splitlines()[-1])
     S, fs, n = 5, 44100.0, 16 * 1024
-    assert line["world"] == 2 and line["range"] == [0, 2]
+    assert line["world"] == 2 and line["range"] == [0, 2] and line["probe"] is None
     assert line["t"] == 2.0  # max over ranks
     assert abs(line["total"] - S * n / fs) < 1e-9 and abs(line["value"] - S * n / fs / 2.0) < 1e-9
     got = np.concatenate([np.load(tmp_path / "shard0.npy"), np.load(tmp_path / "shard1.npy")])
