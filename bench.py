@@ -385,14 +385,20 @@ def cpu_run(kind_pref, fs, B, voice, sl, params_kw, threads):
 
 
 def gen_host_inputs(vp, fs, first, S, n, threads):
-    """vp_synth_host over `threads` Python threads (ctypes releases the GIL)."""
+    """vp_synth_host over `threads` Python threads (ctypes releases the GIL). vp = None: the stand-alone generator
+    tools/_build/libvp_inputgen.so (same definitions, no CUDA, no product library in the process)."""
     voice = np.zeros((S, n), np.float32)
     sl = np.zeros((S, n), np.float32)
-    lib = vp.load_library()
+    if vp is None:
+        fn = C.CDLL(os.path.join(ROOT, "tools", "_build", "libvp_inputgen.so")).vpgen_synth_host
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    else:
+        fn = vp.load_library().vp_synth_host
 
     def work(t):
         for s in range(t, S, threads):
-            lib.vp_synth_host(float(fs), 0, first + s, 1, n, n, voice[s].ctypes.data, sl[s].ctypes.data, None)
+            fn(float(fs), 0, first + s, 1, n, n, voice[s].ctypes.data, sl[s].ctypes.data, None)
     ths = [threading.Thread(target=work, args=(t,)) for t in range(min(threads, S))]
     [t.start() for t in ths]
     [t.join() for t in ths]
@@ -403,7 +409,11 @@ def run_reference(args, wl, group):
     """--impl reference: the reference's own CPU implementation on the host cores, rank 0 only."""
     if group.rank != 0:
         return
-    import vocoderproject_b200 as vp
+    # inputs from the stand-alone generator: nothing of the product is loaded into this process (built by
+    # __graft_entry__.build(); if it is missing, the product's own vp_synth_host -- same definitions -- generates them)
+    vp = None
+    if not os.path.exists(os.path.join(ROOT, "tools", "_build", "libvp_inputgen.so")):
+        import vocoderproject_b200 as vp
     fs, B = wl["fs"], wl["B"]
     n = int(fs * wl["seconds"]) // B * B
     cores = host_cores()

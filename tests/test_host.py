@@ -88,3 +88,22 @@ def test_cpp_host_block_by_block_equals_python_batch(vp, host, K):
     assert j["latency_samples"] == 1024 and j["kernel_launches"] > 0
     assert j["crc_outL"] == "%08x" % zlib.crc32(np.ascontiguousarray(outL).tobytes())
     assert j["crc_outR"] == "%08x" % zlib.crc32(np.ascontiguousarray(outR).tobytes())
+
+
+def test_standalone_input_generator_equals_the_engines(vp):
+    """tools/inputgen.cpp (what bench.py's reference arm loads instead of the product library) and vp_synth_host are one
+    definition built twice: bit-identical inputs, all three flavours, two sample rates."""
+    import ctypes as C
+    import __graft_entry__ as ge
+    lib = C.CDLL(ge.build_inputgen())
+    fn = lib.vpgen_synth_host
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = 20000
+    for fs in (44100.0, 48000.0):
+        for flavour in (0, 1, 2):
+            v, l, r = vp.synth_host(fs, 3, n, flavour=flavour, first_stream=5)
+            gv, gl, gr = (np.zeros((3, n), np.float32) for _ in range(3))
+            assert fn(fs, flavour, 5, 3, n, n, gv.ctypes.data, gl.ctypes.data, gr.ctypes.data) == 0
+            assert np.array_equal(v, gv) and np.array_equal(l, gl) and np.array_equal(r, gr)
+    assert fn(48000.0, 0, 0, 0, n, n, gv.ctypes.data, None, None) != 0   # bad arguments are refused

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvp_engine.so")
 SOURCES = ["vp_engine.cu", "vp_voc.cu", "vp_pitch.cu", "vp_misc.cu"]
-HEADERS = ["vp_common.cuh", "vp_synth.h", os.path.join("..", "..", "include", "vp_engine.h")]
+HEADERS = ["vp_common.cuh", "vp_synth.h", "vp_synth_host.hpp", os.path.join("..", "..", "include", "vp_engine.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
